@@ -1,0 +1,255 @@
+/*
+ * pinc_b200.h — C-ABI of libpinc_b200.so: the B200 (sm_100a) implementation of PINC's
+ * per-timestep particle-in-cell loop behind PINC's own C entry points.
+ *
+ * Every function below with a PINC name has the reference's signature and argument
+ * meaning (cited as /root/reference/src/<file>:<line> of the declaration it replaces),
+ * so a PINC build links this library in place of the corresponding objects
+ * (see INTEGRATION.md).  Struct layouts restate core.h / multigrid.h byte for byte.
+ *
+ * Memory model.  The host structs stay owned by the caller (plain malloc, exactly as
+ * gAlloc/pAlloc/gAllocMpi/gCreateNeighborhood/mgAllocSolver of the reference produce
+ * them).  The first time a Grid* / Population* is seen it gets a device-resident
+ * mirror keyed by the host pointer and its host contents are uploaded.  After that all
+ * PINC-named functions work on the mirror and the large host arrays (grid->val,
+ * pop->pos, pop->vel) are STALE until pincSync*ToHost() is called; host code that
+ * writes them (initial conditions) calls pincSync*ToDevice().  The small host scalars
+ * the reference's driver reads (pop->iStop[], pop->kinEnergy[], pop->potEnergy[],
+ * mpiInfo->nEmigrants[], mpiInfo->nImmigrants[]) are always kept current.
+ *
+ * There is no CPU fallback: every entry point aborts through pincFatal() when no CUDA
+ * device is usable.
+ */
+#ifndef PINC_B200_H
+#define PINC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* hid_t of the HDF5 the host was built with (HDF5 >= 1.10: int64_t; 1.8: int). */
+#ifndef PINC_HID_T
+#define PINC_HID_T int64_t
+#endif
+typedef PINC_HID_T pinc_hid_t;
+
+/* ---------------------------------------------------------------------------------
+ * Data model (restates src/core.h:72-86, 112-138, 146-151, 261-277, 467 and
+ * src/grid.h:22-25, src/multigrid.h:27-57)
+ * ------------------------------------------------------------------------------- */
+typedef void (*funPtr)();                       /* core.h:467 */
+
+typedef enum { PERIODIC = 0x01, DIRICHLET = 0x02, NEUMANN = 0x03, NONE = 0x10 } bndType; /* core.h:146-151 */
+typedef enum { TOHALO = 0, FROMHALO = 1 } opDirection;                                  /* grid.h:22-25 */
+
+typedef struct {                                /* core.h:72-86 */
+	double *pos;            /* AoS: pos[3*i+d], local grid units */
+	double *vel;
+	long int *iStart;       /* nSpecies+1 */
+	long int *iStop;        /* nSpecies   */
+	long int *objVicinity;
+	long int *collisions;
+	double *charge;
+	double *mass;
+	double *kinEnergy;      /* nSpecies+1 */
+	double *potEnergy;      /* nSpecies+1 */
+	int nSpecies;
+	int nDims;
+	pinc_hid_t h5;
+} Population;
+
+typedef struct {                                /* core.h:112-138 */
+	int mpiRank;
+	int mpiSize;
+	int nDims;
+	int *subdomain;
+	int *nSubdomains;
+	int *nSubdomainsProd;
+	int *offset;
+	double *posToSubdomain;
+	int nSpecies;
+	int nNeighbors;
+	int neighborhoodCenter;
+	long int **migrants;
+	long int **migrantsDummy;
+	long int *nEmigrants;       /* [ne*nSpecies+s] */
+	long int *nEmigrantsAlloc;  /* [ne] */
+	long int *nImmigrants;
+	long int nImmigrantsAlloc;
+	double **emigrants;
+	double **emigrantsDummy;
+	double *immigrants;
+	double *thresholds;         /* 2*nDims: lower x,y,z then upper x,y,z */
+	void *send;                 /* MPI_Request* in the reference */
+	void *recv;
+} MpiInfo;
+
+typedef struct {                                /* core.h:261-277 */
+	double *val;
+	int rank;
+	int *size;
+	int *trueSize;
+	long int *sizeProd;
+	int *nGhostLayers;
+	double *sendSlice;
+	double *recvSlice;
+	double *bndSlice;
+	pinc_hid_t h5;
+	pinc_hid_t h5MemSpace;
+	pinc_hid_t h5FileSpace;
+	bndType *bnd;
+} Grid;
+
+typedef struct {                                /* multigrid.h:27-50 */
+	Grid **grids;
+	int nLevels;
+	int nMGCycles;
+	int nPreSmooth;
+	int nPostSmooth;
+	int nCoarseSolve;
+	void (*coarseSolv)(Grid *phi, const Grid *rho, const int nCycles, const MpiInfo *mpiInfo);
+	void (*postSmooth)(Grid *phi, const Grid *rho, const int nCycles, const MpiInfo *mpiInfo);
+	void (*preSmooth)(Grid *phi, const Grid *rho, const int nCycles, const MpiInfo *mpiInfo);
+	void (*restrictor)(const Grid *fine, Grid *coarse);
+	void (*prolongator)(Grid *fine, const Grid *coarse, const MpiInfo *mpiInfo);
+} Multigrid;
+
+typedef struct {                                /* multigrid.h:52-58 */
+	Grid *res;
+	Multigrid *mgRho;
+	Multigrid *mgPhi;
+	Multigrid *mgRes;
+	funPtr mgAlgo;
+} MultigridSolver;
+
+typedef struct Object Object;                   /* object.h: opaque here; puMove ignores it (quirk Q4) */
+
+/* ---------------------------------------------------------------------------------
+ * Particle path (src/pusher.h)
+ * ------------------------------------------------------------------------------- */
+void puMove(Population *pop, Object *obj);                                      /* pusher.h:24  (pusher.c:86)  */
+void puAcc3D1(Population *pop, Grid *E);                                        /* pusher.h:119 (pusher.c:147) */
+void puAcc3D1KE(Population *pop, Grid *E);                                      /* pusher.h:120 (pusher.c:178) */
+void puBoris3D1(Population *pop, Grid *E, const double *T, const double *S);    /* pusher.h:125 (pusher.c:394) */
+void puBoris3D1KE(Population *pop, Grid *E, const double *T, const double *S);  /* pusher.h:126 (pusher.c:433) */
+void puDistr3D1(const Population *pop, Grid *rho);                              /* pusher.h:163 (pusher.c:512) */
+void puExtractEmigrants3D(Population *pop, MpiInfo *mpiInfo);                   /* pusher.h:180 (pusher.c:782) */
+void puMigrate(Population *pop, MpiInfo *mpiInfo, Grid *grid);                  /* pusher.h:184 (pusher.c:1030) */
+int  puRankToNeighbor(MpiInfo *mpiInfo, int rank);                              /* pusher.h:186 (pusher.c:1214) */
+int  puNeighborToRank(MpiInfo *mpiInfo, int neighbor);                          /* pusher.h:187 (pusher.c:1194) */
+int  puNeighborToReciprocal(int neighbor, int nDims);                           /* pusher.h:188 (pusher.c:1181) */
+/* plain-argument form of puGet3DRotationParameters (pusher.c:485; the reference reads
+ * BExt/charge/mass from the ini dictionary, which stays host code) */
+void pincGet3DRotationParameters(int nSpecies, const double *BExt, const double *charge,
+                                 const double *mass, double *T, double *S);
+/* plain-argument form of the validator behind every puXxx_set (pusher.c:1047 puSanity);
+ * returns 0 if the configuration is acceptable, else an error code and a message. */
+int  pincPuSanity(const char *name, int nDims, const int *nGhostLayers, const double *thresholds,
+                  int dim, int order, char *errbuf, int errlen);
+
+/* ---------------------------------------------------------------------------------
+ * Grid path (src/grid.h)
+ * ------------------------------------------------------------------------------- */
+void getSlice(double *slice, const Grid *grid, int d, int offset);              /* grid.h:194 (grid.c:85)  */
+void setSlice(const double *slice, Grid *grid, int d, int offset);              /* grid.h:226 (grid.c:111) */
+void addSlice(const double *slice, Grid *grid, int d, int offset);              /* grid.h:239 (grid.c:137) */
+void gHaloOp(funPtr sliceOp, Grid *grid, const MpiInfo *mpiInfo, opDirection dir);             /* grid.h:156 (grid.c:340) */
+void gHaloOpDim(funPtr sliceOp, Grid *grid, const MpiInfo *mpiInfo, int d, opDirection dir);   /* grid.h:140 (grid.c:349) */
+void gFinDiff1st(const Grid *scalar, Grid *field);                              /* grid.h:316 (grid.c:226) */
+void gFinDiff2nd3D(Grid *result, const Grid *object);                           /* grid.h:325 (grid.c:296) */
+void gZero(Grid *grid);                                                         /* grid.h:247 (grid.c:699) */
+void gMul(Grid *grid, double num);                                              /* grid.h:275 (grid.c:668) */
+void gAdd(Grid *grid, double num);                                              /* grid.h:283 (grid.c:675) */
+void gSub(Grid *grid, double num);                                              /* grid.h:291 (grid.c:682) */
+void gSquare(Grid *grid);                                                       /* grid.h:299 (grid.c:689) */
+void gCopy(const Grid *original, Grid *copy);                                   /* grid.h:267 (grid.c:718) */
+void gAddTo(Grid *result, Grid *addition);                                      /* grid.h:367 (grid.c:783) */
+void gSubFrom(Grid *result, const Grid *subtraction);                           /* grid.h:378 (grid.c:793) */
+double gSumTruegrid(const Grid *grid);                                          /* grid.h:388 (grid.c:833) */
+long int gTotTruesize(const Grid *grid, const MpiInfo *mpiInfo);                /* grid.h:308 (grid.c:849) */
+void gNeutralizeGrid(Grid *grid, const MpiInfo *mpiInfo);                       /* grid.h:357 (grid.c:730) */
+void gBnd(Grid *grid, const MpiInfo *mpiInfo);                                  /* grid.h:402 (grid.c:992); PERIODIC only */
+void gPotEnergy(const Grid *rho, const Grid *phi, Population *pop);             /* grid.h:527 (grid.c:1276) */
+
+/* ---------------------------------------------------------------------------------
+ * Multigrid Poisson solver (src/multigrid.h)
+ * ------------------------------------------------------------------------------- */
+void mgSolve(const MultigridSolver *solver, const Grid *rho, const Grid *phi, const MpiInfo *mpiInfo); /* multigrid.h:95 (multigrid.c:403) */
+void mgSolveRaw(funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *mpiInfo); /* multigrid.c:1688 */
+void mgVRecursive(int level, int bottom, int top, Multigrid *mgRho, Multigrid *mgPhi,
+                  Multigrid *mgRes, const MpiInfo *mpiInfo);                    /* multigrid.c:1550 */
+void mgGS3D(Grid *phi, const Grid *rho, int nCycles, const MpiInfo *mpiInfo);  /* multigrid.c:683 */
+void mgHalfRestrict3D(const Grid *fine, Grid *coarse);                          /* multigrid.c:844 */
+void mgBilinProl3D(Grid *fine, const Grid *coarse, const MpiInfo *mpiInfo);     /* multigrid.c:1127 */
+void mgResidual(Grid *res, const Grid *rho, const Grid *phi, const MpiInfo *mpiInfo); /* multigrid.c:1385 */
+double mgSumTrueSquared(Grid *error, const MpiInfo *mpiInfo);                   /* multigrid.c:1471 */
+void mgSolver(void (**solve)(), MultigridSolver *(**solverAlloc)(), void (**solverFree)()); /* multigrid.c:392 */
+/* plain-argument form of mgAllocSolver/mgAlloc/mgAllocSubGrids (multigrid.c:128-382);
+ * the reference reads the five integers from [multigrid] of the ini file. */
+MultigridSolver *pincMgAllocSolver(Grid *rho, Grid *phi, int mgLevels, int mgCycles,
+                                   int nPreSmooth, int nPostSmooth, int nCoarseSolve);
+void mgFreeSolver(MultigridSolver *solver);                                     /* multigrid.h:94 (multigrid.c:384) */
+/* residual history of the most recent mgSolve on this rank: returns the V-cycle count and
+ * copies up to `cap` values of barRes (multigrid.c:1700-1704), one per V-cycle. */
+int pincMgLastHistory(double *barRes, int cap);
+
+/* ---------------------------------------------------------------------------------
+ * Host-struct constructors with plain arguments (restating gAlloc grid.c:413,
+ * gAllocMpi grid.c:502, gCreateNeighborhood grid.c:1029, pAlloc population.c:42) for
+ * hosts that do not link the reference's ini layer (tests, bench, other bindings).
+ * All arrays are zero-initialised (quirk Q5).
+ * ------------------------------------------------------------------------------- */
+Grid *pincGridAlloc(int nDims, const int *trueSize, const int *nGhostLayers /*2*nDims*/,
+                    int nValues, const int *bnd /*2*nDims, bndType*/);
+void  pincGridFree(Grid *grid);
+MpiInfo *pincMpiAlloc(int nDims, int nSpecies, const int *nSubdomains, const int *nGhostLayers,
+                      const int *trueSize, int mpiRank, int mpiSize);
+void  pincMpiFree(MpiInfo *mpiInfo);
+void  pincCreateNeighborhood(MpiInfo *mpiInfo, const Grid *grid, const long int *nEmigrantsAlloc,
+                             int nAllocEntries /*1, nDims or 3^nDims*/, const double *thresholds /*2*nDims*/);
+Population *pincPopAlloc(int nSpecies, int nDims, const long int *nAllocPerRank,
+                         const double *charge, const double *mass);
+void  pincPopFree(Population *pop);
+
+/* ---------------------------------------------------------------------------------
+ * Device context, coherence, transport, timing
+ * ------------------------------------------------------------------------------- */
+typedef struct PincCtx PincCtx;
+/* One context per rank.  In a PINC build there is one rank per process and the context
+ * is created implicitly on the device given by $PINC_B200_DEVICE / $LOCAL_RANK / 0. */
+PincCtx *pincCtxCreate(int device, int rank, int size);
+void pincCtxMakeCurrent(PincCtx *ctx);          /* binds ctx to the calling host thread */
+void pincCtxDestroy(PincCtx *ctx);
+/* transports for size>1: (a) ranks are host threads of this process (tests on one GPU);
+ * (b) ranks are processes, one GPU each, NCCL over NVLink. */
+void pincCommInitThreads(PincCtx **ctxs, int n);
+int  pincNcclUniqueId(char *out128);
+void pincCommInitNccl(PincCtx *ctx, const char *uniqueId128);
+
+void pincSyncGridToDevice(Grid *grid);
+void pincSyncGridToHost(Grid *grid);
+void pincSyncPopToDevice(Population *pop);
+void pincSyncPopToHost(Population *pop);
+void pincForget(void *hostStruct);              /* drop the mirror of a Grid*/ /*Population* */
+void pincDeviceSynchronize(void);
+/* fused step helpers (same arithmetic as the separate entry points, one pass over the particles):
+ * puAcc3D1KE immediately followed by puMove + puExtractEmigrants3D classification. */
+void pincAccMove3D1KE(Population *pop, Grid *E, MpiInfo *mpiInfo);
+
+/* CUDA-event timing on the context's stream (what bench.py brackets the step with) */
+void   pincTimerStart(void);
+double pincTimerStopMs(void);
+/* per-kernel-class accumulated device time since the last reset (names/ms), for roofline */
+void   pincProfEnable(int on);
+void   pincProfReset(void);
+int    pincProfGet(int idx, char *name, int namelen, double *ms, long int *launches, double *algBytes);
+long int pincLaunchCount(void);
+const char *pincVersion(void);
+int   pincLastError(char *buf, int len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,575 @@
+/*
+ * pinc_oracle.c — CPU restatement of PINC's per-timestep PIC loop (see pinc_oracle.h).
+ *
+ * TEST INFRASTRUCTURE ONLY: never on the product path.  Parity status: PINNED against the
+ * reference's known-answer vectors and against the reference's own sources compiled in
+ * place (oracle/_ref), see tests/test_oracle_*.py.
+ *
+ * Written from the algorithm, not from the text of the reference: loops run over explicit
+ * (j,k,l) node indices; the order of floating point operations inside every expression
+ * follows the cited reference line so results are bit-identical where the reference is
+ * deterministic.  Compile with -ffp-contract=off (the reference is built without FMA).
+ */
+#include "pinc_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define IDX(j,k,l,sx,sy) ((long)(j) + (long)(sx)*((long)(k) + (long)(sy)*(long)(l)))
+
+/* ------------------------------------------------------------------------------------------
+ * Particles
+ * ---------------------------------------------------------------------------------------- */
+
+/* src/pusher.c:86-119 (quirk Q4: the collision loop is dead code; what runs is pos += vel). */
+void orc_move(double *pos, const double *vel, int nSpecies, const long *iStart, const long *iStop){
+	for(int s=0;s<nSpecies;s++)
+		for(long p=3*iStart[s]; p<3*iStop[s]; p++) pos[p] += vel[p];
+}
+
+/* src/grid.c:668-673 */
+void orc_gmul(double *val, long n, double num){
+	for(long p=0;p<n;p++) val[p] *= num;
+}
+
+/* src/pusher.c:1089-1122: trilinear gather of the three field components. */
+static void interp3d1(double *dv, const double *pos, const double *E, long sx, long sy){
+	int j = (int)pos[0], k = (int)pos[1], l = (int)pos[2];
+	double x = pos[0]-j, y = pos[1]-k, z = pos[2]-l;
+	double xc = 1-x, yc = 1-y, zc = 1-z;
+	long p000 = 3*IDX(j,k,l,sx,sy);
+	long p100 = p000+3, p010 = p000+3*sx, p110 = p010+3;
+	long p001 = p000+3*sx*sy, p101 = p001+3, p011 = p001+3*sx, p111 = p011+3;
+	for(int v=0;v<3;v++)
+		dv[v] = zc*( yc*(xc*E[p000+v]+x*E[p100+v]) + y*(xc*E[p010+v]+x*E[p110+v]) )
+		      + z *( yc*(xc*E[p001+v]+x*E[p101+v]) + y*(xc*E[p011+v]+x*E[p111+v]) );
+}
+
+/* src/pusher.c:147-176 (kinEnergy==NULL) and :178-214 (with the mid-step energy).
+ * The whole E grid is rescaled by q/m before and m/q after each species (quirk Q2). */
+void orc_acc3d1(double *pos, double *vel, int nSpecies, const long *iStart, const long *iStop,
+                const double *charge, const double *mass, double *E, const int *size, double *kinEnergy){
+	long sx = size[0], sy = size[1], n = 3L*size[0]*size[1]*size[2];
+	for(int s=0;s<nSpecies;s++){
+		orc_gmul(E,n,charge[s]/mass[s]);
+		double acc = 0;
+		for(long p=3*iStart[s]; p<3*iStop[s]; p+=3){
+			double dv[3];
+			interp3d1(dv,&pos[p],E,sx,sy);
+			double v2 = 0;
+			for(int d=0;d<3;d++){
+				v2 += vel[p+d]*(vel[p+d]+dv[d]);
+				vel[p+d] += dv[d];
+			}
+			acc += v2;
+		}
+		if(kinEnergy){ kinEnergy[s] = acc; kinEnergy[s] *= 0.5*mass[s]; }
+		orc_gmul(E,n,mass[s]/charge[s]);
+	}
+}
+
+/* src/pusher.c:1233-1237 */
+static void add_cross(const double *a, const double *b, double *res){
+	res[0] +=  (a[1]*b[2]-a[2]*b[1]);
+	res[1] += -(a[0]*b[2]-a[2]*b[0]);
+	res[2] +=  (a[0]*b[1]-a[1]*b[0]);
+}
+
+/* src/pusher.c:394-483.  bugCompatible!=0 reproduces quirk Q3 (the rotation acts on
+ * particle 0's velocity); bugCompatible==0 is the textbook Boris rotation of particle p,
+ * which is what the product implements.  Both coincide when T=S=0 or for particle 0. */
+void orc_boris3d1(double *pos, double *vel, int nSpecies, const long *iStart, const long *iStop,
+                  const double *charge, const double *mass, double *E, const int *size,
+                  const double *T, const double *S, double *kinEnergy, int bugCompatible){
+	long sx = size[0], sy = size[1], n = 3L*size[0]*size[1]*size[2];
+	for(int s=0;s<nSpecies;s++){
+		orc_gmul(E,n,charge[s]/mass[s]);
+		double acc = 0;
+		for(long p=3*iStart[s]; p<3*iStop[s]; p+=3){
+			double dv[3], vPrime[3];
+			interp3d1(dv,&pos[p],E,sx,sy);
+			for(int d=0;d<3;d++) vel[p+d] += 0.5*dv[d];
+			double *v = bugCompatible ? vel : &vel[p];
+			memcpy(vPrime,v,sizeof vPrime);
+			add_cross(v,&T[3*s],vPrime);
+			add_cross(vPrime,&S[3*s],v);
+			double v2 = 0;
+			for(int d=0;d<3;d++) v2 += pow(vel[p+d],2);
+			acc += v2;
+			for(int d=0;d<3;d++) vel[p+d] += 0.5*dv[d];
+		}
+		if(kinEnergy){ kinEnergy[s] = acc; kinEnergy[s] *= 0.5*mass[s]; }
+		orc_gmul(E,n,mass[s]/charge[s]);
+	}
+}
+
+/* src/pusher.c:485-505 */
+void orc_rotation_parameters(int nSpecies, const double *BExt, const double *charge,
+                             const double *mass, double *T, double *S){
+	for(int s=0;s<nSpecies;s++){
+		double factor = 0.5*charge[s]/mass[s];
+		double denom = 1;
+		for(int p=0;p<3;p++){ T[3*s+p] = factor*BExt[p]; denom += pow(T[3*s+p],2); }
+		double mul = 2.0/denom;
+		for(int p=0;p<3;p++) S[3*s+p] = mul*T[3*s+p];
+	}
+}
+
+/* src/pusher.c:512-572.  gZero, then per species: rho *= 1/q, scatter raw weights, rho *= q (quirk Q1). */
+void orc_distr3d1(const double *pos, int nSpecies, const long *iStart, const long *iStop,
+                  const double *charge, double *rho, const int *size){
+	long sx = size[0], sy = size[1], n = (long)size[0]*size[1]*size[2];
+	for(long g=0;g<n;g++) rho[g] = 0;
+	for(int s=0;s<nSpecies;s++){
+		orc_gmul(rho,n,1.0/charge[s]);
+		for(long i=iStart[s]; i<iStop[s]; i++){
+			const double *r = &pos[3*i];
+			int j = (int)r[0], k = (int)r[1], l = (int)r[2];
+			double x = r[0]-j, y = r[1]-k, z = r[2]-l;
+			double xc = 1-x, yc = 1-y, zc = 1-z;
+			long p = IDX(j,k,l,sx,sy);
+			rho[p]            += xc*yc*zc;
+			rho[p+1]          += x *yc*zc;
+			rho[p+sx]         += xc*y *zc;
+			rho[p+sx+1]       += x *y *zc;
+			rho[p+sx*sy]      += xc*yc*z;
+			rho[p+sx*sy+1]    += x *yc*z;
+			rho[p+sx*sy+sx]   += xc*y *z;
+			rho[p+sx*sy+sx+1] += x *y *z;
+		}
+		orc_gmul(rho,n,charge[s]);
+	}
+}
+
+/* src/grid.c:1094-1099: upper thresholds are counted from the upper edge. */
+void orc_thresholds(const int *size, const double *thrIn, double *thrOut){
+	for(int d=0;d<3;d++){
+		thrOut[d] = thrIn[d];
+		thrOut[3+d] = (size[d]-1) - thrIn[3+d];
+	}
+}
+
+/* src/pusher.c:782-855: serial classify, pack into the neighbour's buffer, back-fill the hole
+ * with the species' last particle and re-examine the slot. */
+void orc_extract3d(double *pos, double *vel, int nSpecies, const long *iStart, long *iStop,
+                   const double *thr, double **emigrants, long *nEmigrants){
+	double *cursor[27];
+	for(int ne=0;ne<27;ne++) cursor[ne] = emigrants[ne];
+	for(int i=0;i<27*nSpecies;i++) nEmigrants[i] = 0;
+	for(int s=0;s<nSpecies;s++){
+		long i = iStart[s];
+		while(i<iStop[s]){
+			double x = pos[3*i], y = pos[3*i+1], z = pos[3*i+2];
+			int nx = -(x<thr[0]) + (x>=thr[3]);
+			int ny = -(y<thr[1]) + (y>=thr[4]);
+			int nz = -(z<thr[2]) + (z>=thr[5]);
+			int ne = 13 + nx + 3*ny + 9*nz;
+			if(ne==13){ i++; continue; }
+			double *c = cursor[ne];
+			c[0]=x; c[1]=y; c[2]=z; c[3]=vel[3*i]; c[4]=vel[3*i+1]; c[5]=vel[3*i+2];
+			cursor[ne] += 6;
+			nEmigrants[ne*nSpecies+s]++;
+			long last = iStop[s]-1;
+			for(int d=0;d<3;d++){ pos[3*i+d] = pos[3*last+d]; vel[3*i+d] = vel[3*last+d]; }
+			iStop[s]--;
+		}
+	}
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Topology (src/grid.c:166-171, src/pusher.c:1181-1231)
+ * ---------------------------------------------------------------------------------------- */
+static void rank_to_sub(const OrcTopo *t, int rank, int *sub){
+	for(int d=0;d<3;d++){ sub[d] = rank % t->nSub[d]; rank /= t->nSub[d]; }
+}
+static int sub_to_rank(const OrcTopo *t, const int *sub){
+	return sub[0] + t->nSub[0]*(sub[1] + t->nSub[1]*sub[2]);
+}
+int orc_neighbor_to_rank(const OrcTopo *t, int rank, int ne){
+	int sub[3], nb[3];
+	rank_to_sub(t,rank,sub);
+	for(int d=0;d<3;d++){
+		int n = (ne%3)-1; ne /= 3;
+		nb[d] = (sub[d]+n+t->nSub[d]) % t->nSub[d];
+	}
+	return sub_to_rank(t,nb);
+}
+int orc_neighbor_to_reciprocal(int ne){
+	int rec = 0, pw = 1;
+	for(int d=0;d<3;d++){ rec += (2-(ne%3))*pw; ne /= 3; pw *= 3; }
+	return rec;
+}
+int orc_rank_to_neighbor(const OrcTopo *t, int rank, int other){
+	int sub[3], ne = 0, pw = 1;
+	rank_to_sub(t,rank,sub);
+	for(int d=0;d<3;d++){
+		int n = other % t->nSub[d];
+		n = (n-sub[d]+1+t->nSub[d]) % t->nSub[d];
+		other /= t->nSub[d];
+		ne += n*pw; pw *= 3;
+	}
+	return ne;
+}
+
+/* src/pusher.c:914-1035.  Counts travel first (exchangeNMigrants), then the packed
+ * (x,y,z,vx,vy,vz) records; the receiver shifts positions by (n_d)*trueSize[d] where n is
+ * the direction the message came FROM (shiftImmigrants :941) and appends species by species
+ * at iStop[s] (importParticles :967).  Import order: ascending receiver-side neighbour index. */
+void orc_migrate(const OrcTopo *t, double **pos, double **vel, int nSpecies, long **iStop,
+                 double ***emigrants, long **nEmigrants, long **nImmigrants){
+	int R = t->nRanks;
+	for(int r=0;r<R;r++)
+		for(int ne=0;ne<27;ne++){
+			if(ne==13){ for(int s=0;s<nSpecies;s++) nImmigrants[r][13*nSpecies+s] = 0; continue; }
+			int src = orc_neighbor_to_rank(t,r,ne);
+			int rec = orc_neighbor_to_reciprocal(ne);     /* r is neighbour `rec` of src */
+			for(int s=0;s<nSpecies;s++) nImmigrants[r][ne*nSpecies+s] = nEmigrants[src][rec*nSpecies+s];
+		}
+	for(int r=0;r<R;r++)
+		for(int ne=0;ne<27;ne++){
+			if(ne==13) continue;
+			int src = orc_neighbor_to_rank(t,r,ne);
+			int rec = orc_neighbor_to_reciprocal(ne);
+			const double *msg = emigrants[src][rec];
+			double shift[3]; int q = ne;
+			for(int d=0;d<3;d++){ int n = q%3-1; q /= 3; shift[d] = n*t->trueSize[d]; }
+			for(int s=0;s<nSpecies;s++){
+				long cnt = nImmigrants[r][ne*nSpecies+s];
+				double *pp = &pos[r][3*iStop[r][s]], *vv = &vel[r][3*iStop[r][s]];
+				for(long i=0;i<cnt;i++){
+					for(int d=0;d<3;d++){ double v = msg[d]; v += shift[d]; pp[d] = v; }
+					for(int d=0;d<3;d++) vv[d] = msg[3+d];
+					msg += 6; pp += 3; vv += 3;
+				}
+				iStop[r][s] += cnt;
+			}
+		}
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Grid: halo exchange, reductions, finite differences
+ * ---------------------------------------------------------------------------------------- */
+
+/* A slice = every element whose coordinate along d equals `o` (all components, ghost rims
+ * included), in memory order (src/grid.c:72-147). */
+static void slice_get(double *buf, const double *val, const int *size, int nV, int d, int o){
+	long ext[3] = {size[0],size[1],size[2]};
+	long n = 0;
+	for(long l=0;l<ext[2];l++){ if(d==2 && l!=o) continue;
+	for(long k=0;k<ext[1];k++){ if(d==1 && k!=o) continue;
+	for(long j=0;j<ext[0];j++){ if(d==0 && j!=o) continue;
+		long g = nV*IDX(j,k,l,ext[0],ext[1]);
+		for(int c=0;c<nV;c++) buf[n++] = val[g+c];
+	}}}
+}
+static void slice_put(const double *buf, double *val, const int *size, int nV, int d, int o, int add){
+	long ext[3] = {size[0],size[1],size[2]};
+	long n = 0;
+	for(long l=0;l<ext[2];l++){ if(d==2 && l!=o) continue;
+	for(long k=0;k<ext[1];k++){ if(d==1 && k!=o) continue;
+	for(long j=0;j<ext[0];j++){ if(d==0 && j!=o) continue;
+		long g = nV*IDX(j,k,l,ext[0],ext[1]);
+		for(int c=0;c<nV;c++){ if(add) val[g+c] += buf[n++]; else val[g+c] = buf[n++]; }
+	}}}
+}
+
+/* src/grid.c:349-406: upper layer travels up and lands in the receiver's lower place, then
+ * the lower layer travels down.  TOHALO: take size-2 / 1, place 0 / size-1.
+ * FROMHALO: take size-1 / 0, place 1 / size-2. */
+void orc_halo_dim(const OrcTopo *t, double **val, const int *size, int nV, int d, int op, int dir){
+	int R = t->nRanks;
+	long nSlice = (long)nV*size[0]*size[1]*size[2]/size[d];
+	double *buf = malloc(sizeof(double)*nSlice*R);
+	int upTake = size[d]-2+dir, upPlace = size[d]-1-dir, loTake = 1-dir, loPlace = dir;
+	int upper[64], lower[64];
+	for(int r=0;r<R;r++){
+		int sub[3]; rank_to_sub(t,r,sub);
+		int s0 = sub[d];
+		sub[d] = (s0+1)%t->nSub[d];               upper[r] = sub_to_rank(t,sub);
+		sub[d] = (s0-1+t->nSub[d])%t->nSub[d];    lower[r] = sub_to_rank(t,sub);
+	}
+	for(int r=0;r<R;r++) slice_get(buf+nSlice*r,val[r],size,nV,d,upTake);
+	for(int r=0;r<R;r++) slice_put(buf+nSlice*lower[r],val[r],size,nV,d,loPlace,op);
+	for(int r=0;r<R;r++) slice_get(buf+nSlice*r,val[r],size,nV,d,loTake);
+	for(int r=0;r<R;r++) slice_put(buf+nSlice*upper[r],val[r],size,nV,d,upPlace,op);
+	free(buf);
+}
+/* src/grid.c:340-347 */
+void orc_halo(const OrcTopo *t, double **val, const int *size, int nV, int op, int dir){
+	for(int d=0;d<3;d++) orc_halo_dim(t,val,size,nV,d,op,dir);
+}
+
+/* src/grid.c:804-847: true-grid sum, x innermost, one running sum per nesting level. */
+double orc_sum_true(const double *val, const int *size){
+	double s3 = 0;
+	for(int l=1;l<size[2]-1;l++){
+		double s2 = 0;
+		for(int k=1;k<size[1]-1;k++){
+			double s1 = 0;
+			for(int j=1;j<size[0]-1;j++) s1 += val[IDX(j,k,l,size[0],size[1])];
+			s2 += s1;
+		}
+		s3 += s2;
+	}
+	return s3;
+}
+
+/* src/grid.c:730-779: mean over the global true grid, subtracted from every element. */
+void orc_neutralize(const OrcTopo *t, double **val, const int *size){
+	double tot = 0;
+	for(int r=0;r<t->nRanks;r++){ double mine = orc_sum_true(val[r],size); if(r==0) tot = mine; else tot += mine; }
+	double avg = tot/((double)((size[0]-2)*(size[1]-2)*(size[2]-2))*t->nRanks);
+	long n = (long)size[0]*size[1]*size[2];
+	for(int r=0;r<t->nRanks;r++) for(long g=0;g<n;g++) val[r][g] -= avg;
+}
+
+/* src/grid.c:226-261 restricted to what survives the following halo set: true nodes only
+ * (quirk Q9: the reference also writes junk into ghosts inside the flat range). */
+void orc_findiff1st(const double *phi, double *E, const int *size){
+	long sx = size[0], sy = size[1];
+	long sp[3] = {1, sx, sx*sy};
+	long start = sp[0]+sp[1]+sp[2], end = sx*sy*size[2]-start;
+	for(int d=0;d<3;d++)
+		for(long g=start; g<end; g++)
+			E[3*g+d] = 0.5*(phi[g+sp[d]] - phi[g-sp[d]]);
+}
+
+/* src/grid.c:1276-1321 */
+double orc_pot_energy(const double *rho, const double *phi, const int *size){
+	double s3 = 0;
+	for(int l=1;l<size[2]-1;l++){
+		double s2 = 0;
+		for(int k=1;k<size[1]-1;k++){
+			double s1 = 0;
+			for(int j=1;j<size[0]-1;j++){ long g = IDX(j,k,l,size[0],size[1]); s1 += rho[g]*phi[g]; }
+			s2 += s1;
+		}
+		s3 += s2;
+	}
+	return 0.5*s3;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Multigrid
+ * ---------------------------------------------------------------------------------------- */
+
+/* src/multigrid.c:683-767 (quirk Q8): per cycle, first the nodes with (j+k+l) odd, halo set,
+ * neutralise (gBnd, periodic), then the even ones, halo set, neutralise.  The reference
+ * also sweeps x/y ghost columns; those values are overwritten by the halo set and no true
+ * node reads a same-colour node, so only true nodes are updated here. */
+static void gs_colour(double *phi, const double *rho, const int *size, int parity){
+	long sx = size[0], sy = size[1], sxy = sx*sy;
+	const double coeff = 1./6.;
+	for(int l=1;l<size[2]-1;l++) for(int k=1;k<size[1]-1;k++) for(int j=1;j<size[0]-1;j++){
+		if(((j+k+l)&1)!=parity) continue;
+		long g = IDX(j,k,l,sx,sy);
+		phi[g] = coeff*( phi[g+1] + phi[g-1] + phi[g+sx] + phi[g-sx] + phi[g+sxy] + phi[g-sxy] + rho[g]);
+	}
+}
+void orc_gs3d(const OrcTopo *t, double **phi, double **rho, const int *size, int nCycles){
+	for(int c=0;c<nCycles;c++){
+		for(int par=1;par>=0;par--){
+			for(int r=0;r<t->nRanks;r++) gs_colour(phi[r],rho[r],size,par);
+			orc_halo(t,phi,size,1,0,0);
+			orc_neutralize(t,phi,size);
+		}
+	}
+}
+
+/* src/multigrid.c:1385-1403 + src/grid.c:296-334, on true nodes (ghosts are set by the halo
+ * exchange that always follows). */
+void orc_residual(double *res, const double *rho, const double *phi, const int *size){
+	long sx = size[0], sy = size[1], sxy = sx*sy;
+	for(int l=1;l<size[2]-1;l++) for(int k=1;k<size[1]-1;k++) for(int j=1;j<size[0]-1;j++){
+		long g = IDX(j,k,l,sx,sy);
+		double r = -6.*phi[g];
+		r += phi[g+1] + phi[g-1] + phi[g+sx] + phi[g-sx] + phi[g+sxy] + phi[g-sxy];
+		r += rho[g];
+		res[g] = r;
+	}
+}
+
+/* src/multigrid.c:844-911: coarse (J,K,L) is centred on fine (2J-1,2K-1,2L-1). */
+void orc_half_restrict3d(const double *f, const int *fs, double *c, const int *cs){
+	long fx = fs[0], fxy = (long)fs[0]*fs[1];
+	const double coeff = 1./12.;
+	for(int L=1;L<cs[2]-1;L++) for(int K=1;K<cs[1]-1;K++) for(int J=1;J<cs[0]-1;J++){
+		long g = IDX(2*J-1,2*K-1,2*L-1,fs[0],fs[1]);
+		c[IDX(J,K,L,cs[0],cs[1])] = coeff*(6*f[g] + f[g+1] + f[g-1] + f[g+fx] + f[g-fx] + f[g+fxy] + f[g-fxy]);
+	}
+}
+
+/* src/multigrid.c:1127-1238: inject at odd fine nodes, then fill even l, even k, even j by
+ * midpoint averages, exchanging the halo of the dimension about to be interpolated. */
+void orc_bilin_prol3d(const OrcTopo *t, double **fine, const int *fs, double **coarse, const int *cs){
+	int R = t->nRanks;
+	long fx = fs[0], fxy = (long)fs[0]*fs[1];
+	for(int r=0;r<R;r++)
+		for(int L=1;L<cs[2]-1;L++) for(int K=1;K<cs[1]-1;K++) for(int J=1;J<cs[0]-1;J++)
+			fine[r][IDX(2*J-1,2*K-1,2*L-1,fs[0],fs[1])] = coarse[r][IDX(J,K,L,cs[0],cs[1])];
+	orc_halo_dim(t,fine,fs,1,2,0,0);
+	for(int r=0;r<R;r++)
+		for(int l=2;l<fs[2]-1;l+=2) for(int k=1;k<fs[1]-1;k+=2) for(int j=1;j<fs[0]-1;j+=2){
+			long g = IDX(j,k,l,fs[0],fs[1]);
+			fine[r][g] = 0.5*(fine[r][g-fxy]+fine[r][g+fxy]);
+		}
+	orc_halo_dim(t,fine,fs,1,1,0,0);
+	for(int r=0;r<R;r++)
+		for(int l=1;l<fs[2]-1;l++) for(int k=2;k<fs[1]-1;k+=2) for(int j=1;j<fs[0]-1;j+=2){
+			long g = IDX(j,k,l,fs[0],fs[1]);
+			fine[r][g] = 0.5*(fine[r][g-fx]+fine[r][g+fx]);
+		}
+	orc_halo_dim(t,fine,fs,1,0,0,0);
+	for(int r=0;r<R;r++)
+		for(int l=1;l<fs[2]-1;l++) for(int k=1;k<fs[1]-1;k++) for(int j=2;j<fs[0]-1;j+=2){
+			long g = IDX(j,k,l,fs[0],fs[1]);
+			fine[r][g] = 0.5*(fine[r][g-1]+fine[r][g+1]);
+		}
+}
+
+struct OrcMg {
+	OrcTopo topo;
+	int nLevels, nPre, nPost, nCoarse;
+	int size[16][3];
+	double **rho[16], **phi[16], **res[16];   /* [level][rank]; level 0 borrowed per call */
+};
+
+/* src/multigrid.c:128-206, 297-349: level q has trueSize/2^q, one ghost layer per side. */
+OrcMg *orc_mg_alloc(const OrcTopo *t, int nLevels, int nPre, int nPost, int nCoarse){
+	OrcMg *mg = calloc(1,sizeof *mg);
+	mg->topo = *t; mg->nLevels = nLevels; mg->nPre = nPre; mg->nPost = nPost; mg->nCoarse = nCoarse;
+	for(int q=0;q<nLevels;q++){
+		for(int d=0;d<3;d++) mg->size[q][d] = t->trueSize[d]/(1<<q) + 2;
+		long n = (long)mg->size[q][0]*mg->size[q][1]*mg->size[q][2];
+		mg->rho[q] = calloc(t->nRanks,sizeof(double*));
+		mg->phi[q] = calloc(t->nRanks,sizeof(double*));
+		mg->res[q] = calloc(t->nRanks,sizeof(double*));
+		if(q>0) for(int r=0;r<t->nRanks;r++){
+			mg->rho[q][r] = calloc(n,sizeof(double));
+			mg->phi[q][r] = calloc(n,sizeof(double));
+			mg->res[q][r] = calloc(n,sizeof(double));
+		}
+	}
+	return mg;
+}
+void orc_mg_free(OrcMg *mg){
+	for(int q=0;q<mg->nLevels;q++){
+		if(q>0) for(int r=0;r<mg->topo.nRanks;r++){ free(mg->rho[q][r]); free(mg->phi[q][r]); free(mg->res[q][r]); }
+		free(mg->rho[q]); free(mg->phi[q]); free(mg->res[q]);
+	}
+	free(mg);
+}
+double *orc_mg_level(OrcMg *mg, int which, int level, int rank, int *sizeOut){
+	for(int d=0;d<3;d++) sizeOut[d] = mg->size[level][d];
+	return (which==0 ? mg->rho : which==1 ? mg->phi : mg->res)[level][rank];
+}
+
+/* src/multigrid.c:1496-1548 */
+static void vcycle(OrcMg *mg, int level){
+	const OrcTopo *t = &mg->topo;
+	int R = t->nRanks, bottom = mg->nLevels-1;
+	const int *sz = mg->size[level];
+	double **phi = mg->phi[level], **rho = mg->rho[level], **res = mg->res[level];
+	long n = (long)sz[0]*sz[1]*sz[2];
+	if(level==bottom){
+		orc_halo(t,phi,sz,1,0,0);
+		orc_halo(t,rho,sz,1,0,0);
+		orc_neutralize(t,rho,sz);
+		orc_gs3d(t,phi,rho,sz,mg->nCoarse);
+		orc_neutralize(t,phi,sz);
+		orc_bilin_prol3d(t,mg->res[level-1],mg->size[level-1],phi,sz);
+		return;
+	}
+	orc_halo(t,rho,sz,1,0,0);
+	orc_neutralize(t,rho,sz);
+	orc_gs3d(t,phi,rho,sz,mg->nPre);
+	for(int r=0;r<R;r++) orc_residual(res[r],rho[r],phi[r],sz);
+	orc_halo(t,res,sz,1,0,0);
+	for(int r=0;r<R;r++) orc_half_restrict3d(res[r],sz,mg->rho[level+1][r],mg->size[level+1]);
+	vcycle(mg,level+1);
+	for(int r=0;r<R;r++) for(long g=0;g<n;g++) phi[r][g] += res[r][g];
+	orc_halo(t,phi,sz,1,0,0);
+	orc_neutralize(t,phi,sz);
+	orc_gs3d(t,phi,rho,sz,mg->nPost);
+	orc_neutralize(t,phi,sz);
+	if(level>0) orc_bilin_prol3d(t,mg->res[level-1],mg->size[level-1],phi,sz);
+}
+
+void orc_mg_vcycle(OrcMg *mg, double **rho0, double **phi0, double **res0){
+	for(int r=0;r<mg->topo.nRanks;r++){ mg->rho[0][r] = rho0[r]; mg->phi[0][r] = phi0[r]; mg->res[0][r] = res0[r]; }
+	vcycle(mg,0);
+}
+
+/* src/multigrid.c:1688-1706 (nLevels>1 branch): V-cycles until the RMS residual over the
+ * global true grid is <= tol; the residual grid is squared in place (mgSumTrueSquared :1471). */
+int orc_mg_solve(OrcMg *mg, double **rho0, double **phi0, double **res0, double tol,
+                 int maxCycles, double *barResOut, int cap){
+	const OrcTopo *t = &mg->topo;
+	const int *sz = mg->size[0];
+	long n = (long)sz[0]*sz[1]*sz[2];
+	double barRes = 2.;
+	int cycles = 0;
+	while(barRes>tol && cycles<maxCycles){
+		orc_mg_vcycle(mg,rho0,phi0,res0);
+		for(int r=0;r<t->nRanks;r++) orc_residual(res0[r],rho0[r],phi0[r],sz);
+		orc_halo(t,res0,sz,1,0,0);
+		double sum = 0;
+		for(int r=0;r<t->nRanks;r++){
+			for(long g=0;g<n;g++) res0[r][g] = res0[r][g]*res0[r][g];
+			double mine = orc_sum_true(res0[r],sz);
+			if(r==0) sum = mine; else sum += mine;
+		}
+		long tot = 1;
+		for(int d=0;d<3;d++) tot *= (long)t->nSub[d]*(sz[d]-2);
+		barRes = sum;
+		barRes /= tot;
+		barRes = sqrt(barRes);
+		if(cycles<cap) barResOut[cycles] = barRes;
+		cycles++;
+	}
+	return cycles;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * One time step in the canonical order (src/main.c:197-274 without object calls, one fold,
+ * one solve, no HDF5: SURVEY 8c / quirks Q6, Q7).
+ * ---------------------------------------------------------------------------------------- */
+void orc_field_solve(OrcSim *s){
+	const OrcTopo *t = &s->topo;
+	int R = t->nRanks;
+	long nE = 3L*s->size[0]*s->size[1]*s->size[2];
+	for(int r=0;r<R;r++) orc_distr3d1(s->pos[r],s->nSpecies,s->iStart[r],s->iStop[r],s->charge,s->rho[r],s->size);
+	orc_halo(t,s->rho,s->size,1,1,1);
+	s->lastCycles = orc_mg_solve(s->mg,s->rho,s->phi,s->res,1e-10,1000,s->lastBarRes,64);
+	orc_halo(t,s->phi,s->size,1,0,0);
+	for(int r=0;r<R;r++) orc_findiff1st(s->phi[r],s->E[r],s->size);
+	orc_halo(t,s->E,s->size,3,0,0);
+	for(int r=0;r<R;r++) orc_gmul(s->E[r],nE,-1.);
+}
+
+void orc_accelerate(OrcSim *s, double scaleE){
+	int R = s->topo.nRanks;
+	long nE = 3L*s->size[0]*s->size[1]*s->size[2];
+	double ke[8];
+	for(int q=0;q<=s->nSpecies;q++) s->kinEnergy[q] = 0;
+	for(int r=0;r<R;r++){
+		if(scaleE!=1.0) orc_gmul(s->E[r],nE,scaleE);
+		orc_acc3d1(s->pos[r],s->vel[r],s->nSpecies,s->iStart[r],s->iStop[r],s->charge,s->mass,s->E[r],s->size,ke);
+		if(scaleE!=1.0) orc_gmul(s->E[r],nE,1.0/scaleE);
+		for(int q=0;q<s->nSpecies;q++) s->kinEnergy[q] += ke[q];
+	}
+	for(int q=0;q<s->nSpecies;q++) s->kinEnergy[s->nSpecies] += s->kinEnergy[q];
+}
+
+void orc_step(OrcSim *s){
+	const OrcTopo *t = &s->topo;
+	int R = t->nRanks;
+	for(int r=0;r<R;r++) orc_move(s->pos[r],s->vel[r],s->nSpecies,s->iStart[r],s->iStop[r]);
+	for(int r=0;r<R;r++) orc_extract3d(s->pos[r],s->vel[r],s->nSpecies,s->iStart[r],s->iStop[r],s->thresholds,s->emigrants[r],s->nEmigrants[r]);
+	orc_migrate(t,s->pos,s->vel,s->nSpecies,s->iStop,s->emigrants,s->nEmigrants,s->nImmigrants);
+	orc_field_solve(s);
+	orc_accelerate(s,1.0);
+	double pe = 0;
+	for(int r=0;r<R;r++) pe += orc_pot_energy(s->rho[r],s->phi[r],s->size);
+	s->potEnergy = pe;
+}
