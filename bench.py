@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of the PIC time step (push + deposit + multigrid solve + migration) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload warm|warm_big|<ini>]
+
+Workload at N=1: BASELINE.json configs[1] — warm Maxwellian electron-ion plasma on ONE sub-domain of 64^3 cells,
+70 particles per cell and species (36.7 M particles), configs/warm.ini.  For N>1 every GPU keeps that same
+sub-domain (weak scaling): nSubdomains = 1,1,2 / 1,2,2 / 2,2,2, one process per GPU (torchrun), halos and
+migrants over NCCL.  A step = one pass of src/main.c:197-274 (canonical order) over all particles.
+
+value   device-resident throughput: fused particle pass (pincAccMove3D1KE) + persistent multigrid kernel,
+        CUDA-event timed on the library's stream, max over ranks.
+e2e     the same K steps as a JOB that starts and ends in HOST buffers, through the PINC-named entry points in
+        the reference's call order (puMove, puExtractEmigrants3D, puMigrate, puDistr3D1, gHaloOp, mgSolve,
+        gFinDiff1st, puAcc3D1KE, ...): the population is copied host->device from page-locked memory at the
+        start and device->host at the end INSIDE the timed region, and every step reads its results
+        (energies; rho, phi, E as the reference writes them per step) back to the host.
+--impl reference   the reference's own C sources (oracle/_ref, built from /root/reference under an MPI shim)
+        on the host cores, one thread-rank per sub-domain, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "particle-steps/s (push+deposit+MG solve)"
+UNIT = "particle-steps/s"
+SUBDOMAINS = {1: "1,1,1", 2: "1,1,2", 4: "1,2,2", 8: "2,2,2"}
+
+
+def load_cfg(workload, n_gpus, particles_scale=1.0):
+    from pinc_b200 import config
+    path = workload if os.path.exists(workload) else os.path.join(ROOT, "configs", workload + ".ini")
+    ini = config.Ini(open(path).read())
+    if workload == "warm" or n_gpus > 1:
+        ini.d["grid:nsubdomains"] = SUBDOMAINS[n_gpus]
+    if particles_scale != 1.0:
+        for k in ("population:nparticles", "population:nalloc"):
+            v = config.atof(ini.d[k])
+            ini.d[k] = f"{v * particles_scale:g} pc"
+    text = ini.dump()
+    return text, config.load_config(config.Ini(text))
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_reference(args, n_gpus):
+    """The reference's CPU implementation of the same step on the host cores (bounded sample)."""
+    from pinc_b200 import initial
+    from oracle import orc, ref
+    cores = host_cores()
+    n_ranks = 8 if cores >= 8 else (4 if cores >= 4 else (2 if cores >= 2 else 1))
+    # same global problem as the N=1 GPU workload (64^3 cells), decomposed over the host cores; the sample is
+    # bounded by the particle count (ppc scaled down), not by changing the grid
+    scale = args.cpu_sample
+    from pinc_b200 import config
+    ini = config.Ini(open(os.path.join(ROOT, "configs", "warm.ini")).read())
+    sub = SUBDOMAINS[n_ranks]
+    ini.d["grid:nsubdomains"] = sub
+    ini.d["grid:truesize"] = ",".join(str(64 // int(s)) for s in sub.split(","))
+    ini.d["population:nparticles"] = f"{70 * scale:g} pc"
+    ini.d["population:nalloc"] = f"{128 * scale:g} pc"
+    text = ini.dump()
+    cfg = config.load_config(config.Ini(text))
+    kind = "reference" if ref.available() else "port"
+    per_rank = initial.maxwellian(cfg, seed=20261018)
+    W = ref.RefWorld(text, cfg.nRanks) if kind == "reference" else orc.OrcWorld(cfg)
+    W.set_particles(per_rank)
+    W.migrate(); W.field_solve(); W.half_kick()
+    n_part = sum(len(p) for r in per_rank for (p, _) in r)
+    for _ in range(args.warmup):
+        W.step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        W.step()
+    dt = time.perf_counter() - t0
+    value = n_part * args.steps / dt
+    used = cfg.nRanks if kind == "reference" else 1
+    sample = (f"global 64^3 cells as {sub} sub-domains of {ini.d['grid:truesize']}, {70 * scale:g} particles/cell/species "
+              f"({n_part} particles), {args.steps} steps after {args.warmup} warm-up; throughput per particle-step is "
+              f"what is compared (the GPU workload has 70/cell/species)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "warm (BASELINE configs[1]): 64^3 cells, Maxwellian electrons+ions, CPU sample", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    return line
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args, n_gpus, rank, world_size):
+    import torch
+    from pinc_b200 import abi, initial, lib as plib, sim
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    nccl_id = None
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        L = plib.load()
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            L.pincNcclUniqueId(buf)
+        t = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        nccl_id = bytes(t.cpu().tolist())
+    text, cfg = load_cfg(args.workload, n_gpus, args.particles_scale)
+    assert cfg.nRanks == world_size, (cfg.nSubdomains, world_size)
+    os.environ["PINC_B200_DEVICE"] = str(local_rank)
+    W = sim.World(cfg) if world_size == 1 else sim.World(cfg, rank=rank, world_size=world_size, nccl_id=nccl_id)
+    L = W.lib
+    st = W.ranks[rank]
+    t_ic = time.perf_counter()
+    mine = initial.maxwellian(cfg, seed=20261018, ranks=[rank])[0]
+    per_rank = {rank: mine}
+    t_ic = time.perf_counter() - t_ic
+    # page-lock the host arrays the job copies from/to
+    p = st.pop.contents
+    nbytes_pop = 3 * 8 * int(p.iStart[p.nSpecies])
+    L.pincHostRegister(C.cast(p.pos, C.c_void_p), nbytes_pop)
+    L.pincHostRegister(C.cast(p.vel, C.c_void_p), nbytes_pop)
+    for g in (st.rho, st.phi, st.E):
+        L.pincHostRegister(C.cast(g.contents.val, C.c_void_p), 8 * int(g.contents.sizeProd[4]))
+
+    def barrier():
+        L.pincDeviceSynchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---------------- e2e job: host buffers -> K reference-order steps -> host buffers -----------------------
+    W.set_particles(per_rank)            # fills the host arrays (and uploads once so the set-up below can run)
+    W.migrate(); W.field_solve(); W.half_kick()
+    for _ in range(max(1, args.warmup // 2)):
+        W.step(fused=False)
+    L.pincSyncPopToHost(st.pop)          # the job's input state now lives in the host arrays
+    n_live = sum(p.iStop[s] - p.iStart[s] for s in range(p.nSpecies))
+    grid_bytes = sum(8 * int(g.contents.sizeProd[4]) for g in (st.rho, st.phi, st.E))
+    e2e_steps = max(2, min(args.steps, args.e2e_steps))
+    barrier()
+    t0 = time.perf_counter()
+    L.pincSyncPopToDevice(st.pop)                               # H2D: 48 B per live particle
+    for _ in range(e2e_steps):
+        W.step(fused=False)
+        for g in (st.rho, st.phi, st.E):                        # D2H of the step's field results
+            L.pincSyncGridToHost(g)
+        W.energies()
+    L.pincSyncPopToHost(st.pop)                                 # D2H: 48 B per live particle
+    barrier()
+    t_e2e = allmax(time.perf_counter() - t0)
+    n_global_e2e = allsum(float(n_live))
+    e2e = {"value": n_global_e2e * e2e_steps / t_e2e, "unit": UNIT, "steps": e2e_steps,
+           "h2d_bytes_per_step": int(48 * n_live / e2e_steps),
+           "d2h_bytes_per_step": int(48 * n_live / e2e_steps + grid_bytes + 8 * (p.nSpecies + 2)),
+           "ms_per_step": 1e3 * t_e2e / e2e_steps,
+           "path": "PINC entry points in reference order; population H2D at start and D2H at end inside the timed region (page-locked), fields+energies D2H every step"}
+
+    # ---------------- device-resident throughput (fused particle pass) ------------------------------------------
+    for _ in range(args.warmup):
+        W.step(fused=True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = L.pincLaunchCount()
+    sampler.start()
+    L.pincTimerStart()
+    cycles = []
+    for _ in range(args.steps):
+        W.step(fused=True)
+    ms = L.pincTimerStopMs()
+    barrier()
+    clocks = sampler.stop()
+    launches = L.pincLaunchCount() - launches0
+    ms = allmax(ms)
+    n_live = sum(p.iStop[s] - p.iStart[s] for s in range(p.nSpecies))
+    n_global = allsum(float(n_live))
+    value = n_global * args.steps / (ms * 1e-3)
+    hist = W.history()
+
+    # ---------------- per-kernel-class device time (CUDA events around every launch), 3 extra steps ------------
+    L.pincProfReset(); L.pincProfEnable(1)
+    prof_steps = 3
+    for _ in range(prof_steps):
+        W.step(fused=True)
+    prof = plib.profile(L)
+    L.pincProfEnable(0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    kernels = {}
+    tot_ms = sum(v[0] for v in prof.values()) or 1.0
+    for k, (kms, cnt, by) in prof.items():
+        kernels[k] = {"ms_per_step": kms / prof_steps, "launches_per_step": cnt / prof_steps,
+                      "alg_GBps": (by / (kms * 1e-3) / 1e9) if kms > 0 else None, "share": kms / tot_ms}
+    dom = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
+    roofline = None
+    if dom:
+        kms, cnt, by = prof[dom]
+        ach = by / (kms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        except Exception:
+            pass
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic, "peak_source": peak_src,
+                    "alg_bytes_per_launch": by / cnt, "avg_launch_ms": kms / cnt}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: per GPU {cfg.trueSize} cells, {cfg.nSpecies} species, "
+                                   f"{n_live} particles (Maxwellian, sigma_v={cfg.thermalVelocity} cells/step), nSubdomains={cfg.nSubdomains}",
+                       "global_particles": int(n_global), "mgLevels": cfg.mgLevels, "parallelism": f"domain-decomposition x{world_size}",
+                       "l2": "particle arrays (48 B x particles per GPU) exceed the 126 MB L2; no explicit flush",
+                       "vcycles_last_solve": len(hist), "ic_seconds": t_ic},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels}
+    W.close()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="warm")
+    ap.add_argument("--particles-scale", type=float, default=1.0)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--cpu-sample", type=float, default=1.0, help="fraction of the 70 particles/cell used by the CPU arms")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if rank == 0:
+            a = argparse.Namespace(**vars(args))
+            a.steps = min(args.steps, 3); a.warmup = min(args.warmup, 1)
+            print(json.dumps(run_reference(a, args.gpus)), flush=True)
+        return
+    assert world == args.gpus, f"--gpus {args.gpus} needs {args.gpus} ranks (torchrun); WORLD_SIZE={world}"
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    line = run_ours(args, args.gpus, rank, world)
+    if rank == 0:
+        if args.gpus == 1 and not args.no_cpu_baseline:
+            a = argparse.Namespace(**vars(args))
+            a.steps, a.warmup = 2, 1
+            ref_line = run_reference(a, 1)
+            line["cpu_baseline"] = ref_line["cpu_baseline"]
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

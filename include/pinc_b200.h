@@ -23,6 +23,7 @@
 #ifndef PINC_B200_H
 #define PINC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -140,6 +141,7 @@ void puMigrate(Population *pop, MpiInfo *mpiInfo, Grid *grid);                  
 int  puRankToNeighbor(MpiInfo *mpiInfo, int rank);                              /* pusher.h:186 (pusher.c:1214) */
 int  puNeighborToRank(MpiInfo *mpiInfo, int neighbor);                          /* pusher.h:187 (pusher.c:1194) */
 int  puNeighborToReciprocal(int neighbor, int nDims);                           /* pusher.h:188 (pusher.c:1181) */
+void pSumKinEnergy(Population *pop);                                            /* population.h (population.c:700) */
 /* plain-argument form of puGet3DRotationParameters (pusher.c:485; the reference reads
  * BExt/charge/mass from the ini dictionary, which stays host code) */
 void pincGet3DRotationParameters(int nSpecies, const double *BExt, const double *charge,
@@ -194,6 +196,9 @@ void mgFreeSolver(MultigridSolver *solver);                                     
 /* residual history of the most recent mgSolve on this rank: returns the V-cycle count and
  * copies up to `cap` values of barRes (multigrid.c:1700-1704), one per V-cycle. */
 int pincMgLastHistory(double *barRes, int cap);
+/* execution mode of single-rank solves: 1 (default) = one persistent cooperative kernel per solve,
+ * 0 = one kernel per reference call.  Same arithmetic per node; $PINC_B200_MG=ops sets 0 at start-up. */
+void pincMgSetMode(int fused);
 
 /* ---------------------------------------------------------------------------------
  * Host-struct constructors with plain arguments (restating gAlloc grid.c:413,
@@ -227,11 +232,14 @@ void pincCtxDestroy(PincCtx *ctx);
 void pincCommInitThreads(PincCtx **ctxs, int n);
 int  pincNcclUniqueId(char *out128);
 void pincCommInitNccl(PincCtx *ctx, const char *uniqueId128);
+const char *pincTransportName(void);            /* "self", "threads" or "nccl" */
 
 void pincSyncGridToDevice(Grid *grid);
 void pincSyncGridToHost(Grid *grid);
 void pincSyncPopToDevice(Population *pop);
 void pincSyncPopToHost(Population *pop);
+int  pincHostRegister(void *ptr, size_t bytes); /* page-lock a caller-owned host array; 0 on success */
+int  pincHostUnregister(void *ptr);
 void pincForget(void *hostStruct);              /* drop the mirror of a Grid*/ /*Population* */
 void pincDeviceSynchronize(void);
 /* fused step helpers (same arithmetic as the separate entry points, one pass over the particles):

@@ -1,0 +1,171 @@
+// common.h — internal declarations of libpinc_b200 (device mirrors, context, launch helpers).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "../../include/pinc_b200.h"
+
+namespace pinc {
+
+[[noreturn]] void fatal(const char *fmt, ...);
+
+#define PINC_CUDA(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) \
+	::pinc::fatal("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); } while(0)
+
+// ---- kernel classes for the per-class device-time accounting (pincProfGet) ----
+enum KClass { K_PUSH = 0, K_MOVE, K_DEPOSIT, K_EXTRACT, K_IMPORT, K_SORT, K_GRIDOP, K_HALO, K_REDUCE,
+              K_GS, K_RESIDUAL, K_RESTRICT, K_PROLONG, K_MGFUSED, K_FINDIFF, K_LAYOUT, K_NCLASS };
+extern const char *kclassName[K_NCLASS];
+
+// device-side error bits (Ctx::d_flags[0])
+enum DevErr { ERR_POS_RANGE = 1, ERR_CAPACITY = 2, ERR_VEL_MAX = 4 };
+
+// fixed-point scale of the deposition accumulators: weights in [0,1] are summed as
+// round(w * 2^46) in 64-bit integers, so a node can take 2^17 particles per species before the
+// accumulator overflows and the sum does not depend on the order of the additions.
+#define PINC_FIX_BITS 46
+
+struct DevGrid {
+	Grid *host = nullptr;
+	double *d = nullptr;        // values, same layout as host (core.h:261-277)
+	long n = 0;                 // sizeProd[rank]
+	int nv = 1;                 // size[0]
+	int size[3] = {1,1,1};      // ghost-inclusive nx,ny,nz
+	int tsize[3] = {1,1,1};
+	double *d_send = nullptr;   // 2 slabs (up, down) of the largest face
+	double *d_recv = nullptr;
+	long maxSlice = 0;
+	long long *d_fix = nullptr; // fixed-point accumulator for deposition (scalar grids, lazily)
+};
+
+struct DevPop {
+	Population *host = nullptr;
+	int nS = 0;
+	long cap = 0;               // iStart[nS]
+	double *base = nullptr;     // 6*cap doubles: x,y,z,vx,vy,vz planes (SoA)
+	double *alt = nullptr;      // second buffer of the same size (target of the cell sort), lazily
+	long iStart[9] = {0};
+	// cell binning (per species): particles [iStart[s], iStart[s]+sortedN[s]) are ordered by cell and
+	// cellStart[s][c] is the offset (relative to iStart[s]) of the first particle of cell c.
+	int nc[3] = {0,0,0};        // cells per dimension (= size-1) the binning was built for
+	long nCells = 0;            // nc[0]*nc[1]*nc[2]; keys nCells..nCells+26 are the emigrant bins
+	unsigned *d_keys = nullptr; // cap entries
+	unsigned *d_hist[8] = {nullptr};      // nCells+27+1 counts, then (after the scan) offsets
+	unsigned *d_cursor[8] = {nullptr};    // nCells+27 running cursors of the scatter
+	long sortedN[8] = {0};
+	bool keysValid = false;     // d_keys/d_hist hold the classification of the current positions
+	double keyThr[6] = {0};     // thresholds the keys were computed with
+	// migrants
+	double *d_emig = nullptr;   // packed (x,y,z,vx,vy,vz) records, neighbour by neighbour, species inside
+	long emigCap = 0;           // records
+	long emigOff[28] = {0};     // record offset of neighbour ne in d_emig
+	double *d_immig = nullptr;
+	long immigCap = 0;
+	bool extracted = false;     // emigrants sit behind iStop[s], binned by neighbour, not yet packed
+};
+
+struct ProfEvent { cudaEvent_t a, b; int cls; };
+
+struct Transport;
+
+struct Ctx {
+	int device = 0, rank = 0, size = 1;
+	cudaStream_t stream = nullptr;
+	std::unordered_map<const void*, DevGrid*> grids;
+	std::unordered_map<const void*, DevPop*> pops;
+	// scratch
+	double *d_scal = nullptr;       // 256 small device scalars (reductions, means)
+	double *h_scal = nullptr;       // pinned mirror
+	double *d_partial = nullptr;    // per-block partial sums
+	long partialCap = 0;
+	void *d_tmp = nullptr;          // general scratch (grows)
+	size_t tmpBytes = 0;
+	long *h_long = nullptr;         // 1024 pinned host longs
+	long *d_long = nullptr;
+	int *d_flags = nullptr;         // device error bits
+	int *h_flags = nullptr;
+	unsigned *d_bar = nullptr;      // grid barrier words of the persistent multigrid kernel
+	int numSMs = 148;
+	// accounting
+	long launches = 0;
+	int profOn = 0;
+	std::vector<ProfEvent> profEvents;
+	std::vector<cudaEvent_t> evPool;
+	double profMs[K_NCLASS] = {0};
+	long profCount[K_NCLASS] = {0};
+	double profBytes[K_NCLASS] = {0};
+	cudaEvent_t tStart = nullptr, tStop = nullptr;
+	// multigrid residual history of the most recent solve (device + pinned host: [0] = cycles, [1..] = barRes)
+	double *d_mgHist = nullptr, *h_mgHist = nullptr;
+	bool mgHistPending = false;
+	std::vector<double> mgHistory;
+	Transport *tp = nullptr;
+	std::string lastError;
+};
+
+Ctx *cur();                                    // current context of this host thread (created lazily)
+DevGrid *devGrid(Ctx *c, const Grid *g, bool upload = true);
+DevPop *devPop(Ctx *c, const Population *p, bool upload = true);
+void *tmpBuffer(Ctx *c, size_t bytes);
+double *partialBuffer(Ctx *c, long n);
+void checkDeviceFlags(Ctx *c, const char *where);      // after a stream sync
+void streamSync(Ctx *c);
+
+// launch bookkeeping: PINC_LAUNCH(ctx, class, algorithmic bytes, kernel<<<...>>>(...))
+struct LaunchScope {
+	Ctx *c; int cls; cudaEvent_t a = nullptr;
+	LaunchScope(Ctx *c, int cls, double bytes);
+	~LaunchScope();
+};
+#define PINC_LAUNCH(ctx, cls, bytes, ...) do { { ::pinc::LaunchScope ls_((ctx), (cls), (double)(bytes)); __VA_ARGS__; } \
+	cudaError_t e_ = cudaGetLastError(); if(e_ != cudaSuccess) ::pinc::fatal("launch failed (%s) at %s:%d: %s", \
+	::pinc::kclassName[cls], __FILE__, __LINE__, cudaGetErrorString(e_)); } while(0)
+
+inline int gridFor(long n, int block, int maxBlocks){
+	long b = (n + block - 1)/block;
+	if(b < 1) b = 1;
+	if(b > maxBlocks) b = maxBlocks;
+	return (int)b;
+}
+
+// ---- transport (exchange steps between ranks) ----
+struct Msg { int peer; int tag; void *ptr; size_t bytes; };
+struct Transport {
+	virtual ~Transport() {}
+	// all sends and receives of one exchange step; device pointers.  A message is identified by
+	// (sender, receiver, tag); returns when the receives are ordered on ctx->stream.
+	virtual void exchange(Ctx *c, std::vector<Msg> sends, std::vector<Msg> recvs) = 0;
+	virtual void allreduceSum(Ctx *c, double *d_vals, int n) = 0;           // in place, device, stream ordered
+	virtual void allgatherLong(Ctx *c, const long *h_in, int n, long *h_out) = 0;  // host values, blocking
+	virtual void barrier(Ctx *c) = 0;
+	virtual const char *name() const = 0;
+};
+Transport *makeSelfTransport();
+void localCopies(Ctx *c, std::vector<Msg> &sends, std::vector<Msg> &recvs);   // matches and removes self messages
+
+// ---- topology (src/grid.c:166-171, src/pusher.c:1181-1231) ----
+int neighborToRank(const MpiInfo *m, int ne);
+int neighborToReciprocal(int ne, int nDims);
+int rankToNeighbor(const MpiInfo *m, int rank);
+
+// ---- grid ops (grid.cu) ----
+void gridScale(Ctx *c, DevGrid *g, double num);
+void gridZero(Ctx *c, DevGrid *g);
+void gridHaloDim(Ctx *c, DevGrid *g, const MpiInfo *m, int d /*1..3*/, int add, int dir);
+void gridHalo(Ctx *c, DevGrid *g, const MpiInfo *m, int add, int dir);
+void gridNeutralize(Ctx *c, DevGrid *g, const MpiInfo *m);
+void gridAddTo(Ctx *c, DevGrid *r, const DevGrid *a);
+// sum over the true grid of val (mode 0), val^2 after squaring in place (mode 1) or val*other (mode 2);
+// the result lands in c->d_scal[slot] (this rank only, no all-reduce)
+void gridSumTrue(Ctx *c, DevGrid *g, int mode, const DevGrid *other, int slot);
+double readScalar(Ctx *c, int slot);           // D2H of d_scal[slot] + sync
+
+// ---- multigrid (multigrid.cu) ----
+void mgForgetPlans(Ctx *c);
+
+} // namespace pinc

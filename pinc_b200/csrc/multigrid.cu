@@ -1,0 +1,575 @@
+// multigrid.cu — geometric multigrid Poisson solver (src/multigrid.c): red-black Gauss-Seidel (mgGS3D :683),
+// residual (:1385), half-weight restriction (:844), trilinear prolongation (:1127), recursive V-cycle (:1496)
+// and the tolerance loop of mgSolveRaw (:1688).
+//
+// Two execution modes with the SAME per-point arithmetic (the device functions below):
+//
+//  ops    one kernel per reference call, ghost layers kept current by gHaloOp/gBnd exactly as the
+//         reference does.  Used for the individual entry points and whenever the solve spans several ranks.
+//  fused  single-rank periodic solves: ONE persistent cooperative kernel runs the whole tolerance loop.
+//         Ghost layers are not touched inside (neighbours are read at the periodic image of the true node,
+//         which is bit-identical to reading a ghost that setSlice just filled), the mean subtraction of
+//         gBnd is carried as a pending shift that is applied when a value is next read (each value is still
+//         rounded by one subtraction per gBnd, as in the reference), true-grid sums are fused into the sweep
+//         that precedes them, and levels of <= 8192 nodes run inside one CTA on __syncthreads instead of
+//         grid barriers.  Ghosts of every level are filled once at the end, so the arrays are left in the
+//         state the reference leaves them in.
+//
+// The grids of a level are tiny (<= 2.2 M nodes): the solver is bound by the latency of ~45 dependent
+// half-sweeps per level per V-cycle, not by HBM, which is why the fused mode exists.
+#include "common.h"
+#include <cmath>
+
+namespace pinc {
+
+struct Lvl { double *phi, *rho, *res; int s0, s1, s2; };
+
+__device__ __forceinline__ double ldg2(const double *p){ return __ldcg(p); }
+template<bool WRAP> __device__ __forceinline__ int upI(int j, int s){ return (WRAP && j == s-2) ? 1 : j+1; }
+template<bool WRAP> __device__ __forceinline__ int dnI(int j, int s){ return (WRAP && j == 1) ? s-2 : j-1; }
+__device__ __forceinline__ long ix(int j, int k, int l, int s0, int s1){ return j + (long)s0*(k + (long)s1*l); }
+
+// phi_new = 1/6 * (phi[+j] + phi[-j] + phi[+k] + phi[-k] + phi[+l] + phi[-l] + rho), summed left to right
+// (src/multigrid.c:711-714); `sh` is the pending mean shift of the neighbours' colour.
+template<bool WRAP> __device__ __forceinline__ double gsPoint(const double *phi, const double *rho, int j, int k, int l,
+		int s0, int s1, int s2, double sh){
+	long g = ix(j,k,l,s0,s1);
+	double a = ldg2(phi + ix(upI<WRAP>(j,s0),k,l,s0,s1)) - sh;
+	double b = ldg2(phi + ix(dnI<WRAP>(j,s0),k,l,s0,s1)) - sh;
+	double c = ldg2(phi + ix(j,upI<WRAP>(k,s1),l,s0,s1)) - sh;
+	double d = ldg2(phi + ix(j,dnI<WRAP>(k,s1),l,s0,s1)) - sh;
+	double e = ldg2(phi + ix(j,k,upI<WRAP>(l,s2),s0,s1)) - sh;
+	double f = ldg2(phi + ix(j,k,dnI<WRAP>(l,s2),s0,s1)) - sh;
+	const double coeff = 1./6.;
+	return coeff*(a + b + c + d + e + f + ldg2(rho + g));
+}
+// res = -6 phi; res += (sum of six neighbours); res += rho  (src/grid.c:318-322, src/multigrid.c:1400)
+template<bool WRAP> __device__ __forceinline__ double resPoint(const double *phi, const double *rho, int j, int k, int l,
+		int s0, int s1, int s2){
+	long g = ix(j,k,l,s0,s1);
+	double r = -6.*ldg2(phi + g);
+	r += ldg2(phi + ix(upI<WRAP>(j,s0),k,l,s0,s1)) + ldg2(phi + ix(dnI<WRAP>(j,s0),k,l,s0,s1))
+	   + ldg2(phi + ix(j,upI<WRAP>(k,s1),l,s0,s1)) + ldg2(phi + ix(j,dnI<WRAP>(k,s1),l,s0,s1))
+	   + ldg2(phi + ix(j,k,upI<WRAP>(l,s2),s0,s1)) + ldg2(phi + ix(j,k,dnI<WRAP>(l,s2),s0,s1));
+	r += ldg2(rho + g);
+	return r;
+}
+// coarse(J,K,L) = 1/12 * (6 f + f[+j] + f[-j] + f[+k] + f[-k] + f[+l] + f[-l]) centred on fine (2J-1,2K-1,2L-1)
+// (src/multigrid.c:844-911)
+template<bool WRAP> __device__ __forceinline__ double restrictPoint(const double *f, int J, int K, int L, int s0, int s1, int s2){
+	int j = 2*J-1, k = 2*K-1, l = 2*L-1;
+	const double coeff = 1./12.;
+	return coeff*(6*ldg2(f + ix(j,k,l,s0,s1))
+		+ ldg2(f + ix(upI<WRAP>(j,s0),k,l,s0,s1)) + ldg2(f + ix(dnI<WRAP>(j,s0),k,l,s0,s1))
+		+ ldg2(f + ix(j,upI<WRAP>(k,s1),l,s0,s1)) + ldg2(f + ix(j,dnI<WRAP>(k,s1),l,s0,s1))
+		+ ldg2(f + ix(j,k,upI<WRAP>(l,s2),s0,s1)) + ldg2(f + ix(j,k,dnI<WRAP>(l,s2),s0,s1)));
+}
+// Trilinear prolongation of the coarse grid to fine true node (j,k,l), in the nesting the reference's three
+// passes produce (z first, then y, then x; src/multigrid.c:1127-1238).  Periodic wrap on the coarse index.
+__device__ __forceinline__ double prolZ(const double *c, int J, int K, int l, int c0, int c1, int c2){
+	if(l & 1) return ldg2(c + ix(J,K,(l+1)/2,c0,c1));
+	int La = l/2, Lb = (l/2+1 == c2-1) ? 1 : l/2+1;
+	return 0.5*(ldg2(c + ix(J,K,La,c0,c1)) + ldg2(c + ix(J,K,Lb,c0,c1)));
+}
+__device__ __forceinline__ double prolY(const double *c, int J, int k, int l, int c0, int c1, int c2){
+	if(k & 1) return prolZ(c, J, (k+1)/2, l, c0, c1, c2);
+	int Ka = k/2, Kb = (k/2+1 == c1-1) ? 1 : k/2+1;
+	return 0.5*(prolZ(c, J, Ka, l, c0, c1, c2) + prolZ(c, J, Kb, l, c0, c1, c2));
+}
+__device__ __forceinline__ double prolPoint(const double *c, int j, int k, int l, int c0, int c1, int c2){
+	if(j & 1) return prolY(c, (j+1)/2, k, l, c0, c1, c2);
+	int Ja = j/2, Jb = (j/2+1 == c0-1) ? 1 : j/2+1;
+	return 0.5*(prolY(c, Ja, k, l, c0, c1, c2) + prolY(c, Jb, k, l, c0, c1, c2));
+}
+
+__device__ __forceinline__ void truePoint(long i, int t0, int t1, int &j, int &k, int &l){
+	j = (int)(i % t0) + 1; long r = i / t0; k = (int)(r % t1) + 1; l = (int)(r / t1) + 1;
+}
+
+// =================================================================================================
+// ops mode: one kernel per reference call (ghost layers are read, not wrapped)
+// =================================================================================================
+__global__ void k_gs_colour(double *__restrict__ phi, const double *__restrict__ rho, int s0, int s1, int s2, int parity){
+	int t0 = s0-2, t1 = s1-2, t2 = s2-2;
+	long nt = (long)t0*t1*t2;
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; i < nt; i += st){
+		int j, k, l; truePoint(i, t0, t1, j, k, l);
+		if(((j+k+l)&1) != parity) continue;
+		phi[ix(j,k,l,s0,s1)] = gsPoint<false>(phi, rho, j, k, l, s0, s1, s2, 0.0);
+	}
+}
+__global__ void k_residual(double *__restrict__ res, const double *__restrict__ rho, const double *__restrict__ phi, int s0, int s1, int s2){
+	int t0 = s0-2, t1 = s1-2, t2 = s2-2;
+	long nt = (long)t0*t1*t2;
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; i < nt; i += st){
+		int j, k, l; truePoint(i, t0, t1, j, k, l);
+		res[ix(j,k,l,s0,s1)] = resPoint<false>(phi, rho, j, k, l, s0, s1, s2);
+	}
+}
+__global__ void k_restrict(const double *__restrict__ f, int s0, int s1, int s2, double *__restrict__ cgrid, int c0, int c1, int c2){
+	int t0 = c0-2, t1 = c1-2, t2 = c2-2;
+	long nt = (long)t0*t1*t2;
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; i < nt; i += st){
+		int J, K, L; truePoint(i, t0, t1, J, K, L);
+		cgrid[ix(J,K,L,c0,c1)] = restrictPoint<false>(f, J, K, L, s0, s1, s2);
+	}
+}
+// the reference's three prolongation passes; pass 0 injects, pass 1..3 interpolate along z, y, x
+__global__ void k_prolong_pass(double *__restrict__ f, int s0, int s1, int s2, const double *__restrict__ cgrid, int c0, int c1, int pass){
+	int t0 = s0-2, t1 = s1-2, t2 = s2-2;
+	long nt = (long)t0*t1*t2;
+	long sx = s0, sxy = (long)s0*s1;
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; i < nt; i += st){
+		int j, k, l; truePoint(i, t0, t1, j, k, l);
+		long g = ix(j,k,l,s0,s1);
+		if(pass == 0){ if((j&1) && (k&1) && (l&1)) f[g] = cgrid[ix((j+1)/2,(k+1)/2,(l+1)/2,c0,c1)]; }
+		else if(pass == 1){ if((j&1) && (k&1) && !(l&1)) f[g] = 0.5*(f[g-sxy] + f[g+sxy]); }
+		else if(pass == 2){ if((j&1) && !(k&1)) f[g] = 0.5*(f[g-sx] + f[g+sx]); }
+		else { if(!(j&1)) f[g] = 0.5*(f[g-1] + f[g+1]); }
+	}
+}
+
+
+static inline int tGrid(Ctx *c, long nt){ return gridFor(nt, 256, c->numSMs*8); }
+static inline long trueCount(const DevGrid *g){ return (long)g->tsize[0]*g->tsize[1]*g->tsize[2]; }
+
+static void opGS(Ctx *c, DevGrid *phi, DevGrid *rho, int nCycles, const MpiInfo *m){
+	long nt = trueCount(phi);
+	for(int cyc = 0; cyc < nCycles; cyc++)
+		for(int parity = 1; parity >= 0; parity--){
+			PINC_LAUNCH(c, K_GS, 12.0*nt, (k_gs_colour<<<tGrid(c,nt),256,0,c->stream>>>(phi->d, rho->d, phi->size[0], phi->size[1], phi->size[2], parity)));
+			gridHalo(c, phi, m, 0, 0);
+			gridNeutralize(c, phi, m);
+		}
+}
+static void opResidual(Ctx *c, DevGrid *res, DevGrid *rho, DevGrid *phi){
+	long nt = trueCount(phi);
+	PINC_LAUNCH(c, K_RESIDUAL, 24.0*nt, (k_residual<<<tGrid(c,nt),256,0,c->stream>>>(res->d, rho->d, phi->d, phi->size[0], phi->size[1], phi->size[2])));
+}
+static void opRestrict(Ctx *c, DevGrid *fine, DevGrid *coarse){
+	for(int d = 0; d < 3; d++) if(coarse->tsize[d]*2 != fine->tsize[d]) fatal("mgHalfRestrict3D: coarse grid is not half the fine grid");
+	long nt = trueCount(coarse);
+	PINC_LAUNCH(c, K_RESTRICT, 9.0*trueCount(fine), (k_restrict<<<tGrid(c,nt),256,0,c->stream>>>(fine->d, fine->size[0], fine->size[1], fine->size[2], coarse->d, coarse->size[0], coarse->size[1], coarse->size[2])));
+}
+static void opProlong(Ctx *c, DevGrid *fine, DevGrid *coarse, const MpiInfo *m){
+	for(int d = 0; d < 3; d++) if(coarse->tsize[d]*2 != fine->tsize[d]) fatal("mgBilinProl3D: coarse grid is not half the fine grid");
+	long nt = trueCount(fine);
+	for(int pass = 0; pass < 4; pass++){
+		if(pass > 0) gridHaloDim(c, fine, m, 4-pass, 0, 0);          // z, then y, then x (multigrid.c:1170,1194,1215)
+		PINC_LAUNCH(c, K_PROLONG, 4.0*nt, (k_prolong_pass<<<tGrid(c,nt),256,0,c->stream>>>(fine->d, fine->size[0], fine->size[1], fine->size[2], coarse->d, coarse->size[0], coarse->size[1], pass)));
+	}
+}
+
+// src/multigrid.c:1496-1548
+static void opVCycle(Ctx *c, int level, int bottom, int top, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *m){
+	DevGrid *phi = devGrid(c, mgPhi->grids[level]), *rho = devGrid(c, mgRho->grids[level]), *res = devGrid(c, mgRes->grids[level]);
+	if(level == bottom){
+		gridHalo(c, phi, m, 0, 0);
+		gridHalo(c, rho, m, 0, 0);
+		gridNeutralize(c, rho, m);
+		opGS(c, phi, rho, mgRho->nCoarseSolve, m);
+		gridNeutralize(c, phi, m);
+		if(level > 0) opProlong(c, devGrid(c, mgRes->grids[level-1]), phi, m);
+		return;
+	}
+	gridHalo(c, rho, m, 0, 0);
+	gridNeutralize(c, rho, m);
+	opGS(c, phi, rho, mgRho->nPreSmooth, m);
+	opResidual(c, res, rho, phi);
+	gridHalo(c, res, m, 0, 0);
+	opRestrict(c, res, devGrid(c, mgRho->grids[level+1]));
+	opVCycle(c, level+1, bottom, top, mgRho, mgPhi, mgRes, m);
+	gridAddTo(c, phi, res);
+	gridHalo(c, phi, m, 0, 0);
+	gridNeutralize(c, phi, m);
+	opGS(c, phi, rho, mgRho->nPostSmooth, m);
+	gridNeutralize(c, phi, m);
+	if(level > top) opProlong(c, devGrid(c, mgRes->grids[level-1]), phi, m);
+}
+
+// =================================================================================================
+// fused mode: the whole tolerance loop in one persistent cooperative kernel
+// =================================================================================================
+#define MG_MAXLEV 10
+#define MG_BLOCK 512
+#define MG_SMALL 8192        // levels with at most this many true nodes run inside CTA 0
+struct MgPlan {
+	Lvl L[MG_MAXLEV];
+	int nLevels, nPre, nPost, nCoarse, qSmall, maxCycles;
+	double tol, totTrue;
+	double *partial;         // 2*gridDim doubles
+	unsigned *bar;
+	double *hist;            // [0] cycles, [1..] barRes per V-cycle
+};
+
+struct Scope {
+	bool single;             // only this CTA takes part (block-level barriers)
+	unsigned *bar; unsigned gen;
+	double *partial; int flip;
+	double *sh;              // 18 doubles of shared memory
+	__device__ __forceinline__ long tid() const { return single ? threadIdx.x : blockIdx.x*(long)blockDim.x + threadIdx.x; }
+	__device__ __forceinline__ long nthr() const { return single ? blockDim.x : (long)gridDim.x*blockDim.x; }
+	__device__ __forceinline__ void sync(){
+		__syncthreads();
+		if(single) return;
+		if(threadIdx.x == 0){
+			__threadfence();
+			unsigned old = atomicAdd(&bar[0], 1u);
+			if(old == gridDim.x - 1){
+				atomicExch(&bar[0], 0u);
+				__threadfence();
+				atomicAdd(&bar[1], 1u);
+			} else {
+				while(*((volatile unsigned*)&bar[1]) == gen){ }
+			}
+			__threadfence();
+			gen++;
+		}
+		__syncthreads();
+	}
+	// sum over all participating threads; the same bits in every thread; acts as a barrier
+	__device__ __forceinline__ double allSum(double v){
+		int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+		for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+		if(lane == 0) sh[w] = v;
+		__syncthreads();
+		if(w == 0){
+			double t = lane < nw ? sh[lane] : 0.0;
+			for(int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+			if(lane == 0) sh[17] = t;
+		}
+		__syncthreads();
+		double tot = sh[17];
+		if(single){ __syncthreads(); return tot; }
+		if(threadIdx.x == 0) __stcg(&partial[flip*gridDim.x + blockIdx.x], tot);
+		sync();
+		if(w == 0){
+			double a = 0;
+			for(int i = lane; i < (int)gridDim.x; i += 32) a += __ldcg(&partial[flip*gridDim.x + i]);
+			for(int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+			if(lane == 0) sh[17] = a;
+		}
+		__syncthreads();
+		tot = sh[17];
+		__syncthreads();
+		flip ^= 1;
+		return tot;
+	}
+};
+
+// gNeutralizeGrid on the true nodes: returns after the subtraction is visible to everyone
+__device__ void fNeutralize(double *v, int s0, int s1, int s2, Scope &S){
+	int t0 = s0-2, t1 = s1-2, t2 = s2-2; long nt = (long)t0*t1*t2;
+	double acc = 0;
+	for(long i = S.tid(); i < nt; i += S.nthr()){ int j,k,l; truePoint(i,t0,t1,j,k,l); acc += ldg2(v + ix(j,k,l,s0,s1)); }
+	double avg = S.allSum(acc)/(double)nt;
+	for(long i = S.tid(); i < nt; i += S.nthr()){ int j,k,l; truePoint(i,t0,t1,j,k,l); long g = ix(j,k,l,s0,s1); v[g] = ldg2(v + g) - avg; }
+	S.sync();
+}
+
+// mgGS3D with gBnd's mean subtraction carried as pending shifts.  sIn: shift still pending on every value at entry.
+__device__ void fGS(const Lvl &L, int nCycles, double sIn, Scope &S){
+	int s0 = L.s0, s1 = L.s1, s2 = L.s2;
+	int t0 = s0-2, t1 = s1-2, t2 = s2-2; long nt = (long)t0*t1*t2;
+	int half = t0/2; long items = (long)half*t1*t2;
+	double sR = sIn, sPrev = 0;
+	if(nCycles <= 0){
+		if(sIn != 0.0){
+			for(long i = S.tid(); i < nt; i += S.nthr()){ int j,k,l; truePoint(i,t0,t1,j,k,l); long g = ix(j,k,l,s0,s1); L.phi[g] = ldg2(L.phi + g) - sIn; }
+			S.sync();
+		}
+		return;
+	}
+	for(int h = 0; h < 2*nCycles; h++){
+		int parity = (h & 1) ? 0 : 1;
+		double acc = 0;
+		for(long i = S.tid(); i < items; i += S.nthr()){
+			int m = (int)(i % half); long r = i / half; int k = (int)(r % t1) + 1; int l = (int)(r / t1) + 1;
+			int ja = 2*m+1;
+			int jOwn = (((ja+k+l)&1) == parity) ? ja : ja+1;
+			int jOth = 2*ja+1 - jOwn;
+			double vn = gsPoint<true>(L.phi, L.rho, jOwn, k, l, s0, s1, s2, sR);
+			double vo = ldg2(L.phi + ix(jOth,k,l,s0,s1)) - sR;
+			L.phi[ix(jOwn,k,l,s0,s1)] = vn;
+			acc += vn; acc += vo;
+		}
+		double avg = S.allSum(acc)/(double)nt;
+		sPrev = sR; sR = avg;
+	}
+	// materialise: the colour written last (even nodes) carries sR, the other one sPrev then sR
+	for(long i = S.tid(); i < nt; i += S.nthr()){
+		int j,k,l; truePoint(i,t0,t1,j,k,l); long g = ix(j,k,l,s0,s1);
+		double v = ldg2(L.phi + g);
+		if((j+k+l)&1) v -= sPrev;
+		v -= sR;
+		L.phi[g] = v;
+	}
+	S.sync();
+}
+
+__device__ void fDown(const MgPlan &P, int q, Scope &S){
+	const Lvl &L = P.L[q], &C = P.L[q+1];
+	fNeutralize(L.rho, L.s0, L.s1, L.s2, S);
+	fGS(L, P.nPre, 0.0, S);
+	{
+		int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2; long nt = (long)t0*t1*t2;
+		for(long i = S.tid(); i < nt; i += S.nthr()){ int j,k,l; truePoint(i,t0,t1,j,k,l);
+			L.res[ix(j,k,l,L.s0,L.s1)] = resPoint<true>(L.phi, L.rho, j, k, l, L.s0, L.s1, L.s2); }
+		S.sync();
+	}
+	{
+		int t0 = C.s0-2, t1 = C.s1-2, t2 = C.s2-2; long nt = (long)t0*t1*t2;
+		for(long i = S.tid(); i < nt; i += S.nthr()){ int J,K,Lz; truePoint(i,t0,t1,J,K,Lz);
+			C.rho[ix(J,K,Lz,C.s0,C.s1)] = restrictPoint<true>(L.res, J, K, Lz, L.s0, L.s1, L.s2); }
+		S.sync();
+	}
+}
+__device__ void fBottom(const MgPlan &P, Scope &S){
+	const Lvl &L = P.L[P.nLevels-1];
+	fNeutralize(L.rho, L.s0, L.s1, L.s2, S);
+	fGS(L, P.nCoarse, 0.0, S);
+	fNeutralize(L.phi, L.s0, L.s1, L.s2, S);
+}
+// res(q) := P(phi(q+1)); phi(q) += res(q); gBnd; post-smooth; gBnd
+__device__ void fUp(const MgPlan &P, int q, Scope &S){
+	const Lvl &L = P.L[q], &C = P.L[q+1];
+	int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2; long nt = (long)t0*t1*t2;
+	double acc = 0;
+	for(long i = S.tid(); i < nt; i += S.nthr()){
+		int j,k,l; truePoint(i,t0,t1,j,k,l); long g = ix(j,k,l,L.s0,L.s1);
+		double p = prolPoint(C.phi, j, k, l, C.s0, C.s1, C.s2);
+		L.res[g] = p;
+		double v = ldg2(L.phi + g); v += p;
+		L.phi[g] = v;
+		acc += v;
+	}
+	double avg = S.allSum(acc)/(double)nt;
+	fGS(L, P.nPost, avg, S);
+	fNeutralize(L.phi, L.s0, L.s1, L.s2, S);
+}
+__device__ void fGhosts(double *v, int s0, int s1, int s2, Scope &S){
+	long n = (long)s0*s1*s2;
+	for(long i = S.tid(); i < n; i += S.nthr()){
+		int j = (int)(i % s0); long r = i / s0; int k = (int)(r % s1); int l = (int)(r / s1);
+		int jw = j == 0 ? s0-2 : (j == s0-1 ? 1 : j);
+		int kw = k == 0 ? s1-2 : (k == s1-1 ? 1 : k);
+		int lw = l == 0 ? s2-2 : (l == s2-1 ? 1 : l);
+		if(jw != j || kw != k || lw != l) v[i] = ldg2(v + ix(jw,kw,lw,s0,s1));
+	}
+}
+
+__global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
+	__shared__ double sh[18];
+	Scope Sg; Sg.single = false; Sg.bar = P.bar; Sg.partial = P.partial; Sg.flip = 0; Sg.sh = sh; Sg.gen = 0;
+	if(threadIdx.x == 0) Sg.gen = *((volatile unsigned*)&P.bar[1]);
+	Scope S1 = Sg; S1.single = true;
+	int b = P.nLevels - 1;
+	int qs = P.qSmall < 0 ? 0 : P.qSmall;
+	double barRes = 2.;
+	int cycles = 0;
+	while(barRes > P.tol && cycles < P.maxCycles){
+		for(int q = 0; q <= b && q < qs; q++){ if(q < b) fDown(P, q, Sg); else fBottom(P, Sg); }
+		if(qs <= b){
+			if(blockIdx.x == 0){
+				for(int q = qs; q < b; q++) fDown(P, q, S1);
+				fBottom(P, S1);
+				for(int q = b-1; q >= qs; q--) fUp(P, q, S1);
+			}
+			Sg.sync();
+		}
+		for(int q = (qs <= b ? qs : b) - 1; q >= 0; q--) fUp(P, q, Sg);
+		// mgSolveRaw :1700-1704: residual, square in place, true-grid sum, RMS
+		const Lvl &L = P.L[0];
+		int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2; long nt = (long)t0*t1*t2;
+		double acc = 0;
+		for(long i = Sg.tid(); i < nt; i += Sg.nthr()){
+			int j,k,l; truePoint(i,t0,t1,j,k,l);
+			double r = resPoint<true>(L.phi, L.rho, j, k, l, L.s0, L.s1, L.s2);
+			r = r*r;
+			L.res[ix(j,k,l,L.s0,L.s1)] = r;
+			acc += r;
+		}
+		barRes = Sg.allSum(acc);
+		barRes /= P.totTrue;
+		barRes = sqrt(barRes);
+		if(blockIdx.x == 0 && threadIdx.x == 0 && cycles < 250) P.hist[1+cycles] = barRes;
+		cycles++;
+	}
+	if(blockIdx.x == 0 && threadIdx.x == 0) P.hist[0] = (double)cycles;
+	for(int q = 0; q <= b; q++){
+		fGhosts(P.L[q].phi, P.L[q].s0, P.L[q].s1, P.L[q].s2, Sg);
+		fGhosts(P.L[q].rho, P.L[q].s0, P.L[q].s1, P.L[q].s2, Sg);
+		fGhosts(P.L[q].res, P.L[q].s0, P.L[q].s1, P.L[q].s2, Sg);
+	}
+}
+
+int g_mgMode = -1;             // -1: from $PINC_B200_MG at first use; 0 ops; 1 fused
+static void ensureHist(Ctx *c){
+	if(c->d_mgHist) return;
+	PINC_CUDA(cudaMalloc(&c->d_mgHist, 256*sizeof(double)));
+	PINC_CUDA(cudaMallocHost(&c->h_mgHist, 256*sizeof(double)));
+	c->h_mgHist[0] = 0;
+}
+
+static bool fusedEligible(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *m){
+	if(g_mgMode < 0){ const char *e = getenv("PINC_B200_MG"); g_mgMode = (e && !strcmp(e, "ops")) ? 0 : 1; }
+	if(!g_mgMode) return false;
+	if(m->mpiSize != 1) return false;
+	int nL = mgRho->nLevels;
+	if(nL < 2 || nL > MG_MAXLEV) return false;
+	for(int q = 0; q < nL; q++){
+		const Grid *g = mgRho->grids[q];
+		if(g->rank != 4) return false;
+		for(int d = 1; d < 4; d++){
+			if(g->trueSize[d] < 2 || (g->trueSize[d] & 1)) return false;
+			if(g->bnd[d] != PERIODIC || g->bnd[d+g->rank] != PERIODIC) return false;
+		}
+	}
+	(void)c; (void)mgPhi; (void)mgRes;
+	return true;
+}
+
+static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, double tol, int maxCycles){
+	MgPlan P{};
+	int nL = mgRho->nLevels;
+	P.nLevels = nL; P.nPre = mgRho->nPreSmooth; P.nPost = mgRho->nPostSmooth; P.nCoarse = mgRho->nCoarseSolve;
+	P.qSmall = nL;
+	double work = 0;
+	for(int q = 0; q < nL; q++){
+		DevGrid *r = devGrid(c, mgRho->grids[q]), *p = devGrid(c, mgPhi->grids[q]), *e = devGrid(c, mgRes->grids[q]);
+		if(r->n != p->n || r->n != e->n || r->nv != 1) fatal("multigrid level %d: rho/phi/res differ in shape", q);
+		P.L[q] = Lvl{ p->d, r->d, e->d, r->size[0], r->size[1], r->size[2] };
+		long nt = trueCount(r);
+		if(nt <= MG_SMALL && q < P.qSmall) P.qSmall = q;
+		if(nt > MG_SMALL) P.qSmall = nL;         // small levels must be a suffix
+		work += 24.0*nt*(q == nL-1 ? P.nCoarse : P.nPre + P.nPost) + 50.0*nt;
+	}
+	// recompute the suffix of small levels properly
+	P.qSmall = nL;
+	for(int q = nL-1; q >= 0; q--){ if(trueCount(devGrid(c, mgRho->grids[q])) <= MG_SMALL) P.qSmall = q; else break; }
+	P.tol = tol; P.maxCycles = maxCycles;
+	DevGrid *r0 = devGrid(c, mgRho->grids[0]);
+	P.totTrue = (double)trueCount(r0);
+	int grid = P.qSmall == 0 ? 1 : c->numSMs;
+	P.partial = partialBuffer(c, 2L*grid);
+	P.bar = c->d_bar;
+	ensureHist(c);
+	P.hist = c->d_mgHist;
+	void *args[] = { &P };
+	{
+		LaunchScope ls(c, K_MGFUSED, work);
+		PINC_CUDA(cudaLaunchCooperativeKernel((void*)k_mg_solve, dim3(grid), dim3(MG_BLOCK), args, 0, c->stream));
+	}
+	PINC_CUDA(cudaMemcpyAsync(c->h_mgHist, c->d_mgHist, 256*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	c->mgHistPending = true;
+}
+
+static void opsSolve(Ctx *c, funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *m, double tol, int maxCycles){
+	int bottom = mgRho->nLevels - 1;
+	(void)mgAlgo;
+	c->mgHistory.clear();
+	c->mgHistPending = false;
+	if(mgRho->nLevels > 1){
+		DevGrid *res = devGrid(c, mgRes->grids[0]), *rho = devGrid(c, mgRho->grids[0]), *phi = devGrid(c, mgPhi->grids[0]);
+		double barRes = 2.;
+		int cycles = 0;
+		while(barRes > tol && cycles < maxCycles){
+			opVCycle(c, 0, bottom, 0, mgRho, mgPhi, mgRes, m);
+			opResidual(c, res, rho, phi);
+			gridHalo(c, res, m, 0, 0);
+			gridSumTrue(c, res, 1, nullptr, 3);
+			if(m->mpiSize > 1) c->tp->allreduceSum(c, c->d_scal + 3, 1);
+			barRes = readScalar(c, 3);
+			barRes /= (double)gTotTruesize(mgRho->grids[0], m);
+			barRes = sqrt(barRes);
+			c->mgHistory.push_back(barRes);
+			cycles++;
+		}
+	} else {
+		DevGrid *rho = devGrid(c, mgRho->grids[0]), *phi = devGrid(c, mgPhi->grids[0]);
+		for(int cyc = 0; cyc < mgRho->nMGCycles; cyc++){
+			gridHalo(c, rho, m, 0, 0);
+			gridNeutralize(c, rho, m);
+			opGS(c, phi, rho, mgRho->nCoarseSolve, m);
+		}
+	}
+}
+
+void mgForgetPlans(Ctx *c){ (void)c; }
+
+} // namespace pinc
+
+using namespace pinc;
+
+extern "C" {
+
+void mgGS3D(Grid *phi, const Grid *rho, int nCycles, const MpiInfo *mpiInfo){
+	Ctx *c = cur(); opGS(c, devGrid(c, phi), devGrid(c, rho), nCycles, mpiInfo);
+}
+void mgResidual(Grid *res, const Grid *rho, const Grid *phi, const MpiInfo *mpiInfo){
+	(void)mpiInfo; Ctx *c = cur(); opResidual(c, devGrid(c, res), devGrid(c, rho), devGrid(c, phi));
+}
+void mgHalfRestrict3D(const Grid *fine, Grid *coarse){ Ctx *c = cur(); opRestrict(c, devGrid(c, fine), devGrid(c, coarse)); }
+void mgBilinProl3D(Grid *fine, const Grid *coarse, const MpiInfo *mpiInfo){ Ctx *c = cur(); opProlong(c, devGrid(c, fine), devGrid(c, coarse), mpiInfo); }
+double mgSumTrueSquared(Grid *error, const MpiInfo *mpiInfo){
+	Ctx *c = cur();
+	gridSumTrue(c, devGrid(c, error), 1, nullptr, 3);
+	if(mpiInfo->mpiSize > 1) c->tp->allreduceSum(c, c->d_scal + 3, 1);
+	return readScalar(c, 3);
+}
+
+static void checkPlugins(const Multigrid *mg){
+	if(mg->nLevels < 1) fatal("multigrid: nLevels < 1");
+	if((mg->coarseSolv && mg->coarseSolv != mgGS3D) || (mg->preSmooth && mg->preSmooth != mgGS3D) || (mg->postSmooth && mg->postSmooth != mgGS3D))
+		fatal("multigrid: only the gaussSeidelRB smoother (mgGS3D) is implemented");
+	if((mg->restrictor && mg->restrictor != mgHalfRestrict3D) || (mg->prolongator && mg->prolongator != mgBilinProl3D))
+		fatal("multigrid: only halfWeight restriction and bilinear prolongation are implemented");
+}
+
+void mgVRecursive(int level, int bottom, int top, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *mpiInfo){
+	checkPlugins(mgRho);
+	opVCycle(cur(), level, bottom, top, mgRho, mgPhi, mgRes, mpiInfo);
+}
+
+void mgSolveRaw(funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *mpiInfo){
+	if(mgAlgo && mgAlgo != (funPtr)mgVRecursive) fatal("multigrid: only cycle = mgVRecursive is implemented");
+	checkPlugins(mgRho);
+	Ctx *c = cur();
+	const double tol = 1.E-10;                       // src/multigrid.c:1695
+	const int maxCycles = 200;                       // the reference has no bound; this one reports instead of hanging
+	if(fusedEligible(c, mgRho, mgPhi, mgRes, mpiInfo)) fusedSolve(c, mgRho, mgPhi, mgRes, tol, maxCycles);
+	else opsSolve(c, mgAlgo, mgRho, mgPhi, mgRes, mpiInfo, tol, maxCycles);
+}
+
+void mgSolve(const MultigridSolver *solver, const Grid *rho, const Grid *phi, const MpiInfo *mpiInfo){
+	(void)rho; (void)phi;                            // as the reference: the grids captured at allocation are used
+	mgSolveRaw(solver->mgAlgo, solver->mgRho, solver->mgPhi, solver->mgRes, mpiInfo);
+}
+
+void mgSolver(void (**solve)(), MultigridSolver *(**solverAlloc)(), void (**solverFree)()){
+	*solve = (void(*)())mgSolve;
+	*solverAlloc = (MultigridSolver*(*)())pincMgAllocSolver;
+	*solverFree = (void(*)())mgFreeSolver;
+}
+
+void pincMgSetMode(int fused){ pinc::g_mgMode = fused ? 1 : 0; }
+
+int pincMgLastHistory(double *barRes, int cap){
+	Ctx *c = cur();
+	if(c->mgHistPending){
+		streamSync(c);
+		int n = (int)c->h_mgHist[0];
+		c->mgHistory.assign(c->h_mgHist + 1, c->h_mgHist + 1 + (n < 250 ? n : 250));
+		c->mgHistPending = false;
+		if(n >= 200) fprintf(stderr, "PINC-B200 WARNING: multigrid did not reach the tolerance in %d V-cycles\n", n);
+	}
+	int n = (int)c->mgHistory.size();
+	for(int i = 0; i < n && i < cap; i++) barRes[i] = c->mgHistory[i];
+	return n;
+}
+
+} // extern "C"

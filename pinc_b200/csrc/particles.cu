@@ -1,0 +1,631 @@
+// particles.cu — particle kernels and the PINC pusher entry points (src/pusher.h).
+//
+// Device layout: structure of arrays, six planes x,y,z,vx,vy,vz of `cap` doubles (the host keeps the
+// reference's AoS pos[3i+d] / vel[3i+d]; conversion happens in pincSyncPop*).  Species s lives in
+// [iStart[s], iStop[s]) of every plane, exactly as in src/core.h:72-86.
+//
+// Cell binning.  puExtractEmigrants3D is a counting sort of every species by the key
+//     key = cell index  j + nc0*(k + nc1*l)        for particles that stay,
+//     key = nCells + ne                            for emigrants to neighbour ne (src/pusher.c:819-826),
+// so that afterwards (i) the stayers are contiguous and ordered by cell, (ii) the emigrants sit behind
+// iStop[s] packed neighbour by neighbour (the in-GPU compaction for migrants), and (iii) cellStart[]
+// gives every cell's particle range.  The accelerator then reads E with warp-uniform addresses and the
+// deposition runs one warp per cell with no per-particle atomics.
+//
+// Deposition is deterministic: each trilinear weight w in [0,1] is accumulated as round(w*2^46) in a
+// 64-bit integer (warp butterfly per cell, then one integer RED per node), so the sum is exact and
+// independent of particle order; the integer grid is converted to fp64 in the reference's order of
+// operations (src/pusher.c:514,522,568: rho = (rho*(1/q) + sum w)*q per species).
+//
+// All arithmetic that reaches particle state follows the reference's expression order and the library is
+// compiled with -fmad=false (the reference's x86 build has no FMA contraction).
+#include "common.h"
+
+namespace pinc {
+
+struct Thr { double lo[3], up[3]; };
+struct CellSpace { int nc0, nc1, nc2; long nCells; };
+
+__device__ __forceinline__ unsigned classify(double x, double y, double z, const Thr &T, const CellSpace &C, int *flags){
+	int nx = -(x < T.lo[0]) + (x >= T.up[0]);
+	int ny = -(y < T.lo[1]) + (y >= T.up[1]);
+	int nz = -(z < T.lo[2]) + (z >= T.up[2]);
+	int ne = 13 + nx + 3*ny + 9*nz;
+	if(ne != 13) return (unsigned)(C.nCells + ne);
+	int j = (int)x, k = (int)y, l = (int)z;
+	if(j < 0 || j >= C.nc0 || k < 0 || k >= C.nc1 || l < 0 || l >= C.nc2 || !(x >= 0) || !(y >= 0) || !(z >= 0)){
+		atomicOr(flags, ERR_POS_RANGE);
+		j = min(max(j,0),C.nc0-1); k = min(max(k,0),C.nc1-1); l = min(max(l,0),C.nc2-1);
+	}
+	return (unsigned)(j + C.nc0*(k + (long)C.nc1*l));
+}
+
+// all 32 lanes call; lanes with the same key add once
+__device__ __forceinline__ void histAdd(unsigned *hist, unsigned key, bool act){
+	unsigned k = act ? key : 0xffffffffu;
+	unsigned peers = __match_any_sync(0xffffffffu, k);
+	int lane = threadIdx.x & 31;
+	if(act && lane == __ffs(peers)-1) atomicAdd(&hist[key], (unsigned)__popc(peers));
+}
+
+template<int BLOCK> __device__ __forceinline__ double blockSumP(double v){
+	__shared__ double sh[BLOCK/32];
+	for(int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+	int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if(lane == 0) sh[w] = v;
+	__syncthreads();
+	if(w == 0){
+		v = lane < BLOCK/32 ? sh[lane] : 0.0;
+		for(int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+	}
+	return v;
+}
+__global__ void k_final_sum_p(const double *__restrict__ partial, int n, double *__restrict__ out){
+	double acc = 0;
+	for(int i = threadIdx.x; i < n; i += 256) acc += partial[i];
+	acc = blockSumP<256>(acc);
+	if(threadIdx.x == 0) out[0] = acc;
+}
+
+// ---- move (src/pusher.c:86-119, quirk Q4: pos += vel) -------------------------------------------
+__global__ void k_move(double *__restrict__ p, const double *__restrict__ v, long cap, long a, long n){
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; i < n; i += st){
+		long q = a + i;
+		p[q] += v[q]; p[q+cap] += v[q+cap]; p[q+2*cap] += v[q+2*cap];
+	}
+}
+
+// ---- accelerate (src/pusher.c:147-214, 394-483) with the interpolation of :1089-1122 embedded -----
+// KIND 0: leapfrog kick; 1: Boris (half kick, rotation by T then S of THIS particle's velocity, half kick).
+// FUSE 1: also pos += vel (the next step's puMove) and classification of the new position into the sort key.
+struct BorisPar { double T[3], S[3]; };
+template<int KIND, int KE, int FUSE>
+__global__ void __launch_bounds__(256) k_acc(double *__restrict__ P, long cap, long a, long n,
+		const double *__restrict__ E, long sx3, long sxy3, int gs0, int gs1, int gs2, BorisPar B, double *__restrict__ partial,
+		Thr T, CellSpace C, unsigned *__restrict__ keys, unsigned *__restrict__ hist, int *flags){
+	double acc = 0;
+	long stride = (long)gridDim.x*blockDim.x;
+	for(long base = blockIdx.x*(long)blockDim.x; base < n; base += stride){
+		long i = base + threadIdx.x;
+		bool act = i < n;
+		unsigned key = 0;
+		if(act){
+			long q = a + i;
+			double x = P[q], y = P[q+cap], z = P[q+2*cap];
+			double vx = P[q+3*cap], vy = P[q+4*cap], vz = P[q+5*cap];
+			int j = (int)x, k = (int)y, l = (int)z;
+			if(!(x >= 0) || !(y >= 0) || !(z >= 0) || j > gs0-2 || k > gs1-2 || l > gs2-2){
+				atomicOr(flags, ERR_POS_RANGE);          // not migrated: the reference would read out of bounds
+				j = min(max(j,0),gs0-2); k = min(max(k,0),gs1-2); l = min(max(l,0),gs2-2);
+			}
+			double xf = x-j, yf = y-k, zf = z-l;
+			double xc = 1-xf, yc = 1-yf, zc = 1-zf;
+			long p000 = 3L*j + k*sx3 + l*sxy3;
+			const double *e0 = E + p000, *e1 = e0 + sx3, *e2 = e0 + sxy3, *e3 = e2 + sx3;
+			double dv[3];
+			#pragma unroll
+			for(int v = 0; v < 3; v++)
+				dv[v] = zc*( yc*(xc*__ldg(e0+v)+xf*__ldg(e0+3+v)) + yf*(xc*__ldg(e1+v)+xf*__ldg(e1+3+v)) )
+				      + zf*( yc*(xc*__ldg(e2+v)+xf*__ldg(e2+3+v)) + yf*(xc*__ldg(e3+v)+xf*__ldg(e3+3+v)) );
+			if(KIND == 0){
+				if(KE){
+					double v2 = 0;
+					v2 += vx*(vx+dv[0]); v2 += vy*(vy+dv[1]); v2 += vz*(vz+dv[2]);
+					acc += v2;
+				}
+				vx += dv[0]; vy += dv[1]; vz += dv[2];
+			} else {
+				vx += 0.5*dv[0]; vy += 0.5*dv[1]; vz += 0.5*dv[2];
+				double px = vx, py = vy, pz = vz;
+				px +=  (vy*B.T[2]-vz*B.T[1]); py += -(vx*B.T[2]-vz*B.T[0]); pz +=  (vx*B.T[1]-vy*B.T[0]);
+				vx +=  (py*B.S[2]-pz*B.S[1]); vy += -(px*B.S[2]-pz*B.S[0]); vz +=  (px*B.S[1]-py*B.S[0]);
+				if(KE){ double v2 = 0; v2 += vx*vx; v2 += vy*vy; v2 += vz*vz; acc += v2; }
+				vx += 0.5*dv[0]; vy += 0.5*dv[1]; vz += 0.5*dv[2];
+			}
+			P[q+3*cap] = vx; P[q+4*cap] = vy; P[q+5*cap] = vz;
+			if(FUSE){
+				x += vx; y += vy; z += vz;
+				P[q] = x; P[q+cap] = y; P[q+2*cap] = z;
+				key = classify(x, y, z, T, C, flags);
+				keys[q] = key;
+			}
+		}
+		if(FUSE) histAdd(hist, key, act);
+	}
+	if(KE){
+		acc = blockSumP<256>(acc);
+		if(threadIdx.x == 0) partial[blockIdx.x] = acc;
+	}
+}
+
+// ---- classification + histogram of the current positions ------------------------------------------
+__global__ void __launch_bounds__(256) k_keys(const double *__restrict__ P, long cap, long a, long n, Thr T, CellSpace C,
+		unsigned *__restrict__ keys, unsigned *__restrict__ hist, int *flags){
+	long stride = (long)gridDim.x*blockDim.x;
+	for(long base = blockIdx.x*(long)blockDim.x; base < n; base += stride){
+		long i = base + threadIdx.x;
+		bool act = i < n;
+		unsigned key = 0;
+		if(act){
+			long q = a + i;
+			key = classify(P[q], P[q+cap], P[q+2*cap], T, C, flags);
+			keys[q] = key;
+		}
+		histAdd(hist, key, act);
+	}
+}
+
+// ---- exclusive scan of the histogram (in place; element n receives the total) -----------------------
+#define SCAN_CH 4096
+__global__ void __launch_bounds__(256) k_scan_block(unsigned *__restrict__ h, long n, unsigned *__restrict__ blockSums){
+	__shared__ unsigned sh[256];
+	long base = (long)blockIdx.x*SCAN_CH + threadIdx.x*16;
+	unsigned v[16], sum = 0;
+	#pragma unroll
+	for(int i = 0; i < 16; i++){ long g = base + i; v[i] = g < n ? h[g] : 0u; sum += v[i]; }
+	sh[threadIdx.x] = sum;
+	__syncthreads();
+	for(int o = 1; o < 256; o <<= 1){
+		unsigned t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
+		__syncthreads();
+		sh[threadIdx.x] += t;
+		__syncthreads();
+	}
+	unsigned run = sh[threadIdx.x] - sum;            // exclusive prefix of this thread inside the chunk
+	#pragma unroll
+	for(int i = 0; i < 16; i++){ long g = base + i; if(g < n) h[g] = run; run += v[i]; }
+	if(threadIdx.x == 255) blockSums[blockIdx.x] = sh[255];
+}
+__global__ void k_scan_sums(unsigned *__restrict__ s, int nb){
+	__shared__ unsigned sh[1024];
+	__shared__ unsigned carry;
+	if(threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for(int b0 = 0; b0 < nb; b0 += 1024){
+		int i = b0 + threadIdx.x;
+		unsigned v = i < nb ? s[i] : 0u;
+		sh[threadIdx.x] = v;
+		__syncthreads();
+		for(int o = 1; o < 1024; o <<= 1){
+			unsigned t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
+			__syncthreads();
+			sh[threadIdx.x] += t;
+			__syncthreads();
+		}
+		if(i < nb) s[i] = carry + sh[threadIdx.x] - v;
+		__syncthreads();
+		if(threadIdx.x == 1023) carry += sh[1023];
+		__syncthreads();
+	}
+}
+__global__ void k_scan_add(unsigned *__restrict__ h, long n, const unsigned *__restrict__ blockSums){
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x;
+	if(i < n) h[i] += blockSums[i / SCAN_CH];
+}
+
+// ---- scatter into cell order ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scatter(const double *__restrict__ src, double *__restrict__ dst, long cap, long a, long n,
+		const unsigned *__restrict__ keys, const unsigned *__restrict__ off, unsigned *__restrict__ cursor){
+	long stride = (long)gridDim.x*blockDim.x;
+	int lane = threadIdx.x & 31;
+	for(long base = blockIdx.x*(long)blockDim.x; base < n; base += stride){
+		long i = base + threadIdx.x;
+		bool act = i < n;
+		unsigned key = act ? keys[a+i] : 0xffffffffu;
+		unsigned peers = __match_any_sync(0xffffffffu, key);
+		int leader = __ffs(peers)-1;
+		unsigned b = 0;
+		if(act && lane == leader) b = atomicAdd(&cursor[key], (unsigned)__popc(peers));
+		b = __shfl_sync(0xffffffffu, b, leader);
+		if(act){
+			long d = a + off[key] + b + __popc(peers & ((1u<<lane)-1u));
+			long q = a + i;
+			#pragma unroll
+			for(int w = 0; w < 6; w++) dst[d + w*cap] = src[q + w*cap];
+		}
+	}
+}
+
+// ---- deposition (src/pusher.c:512-572) -----------------------------------------------------------------
+__device__ __forceinline__ long long fixw(double w){ return __double2ll_rn(w*(double)(1LL<<PINC_FIX_BITS)); }
+
+// sorted prefix: one warp per cell
+__global__ void __launch_bounds__(256) k_distr_cells(const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ Z,
+		const unsigned *__restrict__ cs, CellSpace C, long sx, long sxy, long long *__restrict__ fix){
+	int lane = threadIdx.x & 31;
+	long warp = (blockIdx.x*(long)blockDim.x + threadIdx.x) >> 5;
+	long nWarps = ((long)gridDim.x*blockDim.x) >> 5;
+	for(long c = warp; c < C.nCells; c += nWarps){
+		unsigned b = cs[c], e = cs[c+1];
+		if(b == e) continue;
+		long long a[8];
+		#pragma unroll
+		for(int q = 0; q < 8; q++) a[q] = 0;
+		for(unsigned i = b + lane; i < e; i += 32){
+			double x = X[i], y = Y[i], z = Z[i];
+			int j = (int)x, k = (int)y, l = (int)z;
+			double xf = x-j, yf = y-k, zf = z-l;
+			double xc = 1-xf, yc = 1-yf, zc = 1-zf;
+			double cc = xc*yc, fc = xf*yc, cf = xc*yf, ff = xf*yf;
+			a[0] += fixw(cc*zc); a[1] += fixw(fc*zc); a[2] += fixw(cf*zc); a[3] += fixw(ff*zc);
+			a[4] += fixw(cc*zf); a[5] += fixw(fc*zf); a[6] += fixw(cf*zf); a[7] += fixw(ff*zf);
+		}
+		// transposing butterfly: 8 values x 32 lanes -> one total per corner in 9 64-bit shuffles
+		bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
+		#pragma unroll
+		for(int q = 0; q < 4; q++){
+			long long send = u16 ? a[q] : a[q+4], keep = u16 ? a[q+4] : a[q];
+			a[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+		}
+		#pragma unroll
+		for(int q = 0; q < 2; q++){
+			long long send = u8 ? a[q] : a[q+2], keep = u8 ? a[q+2] : a[q];
+			a[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+		}
+		{
+			long long send = u4 ? a[0] : a[1], keep = u4 ? a[1] : a[0];
+			a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+		}
+		a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
+		a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+		if((lane & 3) == 0 && a[0] != 0){
+			int cj = (int)(c % C.nc0); long r = c / C.nc0; int ck = (int)(r % C.nc1); int cl = (int)(r / C.nc1);
+			long node = cj + sx*ck + sxy*cl + (u4 ? 1 : 0) + (u8 ? sx : 0) + (u16 ? sxy : 0);
+			atomicAdd((unsigned long long*)&fix[node], (unsigned long long)a[0]);
+		}
+	}
+}
+// unsorted tail (immigrants appended by puMigrate, or a population that was never binned)
+__global__ void __launch_bounds__(256) k_distr_tail(const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ Z,
+		long n, int s0, int s1, int s2, long long *__restrict__ fix, int *flags){
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	long sx = s0, sxy = (long)s0*s1;
+	for(; i < n; i += st){
+		double x = X[i], y = Y[i], z = Z[i];
+		int j = (int)x, k = (int)y, l = (int)z;
+		if(!(x >= 0) || !(y >= 0) || !(z >= 0) || j > s0-2 || k > s1-2 || l > s2-2){ atomicOr(flags, ERR_POS_RANGE); continue; }
+		double xf = x-j, yf = y-k, zf = z-l;
+		double xc = 1-xf, yc = 1-yf, zc = 1-zf;
+		double cc = xc*yc, fc = xf*yc, cf = xc*yf, ff = xf*yf;
+		unsigned long long *f = (unsigned long long*)fix + (j + sx*k + sxy*l);
+		atomicAdd(f,          (unsigned long long)fixw(cc*zc));
+		atomicAdd(f+1,        (unsigned long long)fixw(fc*zc));
+		atomicAdd(f+sx,       (unsigned long long)fixw(cf*zc));
+		atomicAdd(f+sx+1,     (unsigned long long)fixw(ff*zc));
+		atomicAdd(f+sxy,      (unsigned long long)fixw(cc*zf));
+		atomicAdd(f+sxy+1,    (unsigned long long)fixw(fc*zf));
+		atomicAdd(f+sxy+sx,   (unsigned long long)fixw(cf*zf));
+		atomicAdd(f+sxy+sx+1, (unsigned long long)fixw(ff*zf));
+	}
+}
+// rho = (rho*(1/q) + sum w)*q, and the integer grid is cleared for the next species
+__global__ void k_distr_finalize(double *__restrict__ rho, long long *__restrict__ fix, long n, double invq, double q){
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	const double inv = 1.0/(double)(1LL<<PINC_FIX_BITS);
+	for(; i < n; i += st){
+		double r = rho[i];
+		r *= invq;
+		r += (double)fix[i]*inv;
+		r *= q;
+		rho[i] = r;
+		fix[i] = 0;
+	}
+}
+
+// ---- migrants --------------------------------------------------------------------------------------------
+struct PackPar { long srcOff[28]; long dstOff[27]; };     // per neighbour: first emigrant (relative), first record
+__global__ void k_pack_emigrants(const double *__restrict__ P, long cap, long a, long n, PackPar pp, double *__restrict__ out){
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; i < n; i += st){
+		long r = pp.srcOff[0] + i;
+		int ne = 0;
+		while(ne < 26 && r >= pp.srcOff[ne+1]) ne++;
+		long d = pp.dstOff[ne] + (r - pp.srcOff[ne]);
+		long q = a + r;
+		#pragma unroll
+		for(int w = 0; w < 6; w++) out[6*d + w] = P[q + w*cap];
+	}
+}
+struct ImportPar { long srcOff[27]; long cnt[27]; double shift[27][3]; };
+__global__ void k_import(double *__restrict__ P, long cap, long dst0, long n, ImportPar ip, const double *__restrict__ in){
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; i < n; i += st){
+		long r = i; int ne = 0;
+		while(ne < 26 && r >= ip.cnt[ne]){ r -= ip.cnt[ne]; ne++; }
+		const double *rec = in + 6*(ip.srcOff[ne] + r);
+		long q = dst0 + i;
+		#pragma unroll
+		for(int w = 0; w < 3; w++){ double v = rec[w]; v += ip.shift[ne][w]; P[q + w*cap] = v; }
+		#pragma unroll
+		for(int w = 3; w < 6; w++) P[q + w*cap] = rec[w];
+	}
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+static inline int pGrid(Ctx *c, long n){ return gridFor(n, 256, c->numSMs*8); }
+
+static Thr thrOf(const MpiInfo *m){
+	Thr T;
+	for(int d = 0; d < 3; d++){ T.lo[d] = m->thresholds[d]; T.up[d] = m->thresholds[3+d]; }
+	return T;
+}
+// the cell space every non-emigrant position falls into: 0 <= lower threshold, x < upper threshold <= nc
+static void setupCells(Ctx *c, DevPop *dp, const MpiInfo *m){
+	int nc[3];
+	for(int d = 0; d < 3; d++){
+		if(m->thresholds[d] < 0) fatal("negative lower migration threshold");
+		nc[d] = (int)ceil(m->thresholds[3+d]);
+		if(nc[d] < 1) nc[d] = 1;
+	}
+	long nCells = (long)nc[0]*nc[1]*nc[2];
+	if(nCells + 28 >= 0xffffffffL) fatal("cell space too large for 32-bit keys");
+	if(dp->nCells == nCells && dp->nc[0] == nc[0] && dp->nc[1] == nc[1] && dp->d_hist[0]) return;
+	streamSync(c);
+	for(int s = 0; s < dp->nS; s++){
+		if(dp->d_hist[s]) cudaFree(dp->d_hist[s]);
+		if(dp->d_cursor[s]) cudaFree(dp->d_cursor[s]);
+		PINC_CUDA(cudaMalloc(&dp->d_hist[s], (size_t)(nCells+28)*sizeof(unsigned)));
+		PINC_CUDA(cudaMalloc(&dp->d_cursor[s], (size_t)(nCells+28)*sizeof(unsigned)));
+		dp->sortedN[s] = 0;
+	}
+	for(int d = 0; d < 3; d++) dp->nc[d] = nc[d];
+	dp->nCells = nCells;
+	dp->keysValid = false;
+}
+static CellSpace cellsOf(const DevPop *dp){ return CellSpace{ dp->nc[0], dp->nc[1], dp->nc[2], dp->nCells }; }
+
+static void invalidateOrder(DevPop *dp){
+	for(int s = 0; s < dp->nS; s++) dp->sortedN[s] = 0;
+	dp->keysValid = false;
+}
+
+enum AccKind { ACC_LEAP = 0, ACC_BORIS = 1 };
+static void accelerate(Ctx *c, Population *pop, Grid *Egrid, int kind, int ke, const double *T, const double *S, const MpiInfo *fuse){
+	DevPop *dp = devPop(c, pop);
+	DevGrid *E = devGrid(c, Egrid);
+	if(E->nv != 3) fatal("accelerator needs a 3-vector field grid");
+	long sx3 = 3L*E->size[0], sxy3 = sx3*E->size[1];
+	Thr thr{}; CellSpace C{1,1,1,1};
+	if(fuse){
+		setupCells(c, dp, fuse);
+		thr = thrOf(fuse); C = cellsOf(dp);
+		for(int s = 0; s < dp->nS; s++)
+			PINC_CUDA(cudaMemsetAsync(dp->d_hist[s], 0, (size_t)(dp->nCells+28)*sizeof(unsigned), c->stream));
+	}
+	int maxBlocks = 0;
+	for(int s = 0; s < dp->nS; s++){ int b = pGrid(c, pop->iStop[s]-pop->iStart[s]); if(b > maxBlocks) maxBlocks = b; }
+	double *partial = ke ? partialBuffer(c, (long)maxBlocks*dp->nS) : nullptr;
+	for(int s = 0; s < dp->nS; s++){
+		long a = pop->iStart[s], n = pop->iStop[s] - a;
+		// the reference rescales the whole field by q/m and back for every species (quirk Q2); same here
+		gridScale(c, E, pop->charge[s]/pop->mass[s]);
+		BorisPar B{};
+		if(kind == ACC_BORIS) for(int d = 0; d < 3; d++){ B.T[d] = T[3*s+d]; B.S[d] = S[3*s+d]; }
+		int blocks = pGrid(c, n);
+		double *part = ke ? partial + (long)s*maxBlocks : nullptr;
+		if(n > 0){
+			double bytes = (fuse ? 100.0 : 72.0)*n;
+#define ACC_LAUNCH(K,KEE,F) PINC_LAUNCH(c, K_PUSH, bytes, (k_acc<K,KEE,F><<<blocks,256,0,c->stream>>>(dp->base, dp->cap, a, n, E->d, sx3, sxy3, E->size[0], E->size[1], E->size[2], B, part, thr, C, dp->d_keys, fuse ? dp->d_hist[s] : nullptr, c->d_flags)))
+			if(kind == ACC_LEAP){
+				if(ke){ if(fuse) ACC_LAUNCH(0,1,1); else ACC_LAUNCH(0,1,0); }
+				else  { if(fuse) ACC_LAUNCH(0,0,1); else ACC_LAUNCH(0,0,0); }
+			} else {
+				if(ke){ if(fuse) ACC_LAUNCH(1,1,1); else ACC_LAUNCH(1,1,0); }
+				else  { if(fuse) ACC_LAUNCH(1,0,1); else ACC_LAUNCH(1,0,0); }
+			}
+#undef ACC_LAUNCH
+		}
+		if(ke) PINC_LAUNCH(c, K_REDUCE, 8.0*blocks, (k_final_sum_p<<<1,256,0,c->stream>>>(part, n > 0 ? blocks : 0, c->d_scal + 16 + s)));
+		gridScale(c, E, pop->mass[s]/pop->charge[s]);
+	}
+	if(fuse){
+		for(int s = 0; s < dp->nS; s++) dp->sortedN[s] = 0;
+		dp->keysValid = true;
+		for(int d = 0; d < 6; d++) dp->keyThr[d] = fuse->thresholds[d];
+	}
+	if(ke){
+		PINC_CUDA(cudaMemcpyAsync(c->h_scal + 16, c->d_scal + 16, dp->nS*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		streamSync(c);
+		for(int s = 0; s < dp->nS; s++){
+			pop->kinEnergy[s] = c->h_scal[16+s];
+			pop->kinEnergy[s] *= 0.5*pop->mass[s];
+		}
+	}
+}
+
+static void scanHist(Ctx *c, unsigned *h, long n /* entries incl. the total slot */){
+	int nb = (int)((n + SCAN_CH - 1)/SCAN_CH);
+	unsigned *sums = (unsigned*)tmpBuffer(c, (size_t)nb*sizeof(unsigned));
+	PINC_LAUNCH(c, K_SORT, 8.0*n, (k_scan_block<<<nb,256,0,c->stream>>>(h, n, sums)));
+	PINC_LAUNCH(c, K_SORT, 8.0*nb, (k_scan_sums<<<1,1024,0,c->stream>>>(sums, nb)));
+	PINC_LAUNCH(c, K_SORT, 8.0*n, (k_scan_add<<<(unsigned)((n+255)/256),256,0,c->stream>>>(h, n, sums)));
+}
+
+} // namespace pinc
+
+using namespace pinc;
+
+extern "C" {
+
+void puMove(Population *pop, Object *obj){
+	(void)obj;
+	Ctx *c = cur(); DevPop *dp = devPop(c, pop);
+	for(int s = 0; s < dp->nS; s++){
+		long a = pop->iStart[s], n = pop->iStop[s] - a;
+		if(n > 0) PINC_LAUNCH(c, K_MOVE, 72.0*n, (k_move<<<pGrid(c,n),256,0,c->stream>>>(dp->base, dp->base + 3*dp->cap, dp->cap, a, n)));
+	}
+	invalidateOrder(dp);
+}
+
+void puAcc3D1(Population *pop, Grid *E){ accelerate(cur(), pop, E, ACC_LEAP, 0, nullptr, nullptr, nullptr); }
+void puAcc3D1KE(Population *pop, Grid *E){ accelerate(cur(), pop, E, ACC_LEAP, 1, nullptr, nullptr, nullptr); }
+// Quirk Q3: the reference rotates particle 0's velocity for every particle; this implements the Boris
+// rotation of each particle's own velocity (identical for BExt = 0, which every BASELINE config has).
+void puBoris3D1(Population *pop, Grid *E, const double *T, const double *S){ accelerate(cur(), pop, E, ACC_BORIS, 0, T, S, nullptr); }
+void puBoris3D1KE(Population *pop, Grid *E, const double *T, const double *S){ accelerate(cur(), pop, E, ACC_BORIS, 1, T, S, nullptr); }
+void pincAccMove3D1KE(Population *pop, Grid *E, MpiInfo *mpiInfo){ accelerate(cur(), pop, E, ACC_LEAP, 1, nullptr, nullptr, mpiInfo); }
+
+// src/pusher.c:485-505
+void pincGet3DRotationParameters(int nSpecies, const double *BExt, const double *charge, const double *mass, double *T, double *S){
+	for(int s = 0; s < nSpecies; s++){
+		double factor = 0.5*charge[s]/mass[s];
+		double denom = 1;
+		for(int p = 0; p < 3; p++){ T[3*s+p] = factor*BExt[p]; denom += T[3*s+p]*T[3*s+p]; }
+		double mul = 2.0/denom;
+		for(int p = 0; p < 3; p++) S[3*s+p] = mul*T[3*s+p];
+	}
+}
+
+// src/pusher.c:782-855 as a counting sort (see the header comment)
+void puExtractEmigrants3D(Population *pop, MpiInfo *mpiInfo){
+	Ctx *c = cur(); DevPop *dp = devPop(c, pop);
+	if(dp->extracted) fatal("puExtractEmigrants3D called twice without puMigrate");
+	setupCells(c, dp, mpiInfo);
+	if(dp->keysValid) for(int d = 0; d < 6; d++) if(dp->keyThr[d] != mpiInfo->thresholds[d]) dp->keysValid = false;
+	if(!dp->alt) PINC_CUDA(cudaMalloc(&dp->alt, (size_t)6*(dp->cap > 0 ? dp->cap : 1)*sizeof(double)));
+	Thr thr = thrOf(mpiInfo); CellSpace C = cellsOf(dp);
+	long nKeys = dp->nCells + 27;
+	int nS = dp->nS;
+	for(int s = 0; s < nS; s++){
+		long a = pop->iStart[s], n = pop->iStop[s] - a;
+		if(!dp->keysValid){
+			PINC_CUDA(cudaMemsetAsync(dp->d_hist[s], 0, (size_t)(nKeys+1)*sizeof(unsigned), c->stream));
+			if(n > 0) PINC_LAUNCH(c, K_EXTRACT, 28.0*n, (k_keys<<<pGrid(c,n),256,0,c->stream>>>(dp->base, dp->cap, a, n, thr, C, dp->d_keys, dp->d_hist[s], c->d_flags)));
+		}
+		scanHist(c, dp->d_hist[s], nKeys+1);
+		PINC_CUDA(cudaMemsetAsync(dp->d_cursor[s], 0, (size_t)nKeys*sizeof(unsigned), c->stream));
+		if(n > 0) PINC_LAUNCH(c, K_SORT, 100.0*n, (k_scatter<<<pGrid(c,n),256,0,c->stream>>>(dp->base, dp->alt, dp->cap, a, n, dp->d_keys, dp->d_hist[s], dp->d_cursor[s])));
+		// offsets of the 27 emigrant bins + total: 28 values
+		PINC_CUDA(cudaMemcpyAsync(c->h_long + 32*s, dp->d_hist[s] + dp->nCells, 28*sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+	}
+	std::swap(dp->base, dp->alt);
+	streamSync(c);
+	checkDeviceFlags(c, "puExtractEmigrants3D");
+	for(int s = 0; s < nS; s++){
+		const unsigned *o = (const unsigned*)(c->h_long + 32*s);
+		long n = pop->iStop[s] - pop->iStart[s];
+		if((long)o[27] != n) fatal("puExtractEmigrants3D: histogram total %u != %ld particles of species %d", o[27], n, s);
+		for(int ne = 0; ne < 27; ne++) mpiInfo->nEmigrants[ne*nS+s] = (long)o[ne+1] - (long)o[ne];
+		dp->sortedN[s] = o[0];
+		pop->iStop[s] = pop->iStart[s] + o[0];
+	}
+	dp->keysValid = false;
+	dp->extracted = true;
+}
+
+// src/pusher.c:914-1035: counts first, then the (x,y,z,vx,vy,vz) records; immigrants are shifted by
+// (direction they came from)*trueSize and appended species by species in ascending neighbour index.
+void puMigrate(Population *pop, MpiInfo *mpiInfo, Grid *grid){
+	Ctx *c = cur(); DevPop *dp = devPop(c, pop);
+	if(!dp->extracted) fatal("puMigrate: call puExtractEmigrants3D first");
+	int nS = dp->nS;
+	if(27*nS > 1024/2) fatal("too many species");
+	long *nEm = mpiInfo->nEmigrants, *nIm = mpiInfo->nImmigrants;
+	// --- counts (exchangeNMigrants :914) ---
+	if(mpiInfo->mpiSize == 1){
+		for(int ne = 0; ne < 27; ne++) for(int s = 0; s < nS; s++)
+			nIm[ne*nS+s] = ne == 13 ? 0 : nEm[neighborToReciprocal(ne,3)*nS+s];
+	} else {
+		std::vector<long> all((size_t)27*nS*mpiInfo->mpiSize);
+		c->tp->allgatherLong(c, nEm, 27*nS, all.data());
+		for(int ne = 0; ne < 27; ne++){
+			int src = neighborToRank(mpiInfo, ne), rec = neighborToReciprocal(ne, 3);
+			for(int s = 0; s < nS; s++) nIm[ne*nS+s] = ne == 13 ? 0 : all[(size_t)src*27*nS + rec*nS + s];
+		}
+	}
+	// --- pack ---
+	long emOff[28], imOff[28];
+	emOff[0] = imOff[0] = 0;
+	for(int ne = 0; ne < 27; ne++){
+		long e = 0, i = 0;
+		for(int s = 0; s < nS; s++){ e += nEm[ne*nS+s]; i += nIm[ne*nS+s]; }
+		emOff[ne+1] = emOff[ne] + e; imOff[ne+1] = imOff[ne] + i;
+	}
+	if(emOff[27] > dp->emigCap){
+		if(dp->d_emig){ streamSync(c); cudaFree(dp->d_emig); }
+		dp->emigCap = emOff[27] + emOff[27]/2 + 1024;
+		PINC_CUDA(cudaMalloc(&dp->d_emig, (size_t)dp->emigCap*6*sizeof(double)));
+	}
+	if(imOff[27] > dp->immigCap){
+		if(dp->d_immig){ streamSync(c); cudaFree(dp->d_immig); }
+		dp->immigCap = imOff[27] + imOff[27]/2 + 1024;
+		PINC_CUDA(cudaMalloc(&dp->d_immig, (size_t)dp->immigCap*6*sizeof(double)));
+	}
+	for(int s = 0; s < nS; s++){
+		PackPar pp;
+		long run = pop->iStop[s] - pop->iStart[s];          // emigrants start right behind the stayers
+		long tot = 0;
+		for(int ne = 0; ne < 27; ne++){
+			pp.srcOff[ne] = run;
+			long inMsg = 0;
+			for(int s2 = 0; s2 < s; s2++) inMsg += nEm[ne*nS+s2];
+			pp.dstOff[ne] = emOff[ne] + inMsg;
+			run += nEm[ne*nS+s]; tot += nEm[ne*nS+s];
+		}
+		pp.srcOff[27] = run;
+		if(tot > 0) PINC_LAUNCH(c, K_EXTRACT, 96.0*tot, (k_pack_emigrants<<<pGrid(c,tot),256,0,c->stream>>>(dp->base, dp->cap, pop->iStart[s], tot, pp, dp->d_emig)));
+	}
+	// --- exchange (exchangeMigrants :988) ---
+	std::vector<Msg> sends, recvs;
+	for(int ne = 0; ne < 27; ne++){
+		if(ne == 13) continue;
+		int peer = neighborToRank(mpiInfo, ne);
+		sends.push_back({peer, neighborToReciprocal(ne,3), dp->d_emig + 6*emOff[ne], (size_t)(emOff[ne+1]-emOff[ne])*48});
+		recvs.push_back({peer, ne, dp->d_immig + 6*imOff[ne], (size_t)(imOff[ne+1]-imOff[ne])*48});
+	}
+	c->tp->exchange(c, sends, recvs);
+	// --- import (shiftImmigrants :941, importParticles :967) ---
+	for(int s = 0; s < nS; s++){
+		ImportPar ip;
+		long tot = 0;
+		for(int ne = 0; ne < 27; ne++){
+			long inMsg = 0;
+			for(int s2 = 0; s2 < s; s2++) inMsg += nIm[ne*nS+s2];
+			ip.srcOff[ne] = imOff[ne] + inMsg;
+			ip.cnt[ne] = nIm[ne*nS+s];
+			tot += ip.cnt[ne];
+			int q = ne;
+			for(int d = 0; d < 3; d++){ int n = q%3 - 1; q /= 3; ip.shift[ne][d] = (double)(n*grid->trueSize[d+1]); }
+		}
+		if(pop->iStop[s] + tot > pop->iStart[s+1])
+			fatal("puMigrate: species %d overflows its allocation (%ld + %ld immigrants > %ld)", s, pop->iStop[s]-pop->iStart[s], tot, pop->iStart[s+1]-pop->iStart[s]);
+		if(tot > 0) PINC_LAUNCH(c, K_IMPORT, 96.0*tot, (k_import<<<pGrid(c,tot),256,0,c->stream>>>(dp->base, dp->cap, pop->iStop[s], tot, ip, dp->d_immig)));
+		pop->iStop[s] += tot;
+	}
+	dp->extracted = false;
+}
+
+void puDistr3D1(const Population *pop, Grid *rhoGrid){
+	Ctx *c = cur(); DevPop *dp = devPop(c, pop); DevGrid *rho = devGrid(c, rhoGrid);
+	if(rho->nv != 1) fatal("puDistr3D1 needs a scalar grid");
+	if(!rho->d_fix){
+		PINC_CUDA(cudaMalloc(&rho->d_fix, (size_t)rho->n*sizeof(long long)));
+		PINC_CUDA(cudaMemsetAsync(rho->d_fix, 0, (size_t)rho->n*sizeof(long long), c->stream));
+	}
+	gridZero(c, rho);
+	long sx = rho->size[0], sxy = sx*rho->size[1];
+	for(int s = 0; s < dp->nS; s++){
+		long a = pop->iStart[s], n = pop->iStop[s] - a;
+		long ns = dp->sortedN[s] < n ? dp->sortedN[s] : n;
+		if(ns > 0 && (dp->nc[0] > rho->size[0]-1 || dp->nc[1] > rho->size[1]-1 || dp->nc[2] > rho->size[2]-1)) ns = 0;
+		const double *X = dp->base + a, *Y = X + dp->cap, *Z = Y + dp->cap;
+		if(ns > 0){
+			long warps = dp->nCells;
+			int blocks = gridFor(warps*32, 256, c->numSMs*8);
+			PINC_LAUNCH(c, K_DEPOSIT, 24.0*ns, (k_distr_cells<<<blocks,256,0,c->stream>>>(X, Y, Z, dp->d_hist[s], cellsOf(dp), sx, sxy, rho->d_fix)));
+		}
+		if(n - ns > 0)
+			PINC_LAUNCH(c, K_DEPOSIT, 24.0*(n-ns), (k_distr_tail<<<pGrid(c,n-ns),256,0,c->stream>>>(X+ns, Y+ns, Z+ns, n-ns, rho->size[0], rho->size[1], rho->size[2], rho->d_fix, c->d_flags)));
+		PINC_LAUNCH(c, K_DEPOSIT, 32.0*rho->n, (k_distr_finalize<<<gridFor(rho->n,256,c->numSMs*8),256,0,c->stream>>>(rho->d, rho->d_fix, rho->n, 1.0/pop->charge[s], pop->charge[s])));
+	}
+}
+
+// src/population.c:700-710 (host arithmetic on the small per-species scalars)
+void pSumKinEnergy(Population *pop){
+	int nS = pop->nSpecies;
+	pop->kinEnergy[nS] = 0;
+	for(int s = 0; s < nS; s++) pop->kinEnergy[nS] += pop->kinEnergy[s];
+}
+
+} // extern "C"
