@@ -70,5 +70,7 @@ def true_view(a):
 def sorted_particles(pos, vel):
     """Canonical order of a particle multiset: lexicographic by (x, y, z, vx, vy, vz)."""
     rec = np.concatenate([pos, vel], axis=1)
-    idx = np.lexsort(rec.T[::-1])
+    # sort on keys rounded to 1e-7 so that two runs that differ by a few ulp order equal-coordinate particles
+    # (lattice starts have thousands of them) the same way
+    idx = np.lexsort(np.round(rec, 7).T[::-1])
     return rec[idx]

@@ -232,7 +232,8 @@ def _run_mg_case(L, O, true, levels):
         g = solver.contents.mgPhi.contents.grids[q]
         L.pincSyncGridToHost(g)
         got_q = abi.grid_array(g.contents).reshape(-1)
-        assert np.abs(got_q - ref_q).max() <= 1e-11 * max(np.abs(ref_q).max(), 1e-300)
+        # coarse phi holds corrections (tiny once converged): compare on the scale of the fine-grid phi
+        assert np.abs(got_q - ref_q).max() <= 1e-12 * np.abs(pr).max()
     O.orc_mg_free(mg)
     L.mgFreeSolver(solver)
 
