@@ -196,9 +196,15 @@ void mgFreeSolver(MultigridSolver *solver);                                     
 /* residual history of the most recent mgSolve on this rank: returns the V-cycle count and
  * copies up to `cap` values of barRes (multigrid.c:1700-1704), one per V-cycle. */
 int pincMgLastHistory(double *barRes, int cap);
-/* execution mode of single-rank solves: 1 (default) = one persistent cooperative kernel per solve,
- * 0 = one kernel per reference call.  Same arithmetic per node; $PINC_B200_MG=ops sets 0 at start-up. */
-void pincMgSetMode(int fused);
+/* execution mode of single-rank periodic solves (same arithmetic per node in all of them):
+ *   0 ops            one kernel per reference call, ghost layers exchanged as the reference does;
+ *   1 fused          one persistent cooperative kernel over all SMs, gBnd after every half-sweep;
+ *   2 cluster        one kernel on one 16-CTA cluster, phi of all levels in distributed shared memory,
+ *                    gBnd's mean subtraction applied once per smoother call (default; falls back to 1
+ *                    when the levels do not fit the cluster's shared memory);
+ *   3 cluster-exact  as 2 with gBnd after every half-sweep.
+ * $PINC_B200_MG = ops | fused | cluster | cluster-exact selects the start-up value. */
+void pincMgSetMode(int mode);
 
 /* ---------------------------------------------------------------------------------
  * Host-struct constructors with plain arguments (restating gAlloc grid.c:413,

@@ -407,7 +407,9 @@ __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
 	}
 }
 
-int g_mgMode = -1;             // -1: from $PINC_B200_MG at first use; 0 ops; 1 fused
+// -1: from $PINC_B200_MG at first use; 0 ops; 1 fused (grid-wide persistent kernel, gBnd per half-sweep);
+// 2 cluster (DSMEM-resident, gBnd batched per smoother call; default); 3 cluster with gBnd per half-sweep
+int g_mgMode = -1;
 static void ensureHist(Ctx *c){
 	if(c->d_mgHist) return;
 	PINC_CUDA(cudaMalloc(&c->d_mgHist, 256*sizeof(double)));
@@ -416,7 +418,10 @@ static void ensureHist(Ctx *c){
 }
 
 static bool fusedEligible(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *m){
-	if(g_mgMode < 0){ const char *e = getenv("PINC_B200_MG"); g_mgMode = (e && !strcmp(e, "ops")) ? 0 : 1; }
+	if(g_mgMode < 0){
+		const char *e = getenv("PINC_B200_MG");
+		g_mgMode = !e ? 2 : !strcmp(e, "ops") ? 0 : !strcmp(e, "fused") ? 1 : !strcmp(e, "cluster-exact") ? 3 : 2;
+	}
 	if(!g_mgMode) return false;
 	if(m->mpiSize != 1) return false;
 	int nL = mgRho->nLevels;
@@ -541,8 +546,10 @@ void mgSolveRaw(funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 	Ctx *c = cur();
 	const double tol = 1.E-10;                       // src/multigrid.c:1695
 	const int maxCycles = 200;                       // the reference has no bound; this one reports instead of hanging
-	if(fusedEligible(c, mgRho, mgPhi, mgRes, mpiInfo)) fusedSolve(c, mgRho, mgPhi, mgRes, tol, maxCycles);
-	else opsSolve(c, mgAlgo, mgRho, mgPhi, mgRes, mpiInfo, tol, maxCycles);
+	if(fusedEligible(c, mgRho, mgPhi, mgRes, mpiInfo)){
+		if(g_mgMode >= 2 && clusterSolve(c, mgRho, mgPhi, mgRes, tol, maxCycles, g_mgMode == 3)) return;
+		fusedSolve(c, mgRho, mgPhi, mgRes, tol, maxCycles);
+	} else opsSolve(c, mgAlgo, mgRho, mgPhi, mgRes, mpiInfo, tol, maxCycles);
 }
 
 void mgSolve(const MultigridSolver *solver, const Grid *rho, const Grid *phi, const MpiInfo *mpiInfo){
@@ -556,7 +563,7 @@ void mgSolver(void (**solve)(), MultigridSolver *(**solverAlloc)(), void (**solv
 	*solverFree = (void(*)())mgFreeSolver;
 }
 
-void pincMgSetMode(int fused){ pinc::g_mgMode = fused ? 1 : 0; }
+void pincMgSetMode(int mode){ pinc::g_mgMode = mode < 0 ? 0 : (mode > 3 ? 3 : mode); }
 
 int pincMgLastHistory(double *barRes, int cap){
 	Ctx *c = cur();

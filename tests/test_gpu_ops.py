@@ -185,17 +185,20 @@ def _mg_problem(L, true, levels, seed):
     return rho, phi, solver
 
 
-@pytest.mark.parametrize("mode", ["fused", "ops"])
-@pytest.mark.parametrize("true,levels", [((16, 8, 8), 3), ((32, 32, 32), 4), ((64, 32, 32), 5)])
+MG_MODES = {"ops": 0, "fused": 1, "cluster": 2, "cluster-exact": 3}
+
+
+@pytest.mark.parametrize("mode", sorted(MG_MODES))
+@pytest.mark.parametrize("true,levels", [((16, 8, 8), 3), ((32, 32, 32), 4), ((64, 32, 32), 5), ((64, 64, 64), 5), ((48, 16, 24), 3)])
 def test_mg_solve_matches_oracle(gpu_lib, mode, true, levels):
     """mgSolve: V-cycle count, residual norm per V-cycle and phi against the oracle; two solves in a row so
-    that the coarse-level carry-over (quirk Q5) is covered.  Both execution modes of the solver."""
+    that the coarse-level carry-over (quirk Q5) is covered.  All four execution modes of the solver."""
     L, O = gpu_lib, orc.load()
-    L.pincMgSetMode(1 if mode == "fused" else 0)
+    L.pincMgSetMode(MG_MODES[mode])
     try:
         _run_mg_case(L, O, true, levels)
     finally:
-        L.pincMgSetMode(1)
+        L.pincMgSetMode(2)
 
 
 def _run_mg_case(L, O, true, levels):

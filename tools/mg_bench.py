@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""Stand-alone multigrid benchmark (BASELINE config 3, input/mgErrorScaling.ini repaired as in SURVEY 8d-C3):
+rho = k^2 sin(k x) with the reference's PI (src/grid.h:584, quirk Q11) or white noise, N^3 cells, mgLevels =
+log2(N) - 1, V(10,10) with 10 coarse sweeps.  Prints V-cycles, barRes history end, device time per solve and
+per V-cycle for every execution mode of the solver, and the error against the analytic solution."""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import GridH, single_mpi  # noqa: E402
+from pinc_b200 import lib as plib  # noqa: E402
+
+PI = 3.14159265
+MODES = {0: "ops", 1: "fused", 2: "cluster", 3: "cluster-exact"}
+
+
+def main():
+    L = plib.load()
+    sizes = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "16,32,64".split(","))]
+    kind = sys.argv[2] if len(sys.argv) > 2 else "sin"
+    out = []
+    for N in sizes:
+        true = (N, N, N)
+        levels = int(np.log2(N)) - 1
+        for mode in (0, 1, 2, 3):
+            if mode == 0 and N > 64:
+                continue
+            L.pincMgSetMode(mode)
+            rho, phi = GridH(L, true, 1), GridH(L, true, 1)
+            z, y, x = np.meshgrid(*[np.arange(s, dtype=float) for s in rho.size[::-1]], indexing="ij")
+            k = 2 * PI / N
+            if kind == "sin":
+                rho.a[..., 0] = k * k * np.sin(k * (x - 1))
+                sol = np.sin(k * (x - 1))
+            else:
+                rho.a[..., 0] = 8 * np.random.default_rng(0).standard_normal(rho.a.shape[:3])
+                sol = None
+            solver = L.pincMgAllocSolver(rho.ptr, phi.ptr, levels, 1, 10, 10, 10)
+            m = single_mpi(L, true)
+            times = []
+            ncyc = None
+            for rep in range(3):
+                phi.a[...] = 0
+                phi.up(); rho.up()
+                for q in range(1, levels):           # cold start of the coarse levels as well
+                    for mg in (solver.contents.mgPhi,):
+                        g = mg.contents.grids[q]
+                        np.ctypeslib.as_array(g.contents.val, shape=(int(g.contents.sizeProd[4]),))[:] = 0
+                        L.pincSyncGridToDevice(g)
+                L.pincDeviceSynchronize()
+                L.pincTimerStart()
+                L.mgSolve(solver, rho.ptr, phi.ptr, m)
+                times.append(L.pincTimerStopMs())
+                buf = (C.c_double * 256)()
+                ncyc = L.pincMgLastHistory(buf, 256)
+                last = buf[min(ncyc, 250) - 1]
+            err = None
+            if sol is not None:
+                p = phi.down()[1:-1, 1:-1, 1:-1, 0]
+                err = float(np.sqrt(np.mean((p - sol[1:-1, 1:-1, 1:-1]) ** 2)))
+            rec = {"N": N, "levels": levels, "mode": MODES[mode], "rho": kind, "vcycles": ncyc, "barRes_last": last,
+                   "ms_per_solve": min(times), "us_per_vcycle": 1e3 * min(times) / max(ncyc, 1), "rms_error_vs_analytic": err}
+            print(json.dumps(rec), flush=True)
+            out.append(rec)
+            L.mgFreeSolver(solver)
+            rho.free(); phi.free()
+    L.pincMgSetMode(2)
+
+
+if __name__ == "__main__":
+    main()
