@@ -204,6 +204,7 @@ struct MgPlan {
 	double *partial;         // 2*gridDim doubles
 	unsigned *bar;
 	double *hist;            // [0] cycles, [1..] barRes per V-cycle
+	unsigned barBase;
 };
 
 struct Scope {
@@ -213,21 +214,18 @@ struct Scope {
 	double *sh;              // 18 doubles of shared memory
 	__device__ __forceinline__ long tid() const { return single ? threadIdx.x : blockIdx.x*(long)blockDim.x + threadIdx.x; }
 	__device__ __forceinline__ long nthr() const { return single ? blockDim.x : (long)gridDim.x*blockDim.x; }
+	// Grid barrier: one monotonically increasing arrival counter (no reset, no generation word).  The fence
+	// before the arrival orders this CTA's stores; readers fetch other CTAs' data with ld.global.cg (L2), so no
+	// L1 invalidation is needed afterwards.  Measured (tools/ubench_gridbar.cu): 2780 cycles against 4820 for the
+	// fence + counter + generation + fence scheme.
 	__device__ __forceinline__ void sync(){
 		__syncthreads();
 		if(single) return;
 		if(threadIdx.x == 0){
 			__threadfence();
-			unsigned old = atomicAdd(&bar[0], 1u);
-			if(old == gridDim.x - 1){
-				atomicExch(&bar[0], 0u);
-				__threadfence();
-				atomicAdd(&bar[1], 1u);
-			} else {
-				while(*((volatile unsigned*)&bar[1]) == gen){ }
-			}
-			__threadfence();
-			gen++;
+			atomicAdd(&bar[0], 1u);
+			gen += gridDim.x;
+			while((int)(*((volatile unsigned*)&bar[0]) - gen) < 0){ }
 		}
 		__syncthreads();
 	}
@@ -365,7 +363,7 @@ __device__ void fGhosts(double *v, int s0, int s1, int s2, Scope &S){
 __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
 	__shared__ double sh[18];
 	Scope Sg; Sg.single = false; Sg.bar = P.bar; Sg.partial = P.partial; Sg.flip = 0; Sg.sh = sh; Sg.gen = 0;
-	if(threadIdx.x == 0) Sg.gen = *((volatile unsigned*)&P.bar[1]);
+	if(threadIdx.x == 0) Sg.gen = P.barBase;            // arrival count at kernel start (host-tracked)
 	Scope S1 = Sg; S1.single = true;
 	int b = P.nLevels - 1;
 	int qs = P.qSmall < 0 ? 0 : P.qSmall;
@@ -410,6 +408,7 @@ __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
 // -1: from $PINC_B200_MG at first use; 0 ops; 1 fused (grid-wide persistent kernel, gBnd per half-sweep);
 // 2 cluster (DSMEM-resident, gBnd batched per smoother call; default); 3 cluster with gBnd per half-sweep
 int g_mgMode = -1;
+int g_mgForceCluster = 0;     // $PINC_B200_MG=cluster-always: use the cluster kernel whenever it fits
 static void ensureHist(Ctx *c){
 	if(c->d_mgHist) return;
 	PINC_CUDA(cudaMalloc(&c->d_mgHist, 256*sizeof(double)));
@@ -421,6 +420,7 @@ static bool fusedEligible(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid 
 	if(g_mgMode < 0){
 		const char *e = getenv("PINC_B200_MG");
 		g_mgMode = !e ? 2 : !strcmp(e, "ops") ? 0 : !strcmp(e, "fused") ? 1 : !strcmp(e, "cluster-exact") ? 3 : 2;
+		if(e && !strcmp(e, "cluster-always")) g_mgForceCluster = 1;
 	}
 	if(!g_mgMode) return false;
 	if(m->mpiSize != 1) return false;
@@ -462,6 +462,8 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 	int grid = P.qSmall == 0 ? 1 : c->numSMs;
 	P.partial = partialBuffer(c, 2L*grid);
 	P.bar = c->d_bar;
+	PINC_CUDA(cudaMemsetAsync(c->d_bar, 0, 2*sizeof(unsigned), c->stream));
+	P.barBase = 0;
 	ensureHist(c);
 	P.hist = c->d_mgHist;
 	void *args[] = { &P };
@@ -547,7 +549,12 @@ void mgSolveRaw(funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 	const double tol = 1.E-10;                       // src/multigrid.c:1695
 	const int maxCycles = 200;                       // the reference has no bound; this one reports instead of hanging
 	if(fusedEligible(c, mgRho, mgPhi, mgRes, mpiInfo)){
-		if(g_mgMode >= 2 && clusterSolve(c, mgRho, mgPhi, mgRes, tol, maxCycles, g_mgMode == 3)) return;
+		// the cluster kernel runs on 16 SMs: it wins while the finest level is small enough to be latency-bound
+		// (measured: 32^3 304 vs 526 us per V-cycle, 64^3 908 vs 805); larger grids go to the all-SM kernel
+		const Grid *g0 = mgRho->grids[0];
+		long nt0 = (long)g0->trueSize[1]*g0->trueSize[2]*g0->trueSize[3];
+		bool preferCluster = g_mgMode == 3 || g_mgForceCluster || nt0 <= 65536;
+		if(g_mgMode >= 2 && preferCluster && clusterSolve(c, mgRho, mgPhi, mgRes, tol, maxCycles, g_mgMode == 3)) return;
 		fusedSolve(c, mgRho, mgPhi, mgRes, tol, maxCycles);
 	} else opsSolve(c, mgAlgo, mgRho, mgPhi, mgRes, mpiInfo, tol, maxCycles);
 }
@@ -563,7 +570,7 @@ void mgSolver(void (**solve)(), MultigridSolver *(**solverAlloc)(), void (**solv
 	*solverFree = (void(*)())mgFreeSolver;
 }
 
-void pincMgSetMode(int mode){ pinc::g_mgMode = mode < 0 ? 0 : (mode > 3 ? 3 : mode); }
+void pincMgSetMode(int mode){ pinc::g_mgForceCluster = mode == 4; if(mode == 4) mode = 2; pinc::g_mgMode = mode < 0 ? 0 : (mode > 3 ? 3 : mode); }
 
 int pincMgLastHistory(double *barRes, int cap){
 	Ctx *c = cur();

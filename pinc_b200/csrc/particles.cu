@@ -242,14 +242,25 @@ __global__ void __launch_bounds__(256) k_distr_cells(const double *__restrict__ 
 		long long a[8];
 		#pragma unroll
 		for(int q = 0; q < 8; q++) a[q] = 0;
-		for(unsigned i = b + lane; i < e; i += 32){
-			double x = X[i], y = Y[i], z = Z[i];
-			int j = (int)x, k = (int)y, l = (int)z;
-			double xf = x-j, yf = y-k, zf = z-l;
-			double xc = 1-xf, yc = 1-yf, zc = 1-zf;
-			double cc = xc*yc, fc = xf*yc, cf = xc*yf, ff = xf*yf;
-			a[0] += fixw(cc*zc); a[1] += fixw(fc*zc); a[2] += fixw(cf*zc); a[3] += fixw(ff*zc);
-			a[4] += fixw(cc*zf); a[5] += fixw(fc*zf); a[6] += fixw(cf*zf); a[7] += fixw(ff*zf);
+		// up to 96 particles of the cell per trip, all loads issued before the arithmetic (memory-level parallelism)
+		for(unsigned i0 = b; i0 < e; i0 += 96){
+			double x[3], y[3], z[3];
+			#pragma unroll
+			for(int u = 0; u < 3; u++){
+				unsigned i = i0 + lane + 32*u;
+				bool ok = i < e;
+				x[u] = ok ? X[i] : 0.0; y[u] = ok ? Y[i] : 0.0; z[u] = ok ? Z[i] : 0.0;
+			}
+			#pragma unroll
+			for(int u = 0; u < 3; u++){
+				if(i0 + lane + 32*u >= e) continue;
+				int j = (int)x[u], k = (int)y[u], l = (int)z[u];
+				double xf = x[u]-j, yf = y[u]-k, zf = z[u]-l;
+				double xc = 1-xf, yc = 1-yf, zc = 1-zf;
+				double cc = xc*yc, fc = xf*yc, cf = xc*yf, ff = xf*yf;
+				a[0] += fixw(cc*zc); a[1] += fixw(fc*zc); a[2] += fixw(cf*zc); a[3] += fixw(ff*zc);
+				a[4] += fixw(cc*zf); a[5] += fixw(fc*zf); a[6] += fixw(cf*zf); a[7] += fixw(ff*zf);
+			}
 		}
 		// transposing butterfly: 8 values x 32 lanes -> one total per corner in 9 64-bit shuffles
 		bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;

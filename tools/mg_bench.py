@@ -24,11 +24,12 @@ def main():
     L = plib.load()
     sizes = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "16,32,64".split(","))]
     kind = sys.argv[2] if len(sys.argv) > 2 else "sin"
+    modes = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1, 2, 3]
     out = []
     for N in sizes:
         true = (N, N, N)
         levels = int(np.log2(N)) - 1
-        for mode in (0, 1, 2, 3):
+        for mode in modes:
             if mode == 0 and N > 64:
                 continue
             L.pincMgSetMode(mode)
