@@ -21,4 +21,4 @@ def test_two_gpus_nccl(kind):
            "--master-port", "29517", os.path.join(ROOT, "tools", "multi_check.py"), kind, "4"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count(" ok: ") == 2
+    assert r.stdout.count("] ok: ") == 2
