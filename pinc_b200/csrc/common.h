@@ -167,6 +167,7 @@ double readScalar(Ctx *c, int slot);           // D2H of d_scal[slot] + sync
 
 // ---- multigrid (multigrid.cu) ----
 void mgForgetPlans(Ctx *c);
+void *mgProfBuffer(Ctx *c);
 bool clusterSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, double tol, int maxCycles, int exact);
 
 } // namespace pinc

@@ -329,6 +329,16 @@ int pincProfGet(int idx, char *name, int namelen, double *ms, long int *launches
 	return 1;
 }
 long int pincLaunchCount(void){ return cur()->launches; }
+// cycle accounting of the cluster multigrid kernel ($PINC_B200_MGPROF=1): copies 16 (cycles, calls) pairs and clears
+int pincMgProfRead(long long *out32){
+	Ctx *c = cur();
+	long long *d = (long long*)mgProfBuffer(c);
+	if(!d) return 0;
+	streamSync(c);
+	PINC_CUDA(cudaMemcpy(out32, d, 32*sizeof(long long), cudaMemcpyDeviceToHost));
+	PINC_CUDA(cudaMemset(d, 0, 32*sizeof(long long)));
+	return 1;
+}
 const char *pincVersion(void){ return "pinc-b200 0.1 (sm_100a)"; }
 int pincLastError(char *buf, int len){
 	std::lock_guard<std::mutex> lk(g_mu);

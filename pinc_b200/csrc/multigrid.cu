@@ -19,6 +19,7 @@
 // half-sweeps per level per V-cycle, not by HBM, which is why the fused mode exists.
 #include "common.h"
 #include <cmath>
+#include "mgsmem.cuh"
 
 namespace pinc {
 
@@ -82,8 +83,12 @@ __device__ __forceinline__ double prolPoint(const double *c, int j, int k, int l
 	return 0.5*(prolY(c, Ja, k, l, c0, c1, c2) + prolY(c, Jb, k, l, c0, c1, c2));
 }
 
+// (levels have fewer than 2^31 nodes: 32-bit divisions, ~10x cheaper than 64-bit ones)
 __device__ __forceinline__ void truePoint(long i, int t0, int t1, int &j, int &k, int &l){
-	j = (int)(i % t0) + 1; long r = i / t0; k = (int)(r % t1) + 1; l = (int)(r / t1) + 1;
+	unsigned u = (unsigned)i, r = u / (unsigned)t0;
+	j = (int)(u - r*(unsigned)t0) + 1;
+	unsigned q = r / (unsigned)t1;
+	k = (int)(r - q*(unsigned)t1) + 1; l = (int)q + 1;
 }
 
 // =================================================================================================
@@ -196,7 +201,7 @@ static void opVCycle(Ctx *c, int level, int bottom, int top, Multigrid *mgRho, M
 // =================================================================================================
 #define MG_MAXLEV 10
 #define MG_BLOCK 512
-#define MG_SMALL 8192        // levels with at most this many true nodes run inside CTA 0
+#define MG_SMALL MC_SMALL    // levels with at most this many true nodes run inside CTA 0 (shared memory)
 struct MgPlan {
 	Lvl L[MG_MAXLEV];
 	int nLevels, nPre, nPost, nCoarse, qSmall, maxCycles;
@@ -205,6 +210,9 @@ struct MgPlan {
 	unsigned *bar;
 	double *hist;            // [0] cycles, [1..] barRes per V-cycle
 	unsigned barBase;
+	int exact;               // gBnd after every half-sweep (pending shifts) instead of once per smoother call
+	int smemSmall;           // small levels live in CTA 0's shared memory (descriptors in C)
+	CPlan C;
 };
 
 struct Scope {
@@ -270,34 +278,41 @@ __device__ void fNeutralize(double *v, int s0, int s1, int s2, Scope &S){
 }
 
 // mgGS3D with gBnd's mean subtraction carried as pending shifts.  sIn: shift still pending on every value at entry.
-__device__ void fGS(const Lvl &L, int nCycles, double sIn, Scope &S){
+__device__ void fGS(const Lvl &L, int nCycles, double sIn, int exact, Scope &S){
 	int s0 = L.s0, s1 = L.s1, s2 = L.s2;
 	int t0 = s0-2, t1 = s1-2, t2 = s2-2; long nt = (long)t0*t1*t2;
 	int half = t0/2; long items = (long)half*t1*t2;
-	double sR = sIn, sPrev = 0;
-	if(nCycles <= 0){
+	if(nCycles <= 0 || !exact){
 		if(sIn != 0.0){
 			for(long i = S.tid(); i < nt; i += S.nthr()){ int j,k,l; truePoint(i,t0,t1,j,k,l); long g = ix(j,k,l,s0,s1); L.phi[g] = ldg2(L.phi + g) - sIn; }
 			S.sync();
 		}
-		return;
+		if(nCycles <= 0) return;
+		sIn = 0.0;
 	}
+	double sR = sIn, sPrev = 0;
 	for(int h = 0; h < 2*nCycles; h++){
 		int parity = (h & 1) ? 0 : 1;
 		double acc = 0;
 		for(long i = S.tid(); i < items; i += S.nthr()){
-			int m = (int)(i % half); long r = i / half; int k = (int)(r % t1) + 1; int l = (int)(r / t1) + 1;
+			unsigned ui = (unsigned)i, r = ui / (unsigned)half; int m = (int)(ui - r*(unsigned)half);
+			unsigned lq = r / (unsigned)t1; int k = (int)(r - lq*(unsigned)t1) + 1; int l = (int)lq + 1;
 			int ja = 2*m+1;
 			int jOwn = (((ja+k+l)&1) == parity) ? ja : ja+1;
 			int jOth = 2*ja+1 - jOwn;
 			double vn = gsPoint<true>(L.phi, L.rho, jOwn, k, l, s0, s1, s2, sR);
-			double vo = ldg2(L.phi + ix(jOth,k,l,s0,s1)) - sR;
+			if(exact){
+				double vo = ldg2(L.phi + ix(jOth,k,l,s0,s1)) - sR;
+				acc += vn; acc += vo;
+			}
 			L.phi[ix(jOwn,k,l,s0,s1)] = vn;
-			acc += vn; acc += vo;
 		}
-		double avg = S.allSum(acc)/(double)nt;
-		sPrev = sR; sR = avg;
+		if(exact){
+			double avg = S.allSum(acc)/(double)nt;
+			sPrev = sR; sR = avg;
+		} else S.sync();
 	}
+	if(!exact){ fNeutralize(L.phi, s0, s1, s2, S); return; }     // the 2*nCycles gBnd calls, applied once
 	// materialise: the colour written last (even nodes) carries sR, the other one sPrev then sR
 	for(long i = S.tid(); i < nt; i += S.nthr()){
 		int j,k,l; truePoint(i,t0,t1,j,k,l); long g = ix(j,k,l,s0,s1);
@@ -312,7 +327,7 @@ __device__ void fGS(const Lvl &L, int nCycles, double sIn, Scope &S){
 __device__ void fDown(const MgPlan &P, int q, Scope &S){
 	const Lvl &L = P.L[q], &C = P.L[q+1];
 	fNeutralize(L.rho, L.s0, L.s1, L.s2, S);
-	fGS(L, P.nPre, 0.0, S);
+	fGS(L, P.nPre, 0.0, P.exact, S);
 	{
 		int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2; long nt = (long)t0*t1*t2;
 		for(long i = S.tid(); i < nt; i += S.nthr()){ int j,k,l; truePoint(i,t0,t1,j,k,l);
@@ -329,7 +344,7 @@ __device__ void fDown(const MgPlan &P, int q, Scope &S){
 __device__ void fBottom(const MgPlan &P, Scope &S){
 	const Lvl &L = P.L[P.nLevels-1];
 	fNeutralize(L.rho, L.s0, L.s1, L.s2, S);
-	fGS(L, P.nCoarse, 0.0, S);
+	fGS(L, P.nCoarse, 0.0, P.exact, S);
 	fNeutralize(L.phi, L.s0, L.s1, L.s2, S);
 }
 // res(q) := P(phi(q+1)); phi(q) += res(q); gBnd; post-smooth; gBnd
@@ -346,7 +361,7 @@ __device__ void fUp(const MgPlan &P, int q, Scope &S){
 		acc += v;
 	}
 	double avg = S.allSum(acc)/(double)nt;
-	fGS(L, P.nPost, avg, S);
+	fGS(L, P.nPost, avg, P.exact, S);
 	fNeutralize(L.phi, L.s0, L.s1, L.s2, S);
 }
 __device__ void fGhosts(double *v, int s0, int s1, int s2, Scope &S){
@@ -360,8 +375,42 @@ __device__ void fGhosts(double *v, int s0, int s1, int s2, Scope &S){
 	}
 }
 
+// small levels of the all-SM kernel: CTA 0, shared memory, the routines of mgsmem.cuh
+template<bool EXACT> __device__ void smallSection(const MgPlan &P, CK &K){
+	const CPlan &C = P.C;
+	const int b = C.nLevels - 1, qs = P.qSmall;
+	{	// rho(qs) was restricted into global memory by the grid-wide part
+		const CLvl &L = C.L[qs];
+		int n = L.nx*L.ny*L.nz;
+		for(int i = threadIdx.x; i < n; i += blockDim.x){ int j,k,l; ownNode(L,1,i,j,k,l); mgS[L.offRho + i] = __ldcg(L.rho + gix(L,j,k,l)); }
+		__syncthreads();
+	}
+	for(int q = qs; q < b; q++) cDown<true,EXACT>(C, q, K);
+	cBottom<true,EXACT>(C, K);
+	for(int q = b-1; q >= qs; q--) cUp<true,EXACT>(C, q, K);
+	{	// phi(qs) back to global for the grid-wide prolongation
+		const CLvl &L = C.L[qs];
+		int n = L.nx*L.ny*L.nz;
+		for(int i = threadIdx.x; i < n; i += blockDim.x){ int j,k,l; ownNode(L,1,i,j,k,l); L.phiG[gix(L,j,k,l)] = mgS[L.offPhi + i]; }
+	}
+}
+
 __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
 	__shared__ double sh[18];
+	__shared__ double red[40];
+	CK K{ cg::this_cluster(), 0, 1, mgS, red, 0, nullptr };
+	if(P.smemSmall && blockIdx.x == 0){
+		for(int q = P.qSmall; q < P.nLevels; q++){
+			const CLvl &L = P.C.L[q];
+			int n = L.nx*L.ny*L.nz;
+			for(int i = threadIdx.x; i < n; i += blockDim.x){
+				int j,k,l; ownNode(L,1,i,j,k,l);
+				mgS[L.offPhi + i] = __ldcg(L.phiG + gix(L,j,k,l));
+				mgS[L.offRho + i] = __ldcg(L.rho + gix(L,j,k,l));
+			}
+		}
+		__syncthreads();
+	}
 	Scope Sg; Sg.single = false; Sg.bar = P.bar; Sg.partial = P.partial; Sg.flip = 0; Sg.sh = sh; Sg.gen = 0;
 	if(threadIdx.x == 0) Sg.gen = P.barBase;            // arrival count at kernel start (host-tracked)
 	Scope S1 = Sg; S1.single = true;
@@ -373,9 +422,13 @@ __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
 		for(int q = 0; q <= b && q < qs; q++){ if(q < b) fDown(P, q, Sg); else fBottom(P, Sg); }
 		if(qs <= b){
 			if(blockIdx.x == 0){
-				for(int q = qs; q < b; q++) fDown(P, q, S1);
-				fBottom(P, S1);
-				for(int q = b-1; q >= qs; q--) fUp(P, q, S1);
+				if(P.smemSmall){
+					if(P.exact) smallSection<true>(P, K); else smallSection<false>(P, K);
+				} else {
+					for(int q = qs; q < b; q++) fDown(P, q, S1);
+					fBottom(P, S1);
+					for(int q = b-1; q >= qs; q--) fUp(P, q, S1);
+				}
 			}
 			Sg.sync();
 		}
@@ -398,6 +451,19 @@ __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
 		cycles++;
 	}
 	if(blockIdx.x == 0 && threadIdx.x == 0) P.hist[0] = (double)cycles;
+	if(P.smemSmall){
+		if(blockIdx.x == 0)
+			for(int q = P.qSmall; q <= b; q++){
+				const CLvl &L = P.C.L[q];
+				int n = L.nx*L.ny*L.nz;
+				for(int i = threadIdx.x; i < n; i += blockDim.x){
+					int j,k,l; ownNode(L,1,i,j,k,l);
+					L.phiG[gix(L,j,k,l)] = mgS[L.offPhi + i];
+					L.rho[gix(L,j,k,l)] = mgS[L.offRho + i];
+				}
+			}
+		Sg.sync();
+	}
 	for(int q = 0; q <= b; q++){
 		fGhosts(P.L[q].phi, P.L[q].s0, P.L[q].s1, P.L[q].s2, Sg);
 		fGhosts(P.L[q].rho, P.L[q].s0, P.L[q].s1, P.L[q].s2, Sg);
@@ -438,7 +504,7 @@ static bool fusedEligible(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid 
 	return true;
 }
 
-static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, double tol, int maxCycles){
+static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, double tol, int maxCycles, int exact){
 	MgPlan P{};
 	int nL = mgRho->nLevels;
 	P.nLevels = nL; P.nPre = mgRho->nPreSmooth; P.nPost = mgRho->nPostSmooth; P.nCoarse = mgRho->nCoarseSolve;
@@ -456,7 +522,34 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 	// recompute the suffix of small levels properly
 	P.qSmall = nL;
 	for(int q = nL-1; q >= 0; q--){ if(trueCount(devGrid(c, mgRho->grids[q])) <= MG_SMALL) P.qSmall = q; else break; }
-	P.tol = tol; P.maxCycles = maxCycles;
+	P.tol = tol; P.maxCycles = maxCycles; P.exact = exact;
+	// small levels in CTA 0's shared memory (needs at least one grid-wide level above them)
+	size_t smem = 0;
+	P.smemSmall = 0;
+	if(P.qSmall >= 1 && P.qSmall < nL){
+		long off = 0;
+		bool ok = true;
+		P.C.nLevels = nL; P.C.nBig = P.qSmall; P.C.nPre = P.nPre; P.C.nPost = P.nPost; P.C.nCoarse = P.nCoarse; P.C.nc = 1;
+		for(int q = P.qSmall; q < nL; q++){
+			DevGrid *r = devGrid(c, mgRho->grids[q]), *p = devGrid(c, mgPhi->grids[q]), *e = devGrid(c, mgRes->grids[q]);
+			CLvl &L = P.C.L[q];
+			L.phiG = p->d; L.rho = r->d; L.res = e->d;
+			L.nx = r->tsize[0]; L.ny = r->tsize[1]; L.nz = r->tsize[2]; L.s0 = r->size[0]; L.s1 = r->size[1];
+			L.ppc = L.nz; L.small = 1;
+			long nt = (long)L.nx*L.ny*L.nz;
+			if((L.nx/2)*L.ny*L.nz > MC_U*MG_BLOCK) ok = false;
+			L.offPhi = (int)off; off += nt;
+			L.offRho = (int)off; off += nt;
+		}
+		smem = (size_t)off*sizeof(double);
+		static size_t attrSet = 0;
+		if(ok && smem > attrSet){
+			if(cudaFuncSetAttribute((const void*)k_mg_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) attrSet = smem;
+			else { cudaGetLastError(); ok = false; }
+		}
+		P.smemSmall = ok ? 1 : 0;
+		if(!ok) smem = 0;
+	}
 	DevGrid *r0 = devGrid(c, mgRho->grids[0]);
 	P.totTrue = (double)trueCount(r0);
 	int grid = P.qSmall == 0 ? 1 : c->numSMs;
@@ -469,7 +562,7 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 	void *args[] = { &P };
 	{
 		LaunchScope ls(c, K_MGFUSED, work);
-		PINC_CUDA(cudaLaunchCooperativeKernel((void*)k_mg_solve, dim3(grid), dim3(MG_BLOCK), args, 0, c->stream));
+		PINC_CUDA(cudaLaunchCooperativeKernel((void*)k_mg_solve, dim3(grid), dim3(MG_BLOCK), args, smem, c->stream));
 	}
 	PINC_CUDA(cudaMemcpyAsync(c->h_mgHist, c->d_mgHist, 256*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	c->mgHistPending = true;
@@ -555,7 +648,7 @@ void mgSolveRaw(funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 		long nt0 = (long)g0->trueSize[1]*g0->trueSize[2]*g0->trueSize[3];
 		bool preferCluster = g_mgMode == 3 || g_mgForceCluster || nt0 <= 65536;
 		if(g_mgMode >= 2 && preferCluster && clusterSolve(c, mgRho, mgPhi, mgRes, tol, maxCycles, g_mgMode == 3)) return;
-		fusedSolve(c, mgRho, mgPhi, mgRes, tol, maxCycles);
+		fusedSolve(c, mgRho, mgPhi, mgRes, tol, maxCycles, g_mgMode == 1 || g_mgMode == 3);
 	} else opsSolve(c, mgAlgo, mgRho, mgPhi, mgRes, mpiInfo, tol, maxCycles);
 }
 

@@ -228,10 +228,16 @@ __global__ void __launch_bounds__(256) k_scatter(const double *__restrict__ src,
 }
 
 // ---- deposition (src/pusher.c:512-572) -----------------------------------------------------------------
-__device__ __forceinline__ long long fixw(double w){ return __double2ll_rn(w*(double)(1LL<<PINC_FIX_BITS)); }
+// round-to-nearest-even of w*2^46 as an integer, by the 1.5*2^52 magic constant: one FMA (w*2^46 is an exact
+// scaling, so the single rounding of the FMA is the rounding to integer) and one integer subtract, instead of a
+// multiply and a (quarter-rate) F2I.S64; identical values to __double2ll_rn(w*2^46) for 0 <= w <= 1.
+__device__ __forceinline__ long long fixw(double w){
+	const double M = 6755399441055744.0;               // 1.5 * 2^52
+	return __double_as_longlong(__fma_rn(w, (double)(1LL<<PINC_FIX_BITS), M)) - __double_as_longlong(M);
+}
 
 // sorted prefix: one warp per cell
-__global__ void __launch_bounds__(256) k_distr_cells(const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ Z,
+__global__ void __launch_bounds__(256, 4) k_distr_cells(const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ Z,
 		const unsigned *__restrict__ cs, CellSpace C, long sx, long sxy, long long *__restrict__ fix){
 	int lane = threadIdx.x & 31;
 	long warp = (blockIdx.x*(long)blockDim.x + threadIdx.x) >> 5;
@@ -242,6 +248,9 @@ __global__ void __launch_bounds__(256) k_distr_cells(const double *__restrict__ 
 		long long a[8];
 		#pragma unroll
 		for(int q = 0; q < 8; q++) a[q] = 0;
+		// every particle of the bin has (int)x == cj etc. (that is how the key was formed): convert once per cell
+		const int cj = (int)(c % C.nc0); const long cr = c / C.nc0; const int ck = (int)(cr % C.nc1); const int cl = (int)(cr / C.nc1);
+		const double dj = (double)cj, dk = (double)ck, dl = (double)cl;
 		// up to 96 particles of the cell per trip, all loads issued before the arithmetic (memory-level parallelism)
 		for(unsigned i0 = b; i0 < e; i0 += 96){
 			double x[3], y[3], z[3];
@@ -254,8 +263,7 @@ __global__ void __launch_bounds__(256) k_distr_cells(const double *__restrict__ 
 			#pragma unroll
 			for(int u = 0; u < 3; u++){
 				if(i0 + lane + 32*u >= e) continue;
-				int j = (int)x[u], k = (int)y[u], l = (int)z[u];
-				double xf = x[u]-j, yf = y[u]-k, zf = z[u]-l;
+				double xf = x[u]-dj, yf = y[u]-dk, zf = z[u]-dl;
 				double xc = 1-xf, yc = 1-yf, zc = 1-zf;
 				double cc = xc*yc, fc = xf*yc, cf = xc*yf, ff = xf*yf;
 				a[0] += fixw(cc*zc); a[1] += fixw(fc*zc); a[2] += fixw(cf*zc); a[3] += fixw(ff*zc);
@@ -281,7 +289,6 @@ __global__ void __launch_bounds__(256) k_distr_cells(const double *__restrict__ 
 		a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
 		a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
 		if((lane & 3) == 0 && a[0] != 0){
-			int cj = (int)(c % C.nc0); long r = c / C.nc0; int ck = (int)(r % C.nc1); int cl = (int)(r / C.nc1);
 			long node = cj + sx*ck + sxy*cl + (u4 ? 1 : 0) + (u8 ? sx : 0) + (u16 ? sxy : 0);
 			atomicAdd((unsigned long long*)&fix[node], (unsigned long long)a[0]);
 		}
