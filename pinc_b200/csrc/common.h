@@ -23,7 +23,7 @@ enum KClass { K_PUSH = 0, K_MOVE, K_DEPOSIT, K_EXTRACT, K_IMPORT, K_SORT, K_GRID
 extern const char *kclassName[K_NCLASS];
 
 // device-side error bits (Ctx::d_flags[0])
-enum DevErr { ERR_POS_RANGE = 1, ERR_CAPACITY = 2, ERR_VEL_MAX = 4 };
+enum DevErr { ERR_POS_RANGE = 1, ERR_CAPACITY = 2, ERR_VEL_MAX = 4, ERR_P2P_TIMEOUT = 8 };
 
 // fixed-point scale of the deposition accumulators: weights in [0,1] are summed as
 // round(w * 2^46) in 64-bit integers, so a node can take 2^17 particles per species before the
@@ -135,6 +135,19 @@ inline int gridFor(long n, int block, int maxBlocks){
 
 // ---- transport (exchange steps between ranks) ----
 struct Msg { int peer; int tag; void *ptr; size_t bytes; };
+// Peer-to-peer arena of a rank (NVLink): six mailbox planes (lower/upper side of x, y, z) that the neighbours' smoother
+// kernels store their boundary layers into, and one arrival counter per plane.  Every rank's arena is mapped into
+// every other rank (CUDA IPC), so a kernel addresses a neighbour's plane as peerArena[rank] + the same offset.
+#define P2P_PLANE_CAP (1L<<18)            // doubles per mailbox plane (faces up to 512 x 512)
+struct P2P {
+	char *arena = nullptr;                // local arena: [64 x u64 flags][6 planes x P2P_PLANE_CAP doubles]
+	std::vector<char*> peerArena;         // indexed by rank; [own rank] = arena
+	unsigned long long seq = 0;           // exchanges issued so far (identical on all ranks: same call sequence)
+	static size_t flagBytes(){ return 64*sizeof(unsigned long long); }
+	static size_t bytes(){ return flagBytes() + 6*P2P_PLANE_CAP*sizeof(double); }
+	static double *plane(char *a, int i){ return (double*)(a + flagBytes()) + (size_t)i*P2P_PLANE_CAP; }
+	static unsigned long long *flag(char *a, int i){ return (unsigned long long*)a + i; }
+};
 struct Transport {
 	virtual ~Transport() {}
 	// all sends and receives of one exchange step; device pointers.  A message is identified by
@@ -144,6 +157,7 @@ struct Transport {
 	virtual void allgatherLong(Ctx *c, const long *h_in, int n, long *h_out) = 0;  // host values, blocking
 	virtual void barrier(Ctx *c) = 0;
 	virtual const char *name() const = 0;
+	virtual P2P *p2p() { return nullptr; }     // peer-memory arena, if this transport has one
 };
 Transport *makeSelfTransport();
 void localCopies(Ctx *c, std::vector<Msg> &sends, std::vector<Msg> &recvs);   // matches and removes self messages
@@ -158,6 +172,7 @@ void gridScale(Ctx *c, DevGrid *g, double num);
 void gridZero(Ctx *c, DevGrid *g);
 void gridHaloDim(Ctx *c, DevGrid *g, const MpiInfo *m, int d /*1..3*/, int add, int dir);
 void gridHalo(Ctx *c, DevGrid *g, const MpiInfo *m, int add, int dir);
+void gridHaloFaces(Ctx *c, DevGrid *g, const MpiInfo *m);      // faces of the decomposed dimensions only, one exchange
 void gridNeutralize(Ctx *c, DevGrid *g, const MpiInfo *m);
 void gridAddTo(Ctx *c, DevGrid *r, const DevGrid *a);
 // sum over the true grid of val (mode 0), val^2 after squaring in place (mode 1) or val*other (mode 2);

@@ -71,6 +71,7 @@ void checkDeviceFlags(Ctx *c, const char *where){
 	PINC_CUDA(cudaMemsetAsync(c->d_flags, 0, sizeof(int), c->stream));
 	if(f & ERR_POS_RANGE) fatal("%s: particle outside the local grid (not migrated, or |v| >= 1 cell per step)", where);
 	if(f & ERR_CAPACITY)  fatal("%s: particle buffer capacity exceeded", where);
+	if(f & ERR_P2P_TIMEOUT) fatal("%s: a neighbour rank did not arrive within 3 s (peer-memory smoother)", where);
 	fatal("%s: device error flags 0x%x", where, f);
 }
 
@@ -189,8 +190,8 @@ DevGrid *devGrid(Ctx *c, const Grid *g, bool upload){
 	long ms = 0;
 	for(int d = 0; d < 3; d++){ long sl = dg->n/dg->size[d]; if(sl > ms) ms = sl; }
 	dg->maxSlice = ms;
-	PINC_CUDA(cudaMalloc(&dg->d_send, (size_t)2*ms*sizeof(double)));
-	PINC_CUDA(cudaMalloc(&dg->d_recv, (size_t)2*ms*sizeof(double)));
+	PINC_CUDA(cudaMalloc(&dg->d_send, (size_t)6*ms*sizeof(double)));     // up to 3 dimensions x 2 directions in one exchange
+	PINC_CUDA(cudaMalloc(&dg->d_recv, (size_t)6*ms*sizeof(double)));
 	if(upload) PINC_CUDA(cudaMemcpyAsync(dg->d, g->val, (size_t)dg->n*sizeof(double), cudaMemcpyHostToDevice, c->stream));
 	else PINC_CUDA(cudaMemsetAsync(dg->d, 0, (size_t)dg->n*sizeof(double), c->stream));
 	c->grids[g] = dg;

@@ -117,6 +117,50 @@ void gridHaloDim(Ctx *c, DevGrid *g, const MpiInfo *m, int d, int add, int dir){
 	PINC_LAUNCH(c, K_HALO, 16.0*ns, (k_slice_unpack<<<blocks,256,0,c->stream>>>(g->d, g->d_recv, D, dd, loPlace, ns, add)));
 	PINC_LAUNCH(c, K_HALO, 16.0*ns, (k_slice_unpack<<<blocks,256,0,c->stream>>>(g->d, g->d_recv + ns, D, dd, upPlace, ns, add)));
 }
+// Face-only ghost fill (setSlice, TOHALO) of the decomposed dimensions in ONE exchange: what a 7-point stencil
+// needs between two half-sweeps.  Unlike gHaloOp's dimension-by-dimension sequence it does not propagate edge and
+// corner ghosts (the rims of a face may be stale); callers that need those use gridHalo.
+struct FacePar { int dd[6], take[6], place[6]; long ns[6], off[7]; int n; };
+__global__ void k_faces_pack(const double *__restrict__ v, double *__restrict__ buf, Dims D, FacePar F){
+	long e = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; e < F.off[F.n]; e += st){
+		int f = 0; while(f+1 < F.n && e >= F.off[f+1]) f++;
+		buf[e] = v[sliceElem(D, F.dd[f], F.take[f], e - F.off[f])];
+	}
+}
+__global__ void k_faces_unpack(double *__restrict__ v, const double *__restrict__ buf, Dims D, FacePar F){
+	long e = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; e < F.off[F.n]; e += st){
+		int f = 0; while(f+1 < F.n && e >= F.off[f+1]) f++;
+		v[sliceElem(D, F.dd[f], F.place[f], e - F.off[f])] = buf[e];
+	}
+}
+void gridHaloFaces(Ctx *c, DevGrid *g, const MpiInfo *m){
+	FacePar F{}; F.n = 0; F.off[0] = 0;
+	std::vector<Msg> sends, recvs;
+	for(int dd = 0; dd < 3; dd++){
+		if(m->nSubdomains[dd] == 1) continue;
+		int sz = g->size[dd];
+		long ns = g->n / sz;
+		int upper = dimNeighbor(m, dd, +1), lower = dimNeighbor(m, dd, -1);
+		// slab 2*i: my upper true layer -> upper neighbour's lower ghost; slab 2*i+1: my lower true layer -> lower neighbour's upper ghost
+		int f = F.n;
+		F.dd[f] = dd; F.take[f] = sz-2; F.place[f] = 0;    F.ns[f] = ns; F.off[f+1] = F.off[f] + ns;
+		F.dd[f+1] = dd; F.take[f+1] = 1; F.place[f+1] = sz-1; F.ns[f+1] = ns; F.off[f+2] = F.off[f+1] + ns;
+		size_t bytes = (size_t)ns*sizeof(double);
+		sends.push_back({upper, 2*dd,   g->d_send + F.off[f],   bytes});
+		sends.push_back({lower, 2*dd+1, g->d_send + F.off[f+1], bytes});
+		recvs.push_back({lower, 2*dd,   g->d_recv + F.off[f],   bytes});
+		recvs.push_back({upper, 2*dd+1, g->d_recv + F.off[f+1], bytes});
+		F.n += 2;
+	}
+	if(F.n == 0) return;
+	if(F.off[F.n] > 6*g->maxSlice) fatal("gridHaloFaces: exchange buffer too small");
+	int blocks = gridFor(F.off[F.n], 256, c->numSMs*4);
+	PINC_LAUNCH(c, K_HALO, 16.0*F.off[F.n], (k_faces_pack<<<blocks,256,0,c->stream>>>(g->d, g->d_send, dimsOf(g), F)));
+	c->tp->exchange(c, sends, recvs);
+	PINC_LAUNCH(c, K_HALO, 16.0*F.off[F.n], (k_faces_unpack<<<blocks,256,0,c->stream>>>(g->d, g->d_recv, dimsOf(g), F)));
+}
 void gridHalo(Ctx *c, DevGrid *g, const MpiInfo *m, int add, int dir){
 	for(int d = 1; d <= 3; d++) gridHaloDim(c, g, m, d, add, dir);
 }

@@ -142,8 +142,171 @@ __global__ void k_prolong_pass(double *__restrict__ f, int s0, int s1, int s2, c
 static inline int tGrid(Ctx *c, long nt){ return gridFor(nt, 256, c->numSMs*8); }
 static inline long trueCount(const DevGrid *g){ return (long)g->tsize[0]*g->tsize[1]*g->tsize[2]; }
 
+// one colour with per-dimension periodic wrap (bit d of wrapMask: dimension d is not decomposed, read the periodic
+// image instead of the ghost); the other dimensions read ghosts that gridHaloFaces keeps current
+__global__ void k_gs_colour_w(double *__restrict__ phi, const double *__restrict__ rho, int s0, int s1, int s2, int parity, int wrapMask){
+	int t0 = s0-2, t1 = s1-2, t2 = s2-2;
+	long nt = (long)t0*t1*t2;
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; i < nt; i += st){
+		int j, k, l; truePoint(i, t0, t1, j, k, l);
+		if(((j+k+l)&1) != parity) continue;
+		int ju = (wrapMask&1) ? upI<true>(j,s0) : j+1, jd = (wrapMask&1) ? dnI<true>(j,s0) : j-1;
+		int ku = (wrapMask&2) ? upI<true>(k,s1) : k+1, kd = (wrapMask&2) ? dnI<true>(k,s1) : k-1;
+		int lu = (wrapMask&4) ? upI<true>(l,s2) : l+1, ld = (wrapMask&4) ? dnI<true>(l,s2) : l-1;
+		const double coeff = 1./6.;
+		phi[ix(j,k,l,s0,s1)] = coeff*(ldg2(phi + ix(ju,k,l,s0,s1)) + ldg2(phi + ix(jd,k,l,s0,s1)) + ldg2(phi + ix(j,ku,l,s0,s1))
+			+ ldg2(phi + ix(j,kd,l,s0,s1)) + ldg2(phi + ix(j,k,lu,s0,s1)) + ldg2(phi + ix(j,k,ld,s0,s1)) + ldg2(rho + ix(j,k,l,s0,s1)));
+	}
+}
+
+// ---- multi-rank smoother over peer memory (NVLink): one kernel per half-sweep, no pack/unpack, no NCCL call --------
+// A rank's ghost values of phi live in its six mailbox planes (P2P in common.h).  A half-sweep kernel (1) waits until
+// the neighbours' previous half-sweep has arrived (their arrival counters in MY arena), (2) updates its colour,
+// reading ghosts of the decomposed dimensions from the mailbox, and stores every boundary node it updates straight
+// into the neighbour's mailbox plane, (3) the last block to finish fences and bumps the neighbours' counters.  Nodes of
+// one colour only read the other colour, so a neighbour that is one half-sweep ahead never overwrites what is being read.
+struct P2PArgs {
+	const double *myMail[6];        // [2*dd + side]: neighbour's boundary layer on my lower (0) / upper (1) side of dim dd
+	double *peerMail[6];            // [2*dd + 0]: upper neighbour's lower-side plane, [2*dd + 1]: lower neighbour's upper-side plane
+	const unsigned long long *myFlag;     // [6] arrival counters in my arena
+	unsigned long long *peerFlag[6];      // counter of peerMail[i] in the neighbour's arena
+	unsigned long long *ticket;           // block counter (local)
+	unsigned long long seq;
+	int active[3];
+};
+__device__ __forceinline__ void p2pWait(const P2PArgs &A, unsigned long long need, int *flags){
+	if(threadIdx.x == 0){
+		long long t0 = clock64();
+		for(int i = 0; i < 6; i++){
+			if(!A.active[i>>1]) continue;
+			while(*((volatile const unsigned long long*)&A.myFlag[i]) < need){
+				if(clock64() - t0 > 6000000000LL){ atomicOr(flags, ERR_P2P_TIMEOUT); break; }     // ~3 s: report, do not hang
+			}
+		}
+		__threadfence_system();
+	}
+	__syncthreads();
+}
+__device__ __forceinline__ void p2pSignal(const P2PArgs &A){
+	__syncthreads();
+	if(threadIdx.x == 0){
+		__threadfence_system();
+		unsigned long long old = atomicAdd(A.ticket, 1ULL);
+		if(old == gridDim.x - 1){
+			atomicExch(A.ticket, 0ULL);
+			__threadfence_system();
+			for(int i = 0; i < 6; i++) if(A.active[i>>1]) *((volatile unsigned long long*)A.peerFlag[i]) = A.seq;
+		}
+	}
+}
+__device__ __forceinline__ double ldv(const double *p){ return *((volatile const double*)p); }
+// publish both boundary layers of every decomposed dimension (start of a smoother call)
+__global__ void k_p2p_publish(const double *__restrict__ phi, int s0, int s1, int s2, P2PArgs A){
+	long st = (long)gridDim.x*blockDim.x, i0 = blockIdx.x*(long)blockDim.x + threadIdx.x;
+	int sz[3] = {s0, s1, s2};
+	for(int dd = 0; dd < 3; dd++){
+		if(!A.active[dd]) continue;
+		int a = dd == 0 ? s1 : s0, b = dd == 2 ? s1 : s2;          // extents of the plane's two axes (ghost-inclusive)
+		long np = (long)a*b;
+		for(long i = i0; i < np; i += st){
+			int u = (int)(i % a), v = (int)(i / a);
+			int jU[3], jL[3];
+			if(dd == 0){ jU[0] = sz[0]-2; jU[1] = u; jU[2] = v; } else if(dd == 1){ jU[0] = u; jU[1] = sz[1]-2; jU[2] = v; } else { jU[0] = u; jU[1] = v; jU[2] = sz[2]-2; }
+			jL[0] = jU[0]; jL[1] = jU[1]; jL[2] = jU[2]; jL[dd] = 1;
+			A.peerMail[2*dd][i]   = ldg2(phi + ix(jU[0],jU[1],jU[2],s0,s1));
+			A.peerMail[2*dd+1][i] = ldg2(phi + ix(jL[0],jL[1],jL[2],s0,s1));
+		}
+	}
+	p2pSignal(A);
+}
+__global__ void k_gs_p2p(double *__restrict__ phi, const double *__restrict__ rho, int s0, int s1, int s2, int parity, int wrapMask, P2PArgs A, int *flags){
+	p2pWait(A, A.seq - 1, flags);
+	int t0 = s0-2, t1 = s1-2, t2 = s2-2;
+	long nt = (long)t0*t1*t2;
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; i < nt; i += st){
+		int j, k, l; truePoint(i, t0, t1, j, k, l);
+		if(((j+k+l)&1) != parity) continue;
+		double a, b, c, d, e, f;
+		if(wrapMask&1){ a = ldg2(phi + ix(upI<true>(j,s0),k,l,s0,s1)); b = ldg2(phi + ix(dnI<true>(j,s0),k,l,s0,s1)); }
+		else { a = j == t0 ? ldv(A.myMail[1] + (k + (long)s1*l)) : ldg2(phi + ix(j+1,k,l,s0,s1)); b = j == 1 ? ldv(A.myMail[0] + (k + (long)s1*l)) : ldg2(phi + ix(j-1,k,l,s0,s1)); }
+		if(wrapMask&2){ c = ldg2(phi + ix(j,upI<true>(k,s1),l,s0,s1)); d = ldg2(phi + ix(j,dnI<true>(k,s1),l,s0,s1)); }
+		else { c = k == t1 ? ldv(A.myMail[3] + (j + (long)s0*l)) : ldg2(phi + ix(j,k+1,l,s0,s1)); d = k == 1 ? ldv(A.myMail[2] + (j + (long)s0*l)) : ldg2(phi + ix(j,k-1,l,s0,s1)); }
+		if(wrapMask&4){ e = ldg2(phi + ix(j,k,upI<true>(l,s2),s0,s1)); f = ldg2(phi + ix(j,k,dnI<true>(l,s2),s0,s1)); }
+		else { e = l == t2 ? ldv(A.myMail[5] + (j + (long)s0*k)) : ldg2(phi + ix(j,k,l+1,s0,s1)); f = l == 1 ? ldv(A.myMail[4] + (j + (long)s0*k)) : ldg2(phi + ix(j,k,l-1,s0,s1)); }
+		const double coeff = 1./6.;
+		double v = coeff*(a + b + c + d + e + f + ldg2(rho + ix(j,k,l,s0,s1)));
+		phi[ix(j,k,l,s0,s1)] = v;
+		if(!(wrapMask&1)){ if(j == t0) A.peerMail[0][k + (long)s1*l] = v; if(j == 1) A.peerMail[1][k + (long)s1*l] = v; }
+		if(!(wrapMask&2)){ if(k == t1) A.peerMail[2][j + (long)s0*l] = v; if(k == 1) A.peerMail[3][j + (long)s0*l] = v; }
+		if(!(wrapMask&4)){ if(l == t2) A.peerMail[4][j + (long)s0*k] = v; if(l == 1) A.peerMail[5][j + (long)s0*k] = v; }
+	}
+	p2pSignal(A);
+}
+static int dimNb(const MpiInfo *m, int dd, int dir){
+	int nb[3];
+	for(int d = 0; d < 3; d++) nb[d] = m->subdomain[d];
+	nb[dd] = (nb[dd] + dir + m->nSubdomains[dd]) % m->nSubdomains[dd];
+	return nb[0] + m->nSubdomains[0]*(nb[1] + m->nSubdomains[1]*nb[2]);
+}
+static bool p2pArgs(Ctx *c, DevGrid *phi, const MpiInfo *m, P2PArgs &A){
+	P2P *p = c->tp->p2p();
+	if(!p) return false;
+	for(int dd = 0; dd < 3; dd++){
+		long face = phi->n / phi->size[dd];
+		if(face > P2P_PLANE_CAP) return false;
+		A.active[dd] = m->nSubdomains[dd] > 1;
+		char *up = p->peerArena[dimNb(m, dd, +1)], *lo = p->peerArena[dimNb(m, dd, -1)];
+		A.myMail[2*dd] = P2P::plane(p->arena, 2*dd); A.myMail[2*dd+1] = P2P::plane(p->arena, 2*dd+1);
+		A.peerMail[2*dd] = P2P::plane(up, 2*dd);          // my upper layer is the upper neighbour's lower-side ghost
+		A.peerMail[2*dd+1] = P2P::plane(lo, 2*dd+1);      // my lower layer is the lower neighbour's upper-side ghost
+		A.peerFlag[2*dd] = P2P::flag(up, 2*dd); A.peerFlag[2*dd+1] = P2P::flag(lo, 2*dd+1);
+	}
+	A.myFlag = P2P::flag(p->arena, 0);
+	A.ticket = P2P::flag(p->arena, 8);
+	return true;
+}
+
+extern int g_mgMode, g_mgForceCluster;
+// 0 ops, 1 fused-exact, 2 auto, 3 auto-exact (resolved from $PINC_B200_MG at first use; pincMgSetMode overrides)
+static int mgMode(){
+	if(g_mgMode < 0){
+		const char *e = getenv("PINC_B200_MG");
+		g_mgMode = !e ? 2 : !strcmp(e, "ops") ? 0 : !strcmp(e, "fused") ? 1 : !strcmp(e, "cluster-exact") ? 3 : 2;
+		if(e && !strcmp(e, "cluster-always")) g_mgForceCluster = 1;
+	}
+	return g_mgMode;
+}
 static void opGS(Ctx *c, DevGrid *phi, DevGrid *rho, int nCycles, const MpiInfo *m){
 	long nt = trueCount(phi);
+	if(m->mpiSize > 1 && mgMode() == 2 && nCycles > 0){
+		// multi-rank lean path: between half-sweeps only the faces of the decomposed dimensions are exchanged (one
+		// grouped exchange), gBnd's mean subtraction is applied once at the end (see mgcluster.cu for why that is
+		// the same function), then the full dimension-by-dimension halo restores edge and corner ghosts
+		int wrapMask = (m->nSubdomains[0] == 1 ? 1 : 0) | (m->nSubdomains[1] == 1 ? 2 : 0) | (m->nSubdomains[2] == 1 ? 4 : 0);
+		P2PArgs A{};
+		if(p2pArgs(c, phi, m, A)){
+			P2P *p = c->tp->p2p();
+			int blocks = gridFor(nt, 256, c->numSMs);            // one wave: every block must be resident to reach the ticket
+			A.seq = ++p->seq;
+			PINC_LAUNCH(c, K_HALO, 16.0*phi->n/phi->size[2], (k_p2p_publish<<<blocks,256,0,c->stream>>>(phi->d, phi->size[0], phi->size[1], phi->size[2], A)));
+			for(int h = 0; h < 2*nCycles; h++){
+				A.seq = ++p->seq;
+				PINC_LAUNCH(c, K_GS, 12.0*nt, (k_gs_p2p<<<blocks,256,0,c->stream>>>(phi->d, rho->d, phi->size[0], phi->size[1], phi->size[2], (h&1) ? 0 : 1, wrapMask, A, c->d_flags)));
+			}
+			gridHalo(c, phi, m, 0, 0);
+			gridNeutralize(c, phi, m);
+			return;
+		}
+		for(int h = 0; h < 2*nCycles; h++){
+			PINC_LAUNCH(c, K_GS, 12.0*nt, (k_gs_colour_w<<<tGrid(c,nt),256,0,c->stream>>>(phi->d, rho->d, phi->size[0], phi->size[1], phi->size[2], (h&1) ? 0 : 1, wrapMask)));
+			gridHaloFaces(c, phi, m);
+		}
+		gridHalo(c, phi, m, 0, 0);
+		gridNeutralize(c, phi, m);
+		return;
+	}
 	for(int cyc = 0; cyc < nCycles; cyc++)
 		for(int parity = 1; parity >= 0; parity--){
 			PINC_LAUNCH(c, K_GS, 12.0*nt, (k_gs_colour<<<tGrid(c,nt),256,0,c->stream>>>(phi->d, rho->d, phi->size[0], phi->size[1], phi->size[2], parity)));
@@ -471,9 +634,9 @@ __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
 	}
 }
 
+int g_mgMode = -1;
 // -1: from $PINC_B200_MG at first use; 0 ops; 1 fused (grid-wide persistent kernel, gBnd per half-sweep);
 // 2 cluster (DSMEM-resident, gBnd batched per smoother call; default); 3 cluster with gBnd per half-sweep
-int g_mgMode = -1;
 int g_mgForceCluster = 0;     // $PINC_B200_MG=cluster-always: use the cluster kernel whenever it fits
 static void ensureHist(Ctx *c){
 	if(c->d_mgHist) return;
@@ -483,12 +646,7 @@ static void ensureHist(Ctx *c){
 }
 
 static bool fusedEligible(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *m){
-	if(g_mgMode < 0){
-		const char *e = getenv("PINC_B200_MG");
-		g_mgMode = !e ? 2 : !strcmp(e, "ops") ? 0 : !strcmp(e, "fused") ? 1 : !strcmp(e, "cluster-exact") ? 3 : 2;
-		if(e && !strcmp(e, "cluster-always")) g_mgForceCluster = 1;
-	}
-	if(!g_mgMode) return false;
+	if(!mgMode()) return false;
 	if(m->mpiSize != 1) return false;
 	int nL = mgRho->nLevels;
 	if(nL < 2 || nL > MG_MAXLEV) return false;

@@ -151,7 +151,42 @@ static NcclApi *ncclApi(){
 
 struct NcclTransport : Transport {
 	ncclComm_t comm = nullptr;
-	~NcclTransport() override { if(comm) ncclApi()->CommDestroy(comm); }
+	P2P peer; bool peerOk = false;
+	P2P *p2p() override { return peerOk ? &peer : nullptr; }
+	~NcclTransport() override {
+		for(size_t r = 0; r < peer.peerArena.size(); r++) if(peer.peerArena[r] && peer.peerArena[r] != peer.arena) cudaIpcCloseMemHandle(peer.peerArena[r]);
+		if(peer.arena) cudaFree(peer.arena);
+		if(comm) ncclApi()->CommDestroy(comm);
+	}
+	// map every rank's arena into this process (all ranks are processes on one NVLink/NVSwitch node)
+	void setupPeer(Ctx *c){
+		if(getenv("PINC_B200_NO_P2P")) return;
+		NcclApi *n = ncclApi();
+		int ok = cudaMalloc(&peer.arena, P2P::bytes()) == cudaSuccess;
+		cudaIpcMemHandle_t mine; memset(&mine, 0, sizeof mine);
+		if(ok){ cudaMemset(peer.arena, 0, P2P::bytes()); ok = cudaIpcGetMemHandle(&mine, peer.arena) == cudaSuccess; }
+		char *d = (char*)tmpBuffer(c, sizeof(mine)*(c->size + 1));
+		PINC_CUDA(cudaMemcpyAsync(d, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+		PINC_NCCL(n->AllGather(d, d + sizeof mine, sizeof mine, ncclChar, comm, c->stream));
+		std::vector<cudaIpcMemHandle_t> all(c->size);
+		PINC_CUDA(cudaMemcpyAsync(all.data(), d + sizeof mine, sizeof(mine)*c->size, cudaMemcpyDeviceToHost, c->stream));
+		streamSync(c);
+		peer.peerArena.assign(c->size, nullptr);
+		for(int r = 0; r < c->size && ok; r++){
+			if(r == c->rank){ peer.peerArena[r] = peer.arena; continue; }
+			void *p = nullptr;
+			if(cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess){ ok = 0; cudaGetLastError(); }
+			peer.peerArena[r] = (char*)p;
+		}
+		// everybody or nobody
+		double v = ok ? 0.0 : 1.0;
+		PINC_CUDA(cudaMemcpyAsync(c->d_scal + 254, &v, sizeof v, cudaMemcpyHostToDevice, c->stream));
+		PINC_NCCL(n->AllReduce(c->d_scal + 254, c->d_scal + 254, 1, ncclDouble, ncclSum, comm, c->stream));
+		PINC_CUDA(cudaMemcpyAsync(&v, c->d_scal + 254, sizeof v, cudaMemcpyDeviceToHost, c->stream));
+		streamSync(c);
+		peerOk = (v == 0.0);
+		if(!peerOk && c->rank == 0) fprintf(stderr, "PINC-B200 WARNING: peer-to-peer arena unavailable, halo exchange stays on NCCL send/recv\n");
+	}
 	void exchange(Ctx *c, std::vector<Msg> sends, std::vector<Msg> recvs) override {
 		localCopies(c, sends, recvs);
 		// NCCL pairs the sends and receives of two ranks in posting order: order both sides by tag
@@ -221,6 +256,7 @@ void pincCommInitNccl(PincCtx *ctx, const char *uniqueId128){
 	PINC_NCCL(ncclApi()->CommInitRank(&t->comm, c->size, id, c->rank));
 	delete c->tp;
 	c->tp = t;
+	t->setupPeer(c);
 }
 
 const char *pincTransportName(void){ return cur()->tp->name(); }
