@@ -8,7 +8,7 @@
  * host structs with the plain-argument constructors, places particles (pPosLattice + pPosPerturb + pVelZero as
  * main.c:144-152 does, or uniform + Maxwellian when the ini gives thermal velocities), then time-steps.
  * Extensions (not PINC keys): population:thermalVelocityCells (sigma in cells/step), methods:fused = 1 (run
- * puAcc3D1KE + puMove + classification as one pass), time:report = N.
+ * puAcc3D1KE + puMove + classification as one pass; 2: the deposition of the staying particles joins the pass), time:report = N.
  * Multi-rank without MPI: RANK / WORLD_SIZE / LOCAL_RANK from the environment (as torchrun sets them) and the NCCL
  * id passed through the file $PINC_B200_ID_FILE. */
 #define _POSIX_C_SOURCE 200809L
@@ -284,7 +284,8 @@ int main(int argc, char **argv){
 		gFinDiff1st(phi, E);
 		gHaloOp((funPtr)setSlice, E, mpiInfo, TOHALO);
 		gMul(E, -1.);
-		if(fused && withKE){ pincAccMove3D1KE(pop, E, mpiInfo); moved = 1; }
+		if(fused == 2 && withKE){ pincAccMoveDistr3D1KE(pop, E, rho, mpiInfo); moved = 1; }
+		else if(fused && withKE){ pincAccMove3D1KE(pop, E, mpiInfo); moved = 1; }
 		else if(withKE) puAcc3D1KE(pop, E);
 		else puAcc3D1(pop, E);
 		if(withKE) pSumKinEnergy(pop);

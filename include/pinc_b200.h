@@ -251,6 +251,10 @@ void pincDeviceSynchronize(void);
 /* fused step helpers (same arithmetic as the separate entry points, one pass over the particles):
  * puAcc3D1KE immediately followed by puMove + puExtractEmigrants3D classification. */
 void pincAccMove3D1KE(Population *pop, Grid *E, MpiInfo *mpiInfo);
+/* ... and additionally the next step's puDistr3D1 for the particles that stay on this rank: their weights go into
+ * rho's integer accumulators in the same pass; the following puDistr3D1(pop, rho) only adds the immigrants and
+ * converts (bit-identical rho, the accumulation is order independent). */
+void pincAccMoveDistr3D1KE(Population *pop, Grid *E, Grid *rho, MpiInfo *mpiInfo);
 
 /* CUDA-event timing on the context's stream (what bench.py brackets the step with) */
 void   pincTimerStart(void);

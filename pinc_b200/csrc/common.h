@@ -40,7 +40,8 @@ struct DevGrid {
 	double *d_send = nullptr;   // 2 slabs (up, down) of the largest face
 	double *d_recv = nullptr;
 	long maxSlice = 0;
-	long long *d_fix = nullptr; // fixed-point accumulator for deposition (scalar grids, lazily)
+	long long *d_fixS[8] = {nullptr};   // per-species fixed-point accumulators of the deposition (scalar grids, lazily)
+	bool fixDirty = false;              // accumulators hold deposits nobody consumed (cleared before the next use)
 };
 
 struct DevPop {
@@ -67,6 +68,7 @@ struct DevPop {
 	double *d_immig = nullptr;
 	long immigCap = 0;
 	bool extracted = false;     // emigrants sit behind iStop[s], binned by neighbour, not yet packed
+	DevGrid *predep = nullptr;  // the stayers of the current positions are already deposited into this grid's accumulators
 };
 
 struct ProfEvent { cudaEvent_t a, b; int cls; };

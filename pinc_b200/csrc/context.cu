@@ -155,6 +155,7 @@ static void popUpload(Ctx *c, DevPop *dp){
 	for(int s = 0; s < dp->nS; s++) dp->sortedN[s] = 0;
 	dp->keysValid = false;
 	dp->extracted = false;
+	if(dp->predep){ dp->predep->fixDirty = true; dp->predep = nullptr; }
 }
 
 static void popDownload(Ctx *c, DevPop *dp){
@@ -217,7 +218,7 @@ DevPop *devPop(Ctx *c, const Population *p, bool upload){
 }
 
 static void freeDevGrid(DevGrid *g){
-	cudaFree(g->d); cudaFree(g->d_send); cudaFree(g->d_recv); if(g->d_fix) cudaFree(g->d_fix);
+	cudaFree(g->d); cudaFree(g->d_send); cudaFree(g->d_recv); for(int s = 0; s < 8; s++) if(g->d_fixS[s]) cudaFree(g->d_fixS[s]);
 	delete g;
 }
 static void freeDevPop(DevPop *p){

@@ -370,7 +370,7 @@ template<bool SMALL, bool EXACT> __device__ void cBottom(const CPlan &P, CK &K){
 	const CLvl &L = P.L[P.nLevels-1];
 	cNeutralizeRho<SMALL>(L, K);
 	cGS<SMALL,EXACT>(L, P.nCoarse, 0.0, K);
-	cNeutralizePhi<SMALL>(L, K);
+	if(EXACT || P.nCoarse <= 0) cNeutralizePhi<SMALL>(L, K);      // batched mode: cGS just ended with this gBnd
 }
 // trilinear prolongation in the nesting of the reference's three passes (z, then y, then x; multigrid.c:1127-1238)
 static __device__ __forceinline__ double cProlZ(const CLvl &C, const CK &K, int J, int Kk, int l){
@@ -404,7 +404,7 @@ template<bool SMALL, bool EXACT> static __device__ __noinline__ void cUp(const C
 	double avg = sumAll<SMALL>(K, acc)/((double)L.nx*L.ny*L.nz);
 	ps.~ProfScope(); ps.p = nullptr;
 	cGS<SMALL,EXACT>(L, P.nPost, avg, K);
-	cNeutralizePhi<SMALL>(L, K);
+	if(EXACT || P.nPost <= 0) cNeutralizePhi<SMALL>(L, K);
 }
 static __device__ __noinline__ void cGhosts(double *v, const CLvl &L, const CK &K){
 	int s0 = L.s0, s1 = L.s1, s2 = L.nz + 2;

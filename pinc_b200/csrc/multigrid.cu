@@ -375,6 +375,7 @@ struct MgPlan {
 	unsigned barBase;
 	int exact;               // gBnd after every half-sweep (pending shifts) instead of once per smoother call
 	int smemSmall;           // small levels live in CTA 0's shared memory (descriptors in C)
+	long long *prof;         // optional cycle accounting ($PINC_B200_MGPROF)
 	CPlan C;
 };
 
@@ -383,6 +384,7 @@ struct Scope {
 	unsigned *bar; unsigned gen;
 	double *partial; int flip;
 	double *sh;              // 18 doubles of shared memory
+	CK *K;                   // cycle accounting
 	__device__ __forceinline__ long tid() const { return single ? threadIdx.x : blockIdx.x*(long)blockDim.x + threadIdx.x; }
 	__device__ __forceinline__ long nthr() const { return single ? blockDim.x : (long)gridDim.x*blockDim.x; }
 	// Grid barrier: one monotonically increasing arrival counter (no reset, no generation word).  The fence
@@ -442,6 +444,7 @@ __device__ void fNeutralize(double *v, int s0, int s1, int s2, Scope &S){
 
 // mgGS3D with gBnd's mean subtraction carried as pending shifts.  sIn: shift still pending on every value at entry.
 __device__ void fGS(const Lvl &L, int nCycles, double sIn, int exact, Scope &S){
+	ProfScope ps(*S.K, S.single ? PS_GS_SMALL : PS_GS_BIG);
 	int s0 = L.s0, s1 = L.s1, s2 = L.s2;
 	int t0 = s0-2, t1 = s1-2, t2 = s2-2; long nt = (long)t0*t1*t2;
 	int half = t0/2; long items = (long)half*t1*t2;
@@ -457,18 +460,31 @@ __device__ void fGS(const Lvl &L, int nCycles, double sIn, int exact, Scope &S){
 	for(int h = 0; h < 2*nCycles; h++){
 		int parity = (h & 1) ? 0 : 1;
 		double acc = 0;
-		for(long i = S.tid(); i < items; i += S.nthr()){
-			unsigned ui = (unsigned)i, r = ui / (unsigned)half; int m = (int)(ui - r*(unsigned)half);
-			unsigned lq = r / (unsigned)t1; int k = (int)(r - lq*(unsigned)t1) + 1; int l = (int)lq + 1;
-			int ja = 2*m+1;
-			int jOwn = (((ja+k+l)&1) == parity) ? ja : ja+1;
-			int jOth = 2*ja+1 - jOwn;
-			double vn = gsPoint<true>(L.phi, L.rho, jOwn, k, l, s0, s1, s2, sR);
-			if(exact){
-				double vo = ldg2(L.phi + ix(jOth,k,l,s0,s1)) - sR;
-				acc += vn; acc += vo;
+		// two nodes per trip: both nodes' loads are issued before either store (the compiler cannot prove that an
+		// own-colour store does not alias the next node's other-colour loads), so their L2 latencies overlap
+		const long step = S.nthr();
+		for(long i = S.tid(); i < items; i += 2*step){
+			double vn[2], vo[2]; long go[2]; bool ok[2];
+			#pragma unroll
+			for(int w = 0; w < 2; w++){
+				long iw = i + w*step;
+				ok[w] = iw < items;
+				if(!ok[w]) continue;
+				unsigned ui = (unsigned)iw, r = ui / (unsigned)half; int m = (int)(ui - r*(unsigned)half);
+				unsigned lq = r / (unsigned)t1; int k = (int)(r - lq*(unsigned)t1) + 1; int l = (int)lq + 1;
+				int ja = 2*m+1;
+				int jOwn = (((ja+k+l)&1) == parity) ? ja : ja+1;
+				int jOth = 2*ja+1 - jOwn;
+				vn[w] = gsPoint<true>(L.phi, L.rho, jOwn, k, l, s0, s1, s2, sR);
+				if(exact) vo[w] = ldg2(L.phi + ix(jOth,k,l,s0,s1)) - sR;
+				go[w] = ix(jOwn,k,l,s0,s1);
 			}
-			L.phi[ix(jOwn,k,l,s0,s1)] = vn;
+			#pragma unroll
+			for(int w = 0; w < 2; w++){
+				if(!ok[w]) continue;
+				if(exact){ acc += vn[w]; acc += vo[w]; }
+				L.phi[go[w]] = vn[w];
+			}
 		}
 		if(exact){
 			double avg = S.allSum(acc)/(double)nt;
@@ -508,7 +524,7 @@ __device__ void fBottom(const MgPlan &P, Scope &S){
 	const Lvl &L = P.L[P.nLevels-1];
 	fNeutralize(L.rho, L.s0, L.s1, L.s2, S);
 	fGS(L, P.nCoarse, 0.0, P.exact, S);
-	fNeutralize(L.phi, L.s0, L.s1, L.s2, S);
+	if(P.exact || P.nCoarse <= 0) fNeutralize(L.phi, L.s0, L.s1, L.s2, S);      // batched mode: fGS just ended with this gBnd
 }
 // res(q) := P(phi(q+1)); phi(q) += res(q); gBnd; post-smooth; gBnd
 __device__ void fUp(const MgPlan &P, int q, Scope &S){
@@ -525,7 +541,7 @@ __device__ void fUp(const MgPlan &P, int q, Scope &S){
 	}
 	double avg = S.allSum(acc)/(double)nt;
 	fGS(L, P.nPost, avg, P.exact, S);
-	fNeutralize(L.phi, L.s0, L.s1, L.s2, S);
+	if(P.exact || P.nPost <= 0) fNeutralize(L.phi, L.s0, L.s1, L.s2, S);
 }
 __device__ void fGhosts(double *v, int s0, int s1, int s2, Scope &S){
 	long n = (long)s0*s1*s2;
@@ -561,7 +577,7 @@ template<bool EXACT> __device__ void smallSection(const MgPlan &P, CK &K){
 __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
 	__shared__ double sh[18];
 	__shared__ double red[40];
-	CK K{ cg::this_cluster(), 0, 1, mgS, red, 0, nullptr };
+	CK K{ cg::this_cluster(), (int)blockIdx.x, 1, mgS, red, 0, P.prof };
 	if(P.smemSmall && blockIdx.x == 0){
 		for(int q = P.qSmall; q < P.nLevels; q++){
 			const CLvl &L = P.C.L[q];
@@ -576,6 +592,7 @@ __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
 	}
 	Scope Sg; Sg.single = false; Sg.bar = P.bar; Sg.partial = P.partial; Sg.flip = 0; Sg.sh = sh; Sg.gen = 0;
 	if(threadIdx.x == 0) Sg.gen = P.barBase;            // arrival count at kernel start (host-tracked)
+	Sg.K = &K;
 	Scope S1 = Sg; S1.single = true;
 	int b = P.nLevels - 1;
 	int qs = P.qSmall < 0 ? 0 : P.qSmall;
@@ -585,6 +602,7 @@ __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
 		for(int q = 0; q <= b && q < qs; q++){ if(q < b) fDown(P, q, Sg); else fBottom(P, Sg); }
 		if(qs <= b){
 			if(blockIdx.x == 0){
+				ProfScope pss(K, PS_LEVEL0);
 				if(P.smemSmall){
 					if(P.exact) smallSection<true>(P, K); else smallSection<false>(P, K);
 				} else {
@@ -717,6 +735,7 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 	P.barBase = 0;
 	ensureHist(c);
 	P.hist = c->d_mgHist;
+	P.prof = (long long*)mgProfBuffer(c);
 	void *args[] = { &P };
 	{
 		LaunchScope ls(c, K_MGFUSED, work);

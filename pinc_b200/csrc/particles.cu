@@ -48,6 +48,49 @@ __device__ __forceinline__ void histAdd(unsigned *hist, unsigned key, bool act){
 	if(act && lane == __ffs(peers)-1) atomicAdd(&hist[key], (unsigned)__popc(peers));
 }
 
+// round-to-nearest-even of w*2^46 as an integer, by the 1.5*2^52 magic constant: one FMA (w*2^46 is an exact
+// scaling, so the single rounding of the FMA is the rounding to integer) and one integer subtract, instead of a
+// multiply and a (quarter-rate) F2I.S64; identical values to __double2ll_rn(w*2^46) for 0 <= w <= 1.
+__device__ __forceinline__ long long fixw(double w){
+	const double M = 6755399441055744.0;               // 1.5 * 2^52
+	return __double_as_longlong(__fma_rn(w, (double)(1LL<<PINC_FIX_BITS), M)) - __double_as_longlong(M);
+}
+// the eight trilinear weights of a particle at fractional position (xf,yf,zf), products in the reference's order
+// (src/pusher.c:556-563), index = dx + 2*dy + 4*dz
+__device__ __forceinline__ void cornerWeights(double xf, double yf, double zf, long long a[8]){
+	double xc = 1-xf, yc = 1-yf, zc = 1-zf;
+	double cc = xc*yc, fc = xf*yc, cf = xc*yf, ff = xf*yf;
+	a[0] = fixw(cc*zc); a[1] = fixw(fc*zc); a[2] = fixw(cf*zc); a[3] = fixw(ff*zc);
+	a[4] = fixw(cc*zf); a[5] = fixw(fc*zf); a[6] = fixw(cf*zf); a[7] = fixw(ff*zf);
+}
+// transposing butterfly: 8 values x 32 lanes -> the warp total of corner (lane>>2)&7 in every lane, 9 64-bit shuffles
+__device__ __forceinline__ long long warpCornerTotal(long long a[8]){
+	const int lane = threadIdx.x & 31;
+	const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
+	#pragma unroll
+	for(int q = 0; q < 4; q++){
+		long long send = u16 ? a[q] : a[q+4], keep = u16 ? a[q+4] : a[q];
+		a[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+	}
+	#pragma unroll
+	for(int q = 0; q < 2; q++){
+		long long send = u8 ? a[q] : a[q+2], keep = u8 ? a[q+2] : a[q];
+		a[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+	}
+	{
+		long long send = u4 ? a[0] : a[1], keep = u4 ? a[1] : a[0];
+		a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+	}
+	a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
+	a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+	return a[0];
+}
+// node offset of corner (lane>>2)&7 = dx + 2*dy + 4*dz ... held by the lanes with bits 4 (dx), 8 (dy), 16 (dz)
+__device__ __forceinline__ long cornerOffset(long sx, long sxy){
+	const int lane = threadIdx.x & 31;
+	return ((lane & 4) ? 1 : 0) + ((lane & 8) ? sx : 0) + ((lane & 16) ? sxy : 0);
+}
+
 template<int BLOCK> __device__ __forceinline__ double blockSumP(double v){
 	__shared__ double sh[BLOCK/32];
 	for(int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -79,17 +122,22 @@ __global__ void k_move(double *__restrict__ p, const double *__restrict__ v, lon
 // ---- accelerate (src/pusher.c:147-214, 394-483) with the interpolation of :1089-1122 embedded -----
 // KIND 0: leapfrog kick; 1: Boris (half kick, rotation by T then S of THIS particle's velocity, half kick).
 // FUSE 1: also pos += vel (the next step's puMove) and classification of the new position into the sort key.
+// FUSE 2: as 1, plus the deposition of the moved particle (the next step's puDistr3D1) for the particles that stay on
+//         this rank: the lanes of a warp that share a cell (particles are in cell order, ~95 % keep their cell) are
+//         summed with the 9-shuffle butterfly, two groups per warp, stragglers add their eight weights directly.
 struct BorisPar { double T[3], S[3]; };
 template<int KIND, int KE, int FUSE>
-__global__ void __launch_bounds__(256) k_acc(double *__restrict__ P, long cap, long a, long n,
+__global__ void __launch_bounds__(256, 4) k_acc(double *__restrict__ P, long cap, long a, long n,
 		const double *__restrict__ E, long sx3, long sxy3, int gs0, int gs1, int gs2, BorisPar B, double *__restrict__ partial,
-		Thr T, CellSpace C, unsigned *__restrict__ keys, unsigned *__restrict__ hist, int *flags){
+		Thr T, CellSpace C, unsigned *__restrict__ keys, unsigned *__restrict__ hist, int *flags,
+		long long *__restrict__ fix, long fsx, long fsxy){
 	double acc = 0;
 	long stride = (long)gridDim.x*blockDim.x;
 	for(long base = blockIdx.x*(long)blockDim.x; base < n; base += stride){
 		long i = base + threadIdx.x;
 		bool act = i < n;
 		unsigned key = 0;
+		double nx_ = 0, ny_ = 0, nz_ = 0;          // moved position (FUSE 2)
 		if(act){
 			long q = a + i;
 			double x = P[q], y = P[q+cap], z = P[q+2*cap];
@@ -129,9 +177,44 @@ __global__ void __launch_bounds__(256) k_acc(double *__restrict__ P, long cap, l
 				P[q] = x; P[q+cap] = y; P[q+2*cap] = z;
 				key = classify(x, y, z, T, C, flags);
 				keys[q] = key;
+				nx_ = x; ny_ = y; nz_ = z;
 			}
 		}
 		if(FUSE) histAdd(hist, key, act);
+		if(FUSE == 2){
+			const int lane = threadIdx.x & 31;
+			bool stay = act && key < (unsigned)C.nCells;
+			long long w[8];
+			#pragma unroll
+			for(int qq = 0; qq < 8; qq++) w[qq] = 0;
+			if(stay) cornerWeights(nx_ - (double)(int)nx_, ny_ - (double)(int)ny_, nz_ - (double)(int)nz_, w);
+			unsigned remaining = __ballot_sync(0xffffffffu, stay);
+			#pragma unroll 1
+			for(int round = 0; round < 2 && remaining; round++){
+				int leader = __ffs(remaining) - 1;
+				unsigned gkey = __shfl_sync(0xffffffffu, key, leader);
+				bool member = stay && key == gkey;
+				long long v[8];
+				#pragma unroll
+				for(int qq = 0; qq < 8; qq++) v[qq] = member ? w[qq] : 0;
+				long long tot = warpCornerTotal(v);
+				if((lane & 3) == 0 && tot != 0){
+					long cj = gkey % (unsigned)C.nc0, cr = gkey / (unsigned)C.nc0, ck = cr % C.nc1, cl = cr / C.nc1;
+					atomicAdd((unsigned long long*)&fix[cj + fsx*ck + fsxy*cl + cornerOffset(fsx, fsxy)], (unsigned long long)tot);
+				}
+				unsigned done = __ballot_sync(0xffffffffu, member);
+				remaining &= ~done;
+				if(member) stay = false;
+			}
+			if(stay){                                   // a third cell in this warp (rare): eight direct integer REDs
+				long cj = key % (unsigned)C.nc0, cr = key / (unsigned)C.nc0, ck = cr % C.nc1, cl = cr / C.nc1;
+				unsigned long long *f = (unsigned long long*)fix + (cj + fsx*ck + fsxy*cl);
+				atomicAdd(f, (unsigned long long)w[0]); atomicAdd(f+1, (unsigned long long)w[1]);
+				atomicAdd(f+fsx, (unsigned long long)w[2]); atomicAdd(f+fsx+1, (unsigned long long)w[3]);
+				atomicAdd(f+fsxy, (unsigned long long)w[4]); atomicAdd(f+fsxy+1, (unsigned long long)w[5]);
+				atomicAdd(f+fsxy+fsx, (unsigned long long)w[6]); atomicAdd(f+fsxy+fsx+1, (unsigned long long)w[7]);
+			}
+		}
 	}
 	if(KE){
 		acc = blockSumP<256>(acc);
@@ -228,13 +311,6 @@ __global__ void __launch_bounds__(256) k_scatter(const double *__restrict__ src,
 }
 
 // ---- deposition (src/pusher.c:512-572) -----------------------------------------------------------------
-// round-to-nearest-even of w*2^46 as an integer, by the 1.5*2^52 magic constant: one FMA (w*2^46 is an exact
-// scaling, so the single rounding of the FMA is the rounding to integer) and one integer subtract, instead of a
-// multiply and a (quarter-rate) F2I.S64; identical values to __double2ll_rn(w*2^46) for 0 <= w <= 1.
-__device__ __forceinline__ long long fixw(double w){
-	const double M = 6755399441055744.0;               // 1.5 * 2^52
-	return __double_as_longlong(__fma_rn(w, (double)(1LL<<PINC_FIX_BITS), M)) - __double_as_longlong(M);
-}
 
 // sorted prefix: one warp per cell
 __global__ void __launch_bounds__(256, 4) k_distr_cells(const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ Z,
@@ -263,35 +339,15 @@ __global__ void __launch_bounds__(256, 4) k_distr_cells(const double *__restrict
 			#pragma unroll
 			for(int u = 0; u < 3; u++){
 				if(i0 + lane + 32*u >= e) continue;
-				double xf = x[u]-dj, yf = y[u]-dk, zf = z[u]-dl;
-				double xc = 1-xf, yc = 1-yf, zc = 1-zf;
-				double cc = xc*yc, fc = xf*yc, cf = xc*yf, ff = xf*yf;
-				a[0] += fixw(cc*zc); a[1] += fixw(fc*zc); a[2] += fixw(cf*zc); a[3] += fixw(ff*zc);
-				a[4] += fixw(cc*zf); a[5] += fixw(fc*zf); a[6] += fixw(cf*zf); a[7] += fixw(ff*zf);
+				long long w[8];
+				cornerWeights(x[u]-dj, y[u]-dk, z[u]-dl, w);
+				#pragma unroll
+				for(int q = 0; q < 8; q++) a[q] += w[q];
 			}
 		}
-		// transposing butterfly: 8 values x 32 lanes -> one total per corner in 9 64-bit shuffles
-		bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
-		#pragma unroll
-		for(int q = 0; q < 4; q++){
-			long long send = u16 ? a[q] : a[q+4], keep = u16 ? a[q+4] : a[q];
-			a[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-		}
-		#pragma unroll
-		for(int q = 0; q < 2; q++){
-			long long send = u8 ? a[q] : a[q+2], keep = u8 ? a[q+2] : a[q];
-			a[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-		}
-		{
-			long long send = u4 ? a[0] : a[1], keep = u4 ? a[1] : a[0];
-			a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-		}
-		a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
-		a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
-		if((lane & 3) == 0 && a[0] != 0){
-			long node = cj + sx*ck + sxy*cl + (u4 ? 1 : 0) + (u8 ? sx : 0) + (u16 ? sxy : 0);
-			atomicAdd((unsigned long long*)&fix[node], (unsigned long long)a[0]);
-		}
+		long long tot = warpCornerTotal(a);
+		if((lane & 3) == 0 && tot != 0)
+			atomicAdd((unsigned long long*)&fix[cj + sx*ck + sxy*cl + cornerOffset(sx, sxy)], (unsigned long long)tot);
 	}
 }
 // unsorted tail (immigrants appended by puMigrate, or a population that was never binned)
@@ -303,18 +359,17 @@ __global__ void __launch_bounds__(256) k_distr_tail(const double *__restrict__ X
 		double x = X[i], y = Y[i], z = Z[i];
 		int j = (int)x, k = (int)y, l = (int)z;
 		if(!(x >= 0) || !(y >= 0) || !(z >= 0) || j > s0-2 || k > s1-2 || l > s2-2){ atomicOr(flags, ERR_POS_RANGE); continue; }
-		double xf = x-j, yf = y-k, zf = z-l;
-		double xc = 1-xf, yc = 1-yf, zc = 1-zf;
-		double cc = xc*yc, fc = xf*yc, cf = xc*yf, ff = xf*yf;
+		long long w[8];
+		cornerWeights(x-j, y-k, z-l, w);
 		unsigned long long *f = (unsigned long long*)fix + (j + sx*k + sxy*l);
-		atomicAdd(f,          (unsigned long long)fixw(cc*zc));
-		atomicAdd(f+1,        (unsigned long long)fixw(fc*zc));
-		atomicAdd(f+sx,       (unsigned long long)fixw(cf*zc));
-		atomicAdd(f+sx+1,     (unsigned long long)fixw(ff*zc));
-		atomicAdd(f+sxy,      (unsigned long long)fixw(cc*zf));
-		atomicAdd(f+sxy+1,    (unsigned long long)fixw(fc*zf));
-		atomicAdd(f+sxy+sx,   (unsigned long long)fixw(cf*zf));
-		atomicAdd(f+sxy+sx+1, (unsigned long long)fixw(ff*zf));
+		atomicAdd(f,          (unsigned long long)w[0]);
+		atomicAdd(f+1,        (unsigned long long)w[1]);
+		atomicAdd(f+sx,       (unsigned long long)w[2]);
+		atomicAdd(f+sx+1,     (unsigned long long)w[3]);
+		atomicAdd(f+sxy,      (unsigned long long)w[4]);
+		atomicAdd(f+sxy+1,    (unsigned long long)w[5]);
+		atomicAdd(f+sxy+sx,   (unsigned long long)w[6]);
+		atomicAdd(f+sxy+sx+1, (unsigned long long)w[7]);
 	}
 }
 // rho = (rho*(1/q) + sum w)*q, and the integer grid is cleared for the next species
@@ -393,18 +448,39 @@ static void setupCells(Ctx *c, DevPop *dp, const MpiInfo *m){
 }
 static CellSpace cellsOf(const DevPop *dp){ return CellSpace{ dp->nc[0], dp->nc[1], dp->nc[2], dp->nCells }; }
 
+static void dropPredeposit(DevPop *dp);
 static void invalidateOrder(DevPop *dp){
+	dropPredeposit(dp);
 	for(int s = 0; s < dp->nS; s++) dp->sortedN[s] = 0;
 	dp->keysValid = false;
 }
 
 enum AccKind { ACC_LEAP = 0, ACC_BORIS = 1 };
-static void accelerate(Ctx *c, Population *pop, Grid *Egrid, int kind, int ke, const double *T, const double *S, const MpiInfo *fuse){
+static void ensureFix(Ctx *c, DevGrid *rho, int nS){
+	for(int s = 0; s < nS; s++) if(!rho->d_fixS[s]){
+		PINC_CUDA(cudaMalloc(&rho->d_fixS[s], (size_t)rho->n*sizeof(long long)));
+		PINC_CUDA(cudaMemsetAsync(rho->d_fixS[s], 0, (size_t)rho->n*sizeof(long long), c->stream));
+	}
+	if(rho->fixDirty){
+		for(int s = 0; s < nS; s++) PINC_CUDA(cudaMemsetAsync(rho->d_fixS[s], 0, (size_t)rho->n*sizeof(long long), c->stream));
+		rho->fixDirty = false;
+	}
+}
+static void dropPredeposit(DevPop *dp){ if(dp->predep){ dp->predep->fixDirty = true; dp->predep = nullptr; } }
+
+static void accelerate(Ctx *c, Population *pop, Grid *Egrid, int kind, int ke, const double *T, const double *S, const MpiInfo *fuse, Grid *rhoGrid = nullptr){
 	DevPop *dp = devPop(c, pop);
 	DevGrid *E = devGrid(c, Egrid);
 	if(E->nv != 3) fatal("accelerator needs a 3-vector field grid");
 	long sx3 = 3L*E->size[0], sxy3 = sx3*E->size[1];
 	Thr thr{}; CellSpace C{1,1,1,1};
+	DevGrid *rho = nullptr;
+	if(fuse) dropPredeposit(dp);
+	if(fuse && rhoGrid){
+		rho = devGrid(c, rhoGrid);
+		if(rho->nv != 1) fatal("pincAccMoveDistr3D1KE needs a scalar grid for rho");
+		ensureFix(c, rho, dp->nS);
+	}
 	if(fuse){
 		setupCells(c, dp, fuse);
 		thr = thrOf(fuse); C = cellsOf(dp);
@@ -424,8 +500,12 @@ static void accelerate(Ctx *c, Population *pop, Grid *Egrid, int kind, int ke, c
 		double *part = ke ? partial + (long)s*maxBlocks : nullptr;
 		if(n > 0){
 			double bytes = (fuse ? 100.0 : 72.0)*n;
-#define ACC_LAUNCH(K,KEE,F) PINC_LAUNCH(c, K_PUSH, bytes, (k_acc<K,KEE,F><<<blocks,256,0,c->stream>>>(dp->base, dp->cap, a, n, E->d, sx3, sxy3, E->size[0], E->size[1], E->size[2], B, part, thr, C, dp->d_keys, fuse ? dp->d_hist[s] : nullptr, c->d_flags)))
-			if(kind == ACC_LEAP){
+#define ACC_LAUNCH(K,KEE,F) PINC_LAUNCH(c, K_PUSH, bytes, (k_acc<K,KEE,F><<<blocks,256,0,c->stream>>>(dp->base, dp->cap, a, n, E->d, sx3, sxy3, E->size[0], E->size[1], E->size[2], B, part, thr, C, dp->d_keys, fuse ? dp->d_hist[s] : nullptr, c->d_flags, rho ? rho->d_fixS[s] : nullptr, rho ? (long)rho->size[0] : 0, rho ? (long)rho->size[0]*rho->size[1] : 0)))
+			if(kind == ACC_LEAP && rho){
+				if(dp->nc[0] > rho->size[0]-1 || dp->nc[1] > rho->size[1]-1 || dp->nc[2] > rho->size[2]-1) fatal("pincAccMoveDistr3D1KE: rho is smaller than the migration thresholds allow");
+				bytes = 124.0*n;
+				ACC_LAUNCH(0,1,2);
+			} else if(kind == ACC_LEAP){
 				if(ke){ if(fuse) ACC_LAUNCH(0,1,1); else ACC_LAUNCH(0,1,0); }
 				else  { if(fuse) ACC_LAUNCH(0,0,1); else ACC_LAUNCH(0,0,0); }
 			} else {
@@ -441,6 +521,7 @@ static void accelerate(Ctx *c, Population *pop, Grid *Egrid, int kind, int ke, c
 		for(int s = 0; s < dp->nS; s++) dp->sortedN[s] = 0;
 		dp->keysValid = true;
 		for(int d = 0; d < 6; d++) dp->keyThr[d] = fuse->thresholds[d];
+		dp->predep = rho;
 	}
 	if(ke){
 		PINC_CUDA(cudaMemcpyAsync(c->h_scal + 16, c->d_scal + 16, dp->nS*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -483,6 +564,7 @@ void puAcc3D1KE(Population *pop, Grid *E){ accelerate(cur(), pop, E, ACC_LEAP, 1
 void puBoris3D1(Population *pop, Grid *E, const double *T, const double *S){ accelerate(cur(), pop, E, ACC_BORIS, 0, T, S, nullptr); }
 void puBoris3D1KE(Population *pop, Grid *E, const double *T, const double *S){ accelerate(cur(), pop, E, ACC_BORIS, 1, T, S, nullptr); }
 void pincAccMove3D1KE(Population *pop, Grid *E, MpiInfo *mpiInfo){ accelerate(cur(), pop, E, ACC_LEAP, 1, nullptr, nullptr, mpiInfo); }
+void pincAccMoveDistr3D1KE(Population *pop, Grid *E, Grid *rho, MpiInfo *mpiInfo){ accelerate(cur(), pop, E, ACC_LEAP, 1, nullptr, nullptr, mpiInfo, rho); }
 
 // src/pusher.c:485-505
 void pincGet3DRotationParameters(int nSpecies, const double *BExt, const double *charge, const double *mass, double *T, double *S){
@@ -617,26 +699,27 @@ void puMigrate(Population *pop, MpiInfo *mpiInfo, Grid *grid){
 void puDistr3D1(const Population *pop, Grid *rhoGrid){
 	Ctx *c = cur(); DevPop *dp = devPop(c, pop); DevGrid *rho = devGrid(c, rhoGrid);
 	if(rho->nv != 1) fatal("puDistr3D1 needs a scalar grid");
-	if(!rho->d_fix){
-		PINC_CUDA(cudaMalloc(&rho->d_fix, (size_t)rho->n*sizeof(long long)));
-		PINC_CUDA(cudaMemsetAsync(rho->d_fix, 0, (size_t)rho->n*sizeof(long long), c->stream));
-	}
+	bool pre = dp->predep == rho;                 // the stayers were deposited by pincAccMoveDistr3D1KE
+	if(!pre) dropPredeposit(dp);
+	ensureFix(c, rho, dp->nS);
 	gridZero(c, rho);
 	long sx = rho->size[0], sxy = sx*rho->size[1];
 	for(int s = 0; s < dp->nS; s++){
 		long a = pop->iStart[s], n = pop->iStop[s] - a;
 		long ns = dp->sortedN[s] < n ? dp->sortedN[s] : n;
 		if(ns > 0 && (dp->nc[0] > rho->size[0]-1 || dp->nc[1] > rho->size[1]-1 || dp->nc[2] > rho->size[2]-1)) ns = 0;
+		if(pre && ns != dp->sortedN[s]) fatal("puDistr3D1: pre-deposited population changed size");
 		const double *X = dp->base + a, *Y = X + dp->cap, *Z = Y + dp->cap;
-		if(ns > 0){
+		if(ns > 0 && !pre){
 			long warps = dp->nCells;
 			int blocks = gridFor(warps*32, 256, c->numSMs*8);
-			PINC_LAUNCH(c, K_DEPOSIT, 24.0*ns, (k_distr_cells<<<blocks,256,0,c->stream>>>(X, Y, Z, dp->d_hist[s], cellsOf(dp), sx, sxy, rho->d_fix)));
+			PINC_LAUNCH(c, K_DEPOSIT, 24.0*ns, (k_distr_cells<<<blocks,256,0,c->stream>>>(X, Y, Z, dp->d_hist[s], cellsOf(dp), sx, sxy, rho->d_fixS[s])));
 		}
 		if(n - ns > 0)
-			PINC_LAUNCH(c, K_DEPOSIT, 24.0*(n-ns), (k_distr_tail<<<pGrid(c,n-ns),256,0,c->stream>>>(X+ns, Y+ns, Z+ns, n-ns, rho->size[0], rho->size[1], rho->size[2], rho->d_fix, c->d_flags)));
-		PINC_LAUNCH(c, K_DEPOSIT, 32.0*rho->n, (k_distr_finalize<<<gridFor(rho->n,256,c->numSMs*8),256,0,c->stream>>>(rho->d, rho->d_fix, rho->n, 1.0/pop->charge[s], pop->charge[s])));
+			PINC_LAUNCH(c, K_DEPOSIT, 24.0*(n-ns), (k_distr_tail<<<pGrid(c,n-ns),256,0,c->stream>>>(X+ns, Y+ns, Z+ns, n-ns, rho->size[0], rho->size[1], rho->size[2], rho->d_fixS[s], c->d_flags)));
+		PINC_LAUNCH(c, K_DEPOSIT, 32.0*rho->n, (k_distr_finalize<<<gridFor(rho->n,256,c->numSMs*8),256,0,c->stream>>>(rho->d, rho->d_fixS[s], rho->n, 1.0/pop->charge[s], pop->charge[s])));
 	}
+	dp->predep = nullptr;
 }
 
 // src/population.c:700-710 (host arithmetic on the small per-species scalars)

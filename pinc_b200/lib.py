@@ -95,6 +95,7 @@ SIGNATURES = {
     "pincHostUnregister": (C.c_int, [C.c_void_p]),
     "pincDeviceSynchronize": (None, []),
     "pincAccMove3D1KE": (None, [P(abi.Population), P(abi.Grid), P(abi.MpiInfo)]),
+    "pincAccMoveDistr3D1KE": (None, [P(abi.Population), P(abi.Grid), P(abi.Grid), P(abi.MpiInfo)]),
     "pincTimerStart": (None, []),
     "pincTimerStopMs": (C.c_double, []),
     "pincProfEnable": (None, [C.c_int]),

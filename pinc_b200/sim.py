@@ -223,8 +223,9 @@ class World:
 
     def step(self, fused=False):
         """One time step.  fused=False: the reference's call sequence, entry point by entry point.
-        fused=True: puAcc3D1KE, the next step's puMove and the emigrant classification run as one pass over
-        the particles (pincAccMove3D1KE); same arithmetic, same results."""
+        fused=True: puAcc3D1KE, the next step's puMove, the emigrant classification and the deposition of the
+        particles that stay run as one pass over the particles (pincAccMoveDistr3D1KE); fused="nodeposit" leaves the
+        deposition to puDistr3D1 (pincAccMove3D1KE).  Same arithmetic, bit-identical fields."""
         L = self.lib
 
         def phase(r, st):
@@ -239,14 +240,16 @@ class World:
             L.gFinDiff1st(st.phi, st.E)
             L.gHaloOp(self.set_slice, st.E, st.mpi, abi.TOHALO)
             L.gMul(st.E, -1.0)
-            if fused:
+            if fused == "nodeposit":
                 L.pincAccMove3D1KE(st.pop, st.E, st.mpi)
+            elif fused:
+                L.pincAccMoveDistr3D1KE(st.pop, st.E, st.rho, st.mpi)
             else:
                 L.puAcc3D1KE(st.pop, st.E)
             L.pSumKinEnergy(st.pop)
             L.gPotEnergy(st.rho, st.phi, st.pop)
         self.run(phase)
-        self._moved = fused
+        self._moved = bool(fused)
 
     def unmove(self):
         """Positions of a fused run are one puMove ahead of the reference's end-of-step state; step back

@@ -101,7 +101,7 @@ def test_warm_plasma_single_subdomain(fused):
 def test_fused_equals_unfused_bitwise_and_reproducible():
     cfg, per_rank = warm_small()
     outs = []
-    for fused in (False, True, True):
+    for fused in (False, True, True, "nodeposit"):
         W = sim.World(cfg)
         W.set_particles(per_rank)
         W.migrate(); W.field_solve(); W.half_kick()
@@ -112,3 +112,4 @@ def test_fused_equals_unfused_bitwise_and_reproducible():
     for n in ("rho", "phi", "E"):
         assert np.array_equal(outs[1][n], outs[2][n]), n          # run to run
         assert np.array_equal(outs[0][n], outs[1][n]), n          # fused pass vs separate entry points
+        assert np.array_equal(outs[0][n], outs[3][n]), n          # fused pass without the deposition

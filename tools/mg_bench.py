@@ -71,7 +71,7 @@ def main():
                 buf = (C.c_longlong * 32)()
                 L.pincMgProfRead.argtypes = [C.POINTER(C.c_longlong)]
                 if L.pincMgProfRead(buf):
-                    names = ["neut_rho", "gs_big", "gs_small", "restrict", "prolong", "neut_phi", "norm", "gs_big_sync"]
+                    names = ["neut_rho", "gs_big", "gs_small", "restrict", "prolong", "neut_phi", "norm", "gs_big_sync", "small_section"]
                     solves = 3
                     rec["prof_us_per_vcycle"] = {n: round(buf[2 * i] / 1965.0 / (solves * max(ncyc, 1)), 2) for i, n in enumerate(names)}
                     rec["prof_calls_per_vcycle"] = {n: round(buf[2 * i + 1] / (solves * max(ncyc, 1)), 1) for i, n in enumerate(names)}
