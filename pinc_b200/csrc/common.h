@@ -174,6 +174,7 @@ void gridScale(Ctx *c, DevGrid *g, double num);
 void gridZero(Ctx *c, DevGrid *g);
 void gridHaloDim(Ctx *c, DevGrid *g, const MpiInfo *m, int d /*1..3*/, int add, int dir);
 void gridHalo(Ctx *c, DevGrid *g, const MpiInfo *m, int add, int dir);
+bool gridHaloP2P(Ctx *c, DevGrid *g, const MpiInfo *m);       // multigrid.cu: ghost fill over peer memory, false if unavailable
 void gridHaloFaces(Ctx *c, DevGrid *g, const MpiInfo *m);      // faces of the decomposed dimensions only, one exchange
 void gridNeutralize(Ctx *c, DevGrid *g, const MpiInfo *m);
 void gridAddTo(Ctx *c, DevGrid *r, const DevGrid *a);

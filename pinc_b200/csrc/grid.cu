@@ -162,6 +162,7 @@ void gridHaloFaces(Ctx *c, DevGrid *g, const MpiInfo *m){
 	PINC_LAUNCH(c, K_HALO, 16.0*F.off[F.n], (k_faces_unpack<<<blocks,256,0,c->stream>>>(g->d, g->d_recv, dimsOf(g), F)));
 }
 void gridHalo(Ctx *c, DevGrid *g, const MpiInfo *m, int add, int dir){
+	if(!add && dir == 0 && gridHaloP2P(c, g, m)) return;          // ghost fill of a scalar grid over peer memory
 	for(int d = 1; d <= 3; d++) gridHaloDim(c, g, m, d, add, dir);
 }
 

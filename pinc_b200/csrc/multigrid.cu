@@ -166,6 +166,7 @@ __global__ void k_gs_colour_w(double *__restrict__ phi, const double *__restrict
 // reading ghosts of the decomposed dimensions from the mailbox, and stores every boundary node it updates straight
 // into the neighbour's mailbox plane, (3) the last block to finish fences and bumps the neighbours' counters.  Nodes of
 // one colour only read the other colour, so a neighbour that is one half-sweep ahead never overwrites what is being read.
+static int mgModeResolved();
 struct P2PArgs {
 	const double *myMail[6];        // [2*dd + side]: neighbour's boundary layer on my lower (0) / upper (1) side of dim dd
 	double *peerMail[6];            // [2*dd + 0]: upper neighbour's lower-side plane, [2*dd + 1]: lower neighbour's upper-side plane
@@ -202,11 +203,11 @@ __device__ __forceinline__ void p2pSignal(const P2PArgs &A){
 }
 __device__ __forceinline__ double ldv(const double *p){ return *((volatile const double*)p); }
 // publish both boundary layers of every decomposed dimension (start of a smoother call)
-__global__ void k_p2p_publish(const double *__restrict__ phi, int s0, int s1, int s2, P2PArgs A){
+__device__ __forceinline__ void p2pPublishPlanes(const double *__restrict__ phi, int s0, int s1, int s2, const P2PArgs &A, int dimMask){
 	long st = (long)gridDim.x*blockDim.x, i0 = blockIdx.x*(long)blockDim.x + threadIdx.x;
 	int sz[3] = {s0, s1, s2};
 	for(int dd = 0; dd < 3; dd++){
-		if(!A.active[dd]) continue;
+		if(!A.active[dd] || !(dimMask & (1 << dd))) continue;
 		int a = dd == 0 ? s1 : s0, b = dd == 2 ? s1 : s2;          // extents of the plane's two axes (ghost-inclusive)
 		long np = (long)a*b;
 		for(long i = i0; i < np; i += st){
@@ -217,6 +218,31 @@ __global__ void k_p2p_publish(const double *__restrict__ phi, int s0, int s1, in
 			A.peerMail[2*dd][i]   = ldg2(phi + ix(jU[0],jU[1],jU[2],s0,s1));
 			A.peerMail[2*dd+1][i] = ldg2(phi + ix(jL[0],jL[1],jL[2],s0,s1));
 		}
+	}
+}
+// Every peer-memory operation has a sequence number S that is the same on all ranks (same call sequence).  It starts
+// when the neighbours have finished operation S-1 (so whatever they wrote for us has arrived and whatever they read
+// from our last writes is done), may store into the neighbours' planes only what they do not read during their own
+// operation S, and ends by publishing S in the neighbours' arrival counters.
+__global__ void k_p2p_publish(const double *__restrict__ phi, int s0, int s1, int s2, P2PArgs A, int dimMask, int *flags){
+	p2pWait(A, A.seq - 1, flags);
+	p2pPublishPlanes(phi, s0, s1, s2, A, dimMask);
+	p2pSignal(A);
+}
+// ghost layers of dimension dd := the planes the neighbours published (full planes, rims included)
+__global__ void k_p2p_copy(double *__restrict__ phi, int s0, int s1, int s2, int dd, P2PArgs A, int *flags){
+	p2pWait(A, A.seq - 1, flags);
+	int a = dd == 0 ? s1 : s0, b = dd == 2 ? s1 : s2;
+	long np = (long)a*b, st = (long)gridDim.x*blockDim.x;
+	int sz = dd == 0 ? s0 : (dd == 1 ? s1 : s2);
+	for(long i = blockIdx.x*(long)blockDim.x + threadIdx.x; i < np; i += st){
+		int u = (int)(i % a), v = (int)(i / a);
+		long gLo, gHi;
+		if(dd == 0){ gLo = ix(0,u,v,s0,s1); gHi = ix(sz-1,u,v,s0,s1); }
+		else if(dd == 1){ gLo = ix(u,0,v,s0,s1); gHi = ix(u,sz-1,v,s0,s1); }
+		else { gLo = ix(u,v,0,s0,s1); gHi = ix(u,v,sz-1,s0,s1); }
+		phi[gLo] = ldv(A.myMail[2*dd] + i);
+		phi[gHi] = ldv(A.myMail[2*dd+1] + i);
 	}
 	p2pSignal(A);
 }
@@ -244,6 +270,71 @@ __global__ void k_gs_p2p(double *__restrict__ phi, const double *__restrict__ rh
 	}
 	p2pSignal(A);
 }
+// The whole smoother call (publish + 2*nCycles half-sweeps) as ONE cooperative kernel: between half-sweeps a block
+// fences its peer stores, takes a ticket, the last block publishes the sequence number to the neighbours and to the
+// local generation word, and every block waits until both the local generation and the neighbours' counters have
+// reached it.  Sequence numbers seq0 .. seq0 + 2*nCycles.
+__global__ void k_gs_p2p_loop(double *__restrict__ phi, const double *__restrict__ rho, int s0, int s1, int s2, int nHalf, int wrapMask,
+		P2PArgs A, unsigned long long *localGen, int *flags, long long *prof){
+	const unsigned long long seq0 = A.seq;
+	const bool pr = prof && blockIdx.x == 0 && threadIdx.x == 0;
+	long long tA = 0, tB = 0, tC = 0, tD = 0;
+	int t0 = s0-2, t1 = s1-2, t2 = s2-2;
+	long nt = (long)t0*t1*t2;
+	p2pWait(A, seq0 - 1, flags);
+	p2pPublishPlanes(phi, s0, s1, s2, A, 7);
+	for(int h = 0; h <= nHalf; h++){
+		// end of operation seq0+h (h = 0: the publish): fence, ticket, last block signals
+		const unsigned long long seq = seq0 + h;
+		if(pr) tA = clock64();
+		__syncthreads();
+		if(threadIdx.x == 0){
+			if(pr){ tB = clock64(); prof[20] += tB - tA; }        // sweep tail: waiting for the block's other warps
+			__threadfence_system();
+			if(pr){ tC = clock64(); prof[22] += tC - tB; prof[21] += 1; }   // system fence
+			unsigned long long old = atomicAdd(A.ticket, 1ULL);
+			if(old == gridDim.x - 1){
+				atomicExch(A.ticket, 0ULL);
+				__threadfence();          // the flag stores below are issued after the ticket is known (control dependency)
+				for(int i = 0; i < 6; i++) if(A.active[i>>1]) *((volatile unsigned long long*)A.peerFlag[i]) = seq;
+				*((volatile unsigned long long*)localGen) = seq;
+			}
+			if(h < nHalf){
+				long long c0 = clock64();
+				bool ok = false;
+				while(!ok){
+					ok = *((volatile unsigned long long*)localGen) >= seq;
+					for(int i = 0; i < 6 && ok; i++) if(A.active[i>>1] && *((volatile const unsigned long long*)&A.myFlag[i]) < seq) ok = false;
+					if(!ok && clock64() - c0 > 6000000000LL){ atomicOr(flags, ERR_P2P_TIMEOUT); break; }
+				}
+				if(pr){ tD = clock64(); prof[24] += tD - tC; }      // ticket + local generation + neighbours' counters
+			}
+		}
+		__syncthreads();
+		if(h == nHalf) break;
+		if(pr) tA = clock64();
+		const int parity = (h & 1) ? 0 : 1;
+		long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+		for(; i < nt; i += st){
+			int j, k, l; truePoint(i, t0, t1, j, k, l);
+			if(((j+k+l)&1) != parity) continue;
+			double a, b, c, d, e, f;
+			if(wrapMask&1){ a = ldg2(phi + ix(upI<true>(j,s0),k,l,s0,s1)); b = ldg2(phi + ix(dnI<true>(j,s0),k,l,s0,s1)); }
+			else { a = j == t0 ? ldv(A.myMail[1] + (k + (long)s1*l)) : ldg2(phi + ix(j+1,k,l,s0,s1)); b = j == 1 ? ldv(A.myMail[0] + (k + (long)s1*l)) : ldg2(phi + ix(j-1,k,l,s0,s1)); }
+			if(wrapMask&2){ c = ldg2(phi + ix(j,upI<true>(k,s1),l,s0,s1)); d = ldg2(phi + ix(j,dnI<true>(k,s1),l,s0,s1)); }
+			else { c = k == t1 ? ldv(A.myMail[3] + (j + (long)s0*l)) : ldg2(phi + ix(j,k+1,l,s0,s1)); d = k == 1 ? ldv(A.myMail[2] + (j + (long)s0*l)) : ldg2(phi + ix(j,k-1,l,s0,s1)); }
+			if(wrapMask&4){ e = ldg2(phi + ix(j,k,upI<true>(l,s2),s0,s1)); f = ldg2(phi + ix(j,k,dnI<true>(l,s2),s0,s1)); }
+			else { e = l == t2 ? ldv(A.myMail[5] + (j + (long)s0*k)) : ldg2(phi + ix(j,k,l+1,s0,s1)); f = l == 1 ? ldv(A.myMail[4] + (j + (long)s0*k)) : ldg2(phi + ix(j,k,l-1,s0,s1)); }
+			const double coeff = 1./6.;
+			double v = coeff*(a + b + c + d + e + f + ldg2(rho + ix(j,k,l,s0,s1)));
+			phi[ix(j,k,l,s0,s1)] = v;
+			if(!(wrapMask&1)){ if(j == t0) A.peerMail[0][k + (long)s1*l] = v; if(j == 1) A.peerMail[1][k + (long)s1*l] = v; }
+			if(!(wrapMask&2)){ if(k == t1) A.peerMail[2][j + (long)s0*l] = v; if(k == 1) A.peerMail[3][j + (long)s0*l] = v; }
+			if(!(wrapMask&4)){ if(l == t2) A.peerMail[4][j + (long)s0*k] = v; if(l == 1) A.peerMail[5][j + (long)s0*k] = v; }
+		}
+		if(pr){ prof[26] += clock64() - tA; }                     // thread 0's own share of the sweep
+	}
+}
 static int dimNb(const MpiInfo *m, int dd, int dir){
 	int nb[3];
 	for(int d = 0; d < 3; d++) nb[d] = m->subdomain[d];
@@ -268,6 +359,28 @@ static bool p2pArgs(Ctx *c, DevGrid *phi, const MpiInfo *m, P2PArgs &A){
 	return true;
 }
 
+// gHaloOp(setSlice, TOHALO) of a scalar grid over peer memory: per decomposed dimension one kernel that stores the two
+// boundary planes (rims included, so edges and corners propagate dimension by dimension as in src/grid.c:340-347)
+// into the neighbours' mailbox planes and one that copies the planes received into the ghost layers
+bool gridHaloP2P(Ctx *c, DevGrid *g, const MpiInfo *m){
+	if(g->nv != 1 || m->mpiSize < 2) return false;
+	if(mgModeResolved() != 2) return false;
+	P2PArgs A{};
+	if(!p2pArgs(c, g, m, A)) return false;
+	P2P *p = c->tp->p2p();
+	int s0 = g->size[0], s1 = g->size[1], s2 = g->size[2];
+	for(int dd = 0; dd < 3; dd++){
+		if(m->nSubdomains[dd] == 1){ gridHaloDim(c, g, m, dd+1, 0, 0); continue; }
+		long np = g->n / g->size[dd];
+		int blocks = gridFor(np, 256, c->numSMs);
+		A.seq = ++p->seq;
+		PINC_LAUNCH(c, K_HALO, 16.0*np, (k_p2p_publish<<<blocks,256,0,c->stream>>>(g->d, s0, s1, s2, A, 1 << dd, c->d_flags)));
+		A.seq = ++p->seq;
+		PINC_LAUNCH(c, K_HALO, 16.0*np, (k_p2p_copy<<<blocks,256,0,c->stream>>>(g->d, s0, s1, s2, dd, A, c->d_flags)));
+	}
+	return true;
+}
+
 extern int g_mgMode, g_mgForceCluster;
 // 0 ops, 1 fused-exact, 2 auto, 3 auto-exact (resolved from $PINC_B200_MG at first use; pincMgSetMode overrides)
 static int mgMode(){
@@ -278,6 +391,7 @@ static int mgMode(){
 	}
 	return g_mgMode;
 }
+static int mgModeResolved(){ return mgMode(); }
 static void opGS(Ctx *c, DevGrid *phi, DevGrid *rho, int nCycles, const MpiInfo *m){
 	long nt = trueCount(phi);
 	if(m->mpiSize > 1 && mgMode() == 2 && nCycles > 0){
@@ -288,12 +402,17 @@ static void opGS(Ctx *c, DevGrid *phi, DevGrid *rho, int nCycles, const MpiInfo 
 		P2PArgs A{};
 		if(p2pArgs(c, phi, m, A)){
 			P2P *p = c->tp->p2p();
-			int blocks = gridFor(nt, 256, c->numSMs);            // one wave: every block must be resident to reach the ticket
-			A.seq = ++p->seq;
-			PINC_LAUNCH(c, K_HALO, 16.0*phi->n/phi->size[2], (k_p2p_publish<<<blocks,256,0,c->stream>>>(phi->d, phi->size[0], phi->size[1], phi->size[2], A)));
-			for(int h = 0; h < 2*nCycles; h++){
-				A.seq = ++p->seq;
-				PINC_LAUNCH(c, K_GS, 12.0*nt, (k_gs_p2p<<<blocks,256,0,c->stream>>>(phi->d, rho->d, phi->size[0], phi->size[1], phi->size[2], (h&1) ? 0 : 1, wrapMask, A, c->d_flags)));
+			int blocks = gridFor(nt/2, 256, c->numSMs);          // co-resident: the blocks wait for each other's tickets
+			A.seq = p->seq + 1;                                   // publish = seq, half-sweep h = seq + h
+			p->seq += 1 + 2*nCycles;
+			int nHalf = 2*nCycles, s0 = phi->size[0], s1 = phi->size[1], s2 = phi->size[2];
+			unsigned long long *gen = P2P::flag(p->arena, 9);
+			int *dflags = c->d_flags;
+			long long *prof = (long long*)mgProfBuffer(c);
+			void *args[] = { &phi->d, &rho->d, &s0, &s1, &s2, &nHalf, &wrapMask, &A, &gen, &dflags, &prof };
+			{
+				LaunchScope ls(c, K_GS, 12.0*nt*nHalf);
+				PINC_CUDA(cudaLaunchCooperativeKernel((void*)k_gs_p2p_loop, dim3(blocks), dim3(256), args, 0, c->stream));
 			}
 			gridHalo(c, phi, m, 0, 0);
 			gridNeutralize(c, phi, m);
