@@ -54,6 +54,7 @@ static __device__ __forceinline__ long gix(const CLvl &L, int j, int k, int l){ 
 
 // pointer to node (1,1,l) of plane l of an array that is distributed like phi (offset `off`), any owner
 static __device__ __forceinline__ double *planePtr(const CLvl &L, const CK &K, int off, int l){
+	if(L.small && K.rank == 0) return mgS + off + (l-1)*L.ny*L.nx;        // whole level lives in this CTA: no owner arithmetic
 	int r = (l-1)/L.ppc;
 	int lp = (l-1) - r*L.ppc;
 	double *base = mgS + off;

@@ -25,6 +25,8 @@ namespace pinc {
 
 struct Lvl { double *phi, *rho, *res; int s0, s1, s2; };
 
+// loads of data other CTAs wrote in an earlier phase of the same kernel go to L2 (measured: L1-cached loads, which the
+// release/acquire grid barrier would allow, do not shorten the sweep: it is latency-, not L2-bandwidth-bound)
 __device__ __forceinline__ double ldg2(const double *p){ return __ldcg(p); }
 template<bool WRAP> __device__ __forceinline__ int upI(int j, int s){ return (WRAP && j == s-2) ? 1 : j+1; }
 template<bool WRAP> __device__ __forceinline__ int dnI(int j, int s){ return (WRAP && j == 1) ? s-2 : j-1; }
@@ -518,6 +520,9 @@ struct Scope {
 			atomicAdd(&bar[0], 1u);
 			gen += gridDim.x;
 			while((int)(*((volatile unsigned*)&bar[0]) - gen) < 0){ }
+			unsigned seen;
+			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&bar[0]) : "memory");
+			(void)seen;
 		}
 		__syncthreads();
 	}
