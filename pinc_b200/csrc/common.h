@@ -145,6 +145,7 @@ struct P2P {
 	char *arena = nullptr;                // local arena: [64 x u64 flags][6 planes x P2P_PLANE_CAP doubles]
 	std::vector<char*> peerArena;         // indexed by rank; [own rank] = arena
 	unsigned long long seq = 0;           // exchanges issued so far (identical on all ranks: same call sequence)
+	unsigned long long base = 0;          // host mirror of the device-side sequence base (flag slot 10)
 	static size_t flagBytes(){ return 64*sizeof(unsigned long long); }
 	static size_t bytes(){ return flagBytes() + 6*P2P_PLANE_CAP*sizeof(double); }
 	static double *plane(char *a, int i){ return (double*)(a + flagBytes()) + (size_t)i*P2P_PLANE_CAP; }

@@ -175,7 +175,8 @@ struct P2PArgs {
 	const unsigned long long *myFlag;     // [6] arrival counters in my arena
 	unsigned long long *peerFlag[6];      // counter of peerMail[i] in the neighbour's arena
 	unsigned long long *ticket;           // block counter (local)
-	unsigned long long seq;
+	const unsigned long long *seqBase;    // device word: sequence number = *seqBase + seq (lets a captured CUDA graph be replayed)
+	unsigned long long seq;               // offset from *seqBase
 	int active[3];
 };
 __device__ __forceinline__ void p2pWait(const P2PArgs &A, unsigned long long need, int *flags){
@@ -199,7 +200,8 @@ __device__ __forceinline__ void p2pSignal(const P2PArgs &A){
 		if(old == gridDim.x - 1){
 			atomicExch(A.ticket, 0ULL);
 			__threadfence_system();
-			for(int i = 0; i < 6; i++) if(A.active[i>>1]) *((volatile unsigned long long*)A.peerFlag[i]) = A.seq;
+			const unsigned long long sq = *A.seqBase + A.seq;
+			for(int i = 0; i < 6; i++) if(A.active[i>>1]) *((volatile unsigned long long*)A.peerFlag[i]) = sq;
 		}
 	}
 }
@@ -227,13 +229,13 @@ __device__ __forceinline__ void p2pPublishPlanes(const double *__restrict__ phi,
 // from our last writes is done), may store into the neighbours' planes only what they do not read during their own
 // operation S, and ends by publishing S in the neighbours' arrival counters.
 __global__ void k_p2p_publish(const double *__restrict__ phi, int s0, int s1, int s2, P2PArgs A, int dimMask, int *flags){
-	p2pWait(A, A.seq - 1, flags);
+	p2pWait(A, *A.seqBase + A.seq - 1, flags);
 	p2pPublishPlanes(phi, s0, s1, s2, A, dimMask);
 	p2pSignal(A);
 }
 // ghost layers of dimension dd := the planes the neighbours published (full planes, rims included)
 __global__ void k_p2p_copy(double *__restrict__ phi, int s0, int s1, int s2, int dd, P2PArgs A, int *flags){
-	p2pWait(A, A.seq - 1, flags);
+	p2pWait(A, *A.seqBase + A.seq - 1, flags);
 	int a = dd == 0 ? s1 : s0, b = dd == 2 ? s1 : s2;
 	long np = (long)a*b, st = (long)gridDim.x*blockDim.x;
 	int sz = dd == 0 ? s0 : (dd == 1 ? s1 : s2);
@@ -249,7 +251,7 @@ __global__ void k_p2p_copy(double *__restrict__ phi, int s0, int s1, int s2, int
 	p2pSignal(A);
 }
 __global__ void k_gs_p2p(double *__restrict__ phi, const double *__restrict__ rho, int s0, int s1, int s2, int parity, int wrapMask, P2PArgs A, int *flags){
-	p2pWait(A, A.seq - 1, flags);
+	p2pWait(A, *A.seqBase + A.seq - 1, flags);
 	int t0 = s0-2, t1 = s1-2, t2 = s2-2;
 	long nt = (long)t0*t1*t2;
 	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
@@ -278,7 +280,7 @@ __global__ void k_gs_p2p(double *__restrict__ phi, const double *__restrict__ rh
 // reached it.  Sequence numbers seq0 .. seq0 + 2*nCycles.
 __global__ void k_gs_p2p_loop(double *__restrict__ phi, const double *__restrict__ rho, int s0, int s1, int s2, int nHalf, int wrapMask,
 		P2PArgs A, unsigned long long *localGen, int *flags, long long *prof){
-	const unsigned long long seq0 = A.seq;
+	const unsigned long long seq0 = *A.seqBase + A.seq;
 	const bool pr = prof && blockIdx.x == 0 && threadIdx.x == 0;
 	long long tA = 0, tB = 0, tC = 0, tD = 0;
 	int t0 = s0-2, t1 = s1-2, t2 = s2-2;
@@ -358,6 +360,7 @@ static bool p2pArgs(Ctx *c, DevGrid *phi, const MpiInfo *m, P2PArgs &A){
 	}
 	A.myFlag = P2P::flag(p->arena, 0);
 	A.ticket = P2P::flag(p->arena, 8);
+	A.seqBase = P2P::flag(p->arena, 10);
 	return true;
 }
 
@@ -375,9 +378,9 @@ bool gridHaloP2P(Ctx *c, DevGrid *g, const MpiInfo *m){
 		if(m->nSubdomains[dd] == 1){ gridHaloDim(c, g, m, dd+1, 0, 0); continue; }
 		long np = g->n / g->size[dd];
 		int blocks = gridFor(np, 256, c->numSMs);
-		A.seq = ++p->seq;
+		A.seq = ++p->seq - p->base;
 		PINC_LAUNCH(c, K_HALO, 16.0*np, (k_p2p_publish<<<blocks,256,0,c->stream>>>(g->d, s0, s1, s2, A, 1 << dd, c->d_flags)));
-		A.seq = ++p->seq;
+		A.seq = ++p->seq - p->base;
 		PINC_LAUNCH(c, K_HALO, 16.0*np, (k_p2p_copy<<<blocks,256,0,c->stream>>>(g->d, s0, s1, s2, dd, A, c->d_flags)));
 	}
 	return true;
@@ -405,7 +408,7 @@ static void opGS(Ctx *c, DevGrid *phi, DevGrid *rho, int nCycles, const MpiInfo 
 		if(p2pArgs(c, phi, m, A)){
 			P2P *p = c->tp->p2p();
 			int blocks = gridFor(nt/2, 256, c->numSMs);          // co-resident: the blocks wait for each other's tickets
-			A.seq = p->seq + 1;                                   // publish = seq, half-sweep h = seq + h
+			A.seq = p->seq + 1 - p->base;                         // publish = seq, half-sweep h = seq + h
 			p->seq += 1 + 2*nCycles;
 			int nHalf = 2*nCycles, s0 = phi->size[0], s1 = phi->size[1], s2 = phi->size[2];
 			unsigned long long *gen = P2P::flag(p->arena, 9);
@@ -869,6 +872,23 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 	c->mgHistPending = true;
 }
 
+__global__ void k_seq_advance(unsigned long long *base, unsigned long long n){ *base += n; }
+
+// One V-cycle + residual + norm of a multi-rank solve is ~230 small kernels and ~30 NCCL calls that never change from
+// cycle to cycle: the second V-cycle of a solver is captured into a CUDA graph and every later one is a graph launch
+// (host enqueue cost was the bottleneck: 28 000 launches per time step).  The sequence numbers of the peer-memory
+// operations are offsets from a device word that the graph itself advances, so a replay continues the sequence.
+struct CycleGraph { cudaGraphExec_t exec = nullptr; unsigned long long nOps = 0; long launches = 0; int state = 0; /* 0 none, 1 ready, -1 disabled */ };
+static std::unordered_map<const void*, CycleGraph> g_graphs;
+
+static void oneCycle(Ctx *c, int bottom, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *m, DevGrid *res, DevGrid *rho, DevGrid *phi){
+	opVCycle(c, 0, bottom, 0, mgRho, mgPhi, mgRes, m);
+	opResidual(c, res, rho, phi);
+	gridHalo(c, res, m, 0, 0);
+	gridSumTrue(c, res, 1, nullptr, 3);
+	if(m->mpiSize > 1) c->tp->allreduceSum(c, c->d_scal + 3, 1);
+}
+
 static void opsSolve(Ctx *c, funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *m, double tol, int maxCycles){
 	int bottom = mgRho->nLevels - 1;
 	(void)mgAlgo;
@@ -878,12 +898,44 @@ static void opsSolve(Ctx *c, funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, 
 		DevGrid *res = devGrid(c, mgRes->grids[0]), *rho = devGrid(c, mgRho->grids[0]), *phi = devGrid(c, mgPhi->grids[0]);
 		double barRes = 2.;
 		int cycles = 0;
+		P2P *p = c->tp->p2p();
+		static int noGraph = -1;
+		if(noGraph < 0) noGraph = getenv("PINC_B200_NO_GRAPH") ? 1 : 0;
+		const bool graphable = p && m->mpiSize > 1 && mgMode() == 2 && !noGraph && !c->profOn;
+		CycleGraph &G = g_graphs[mgRho];
 		while(barRes > tol && cycles < maxCycles){
-			opVCycle(c, 0, bottom, 0, mgRho, mgPhi, mgRes, m);
-			opResidual(c, res, rho, phi);
-			gridHalo(c, res, m, 0, 0);
-			gridSumTrue(c, res, 1, nullptr, 3);
-			if(m->mpiSize > 1) c->tp->allreduceSum(c, c->d_scal + 3, 1);
+			if(graphable && G.state == 1){
+				PINC_CUDA(cudaGraphLaunch(G.exec, c->stream));
+				p->seq += G.nOps; p->base += G.nOps;
+				c->launches += G.launches;
+			} else if(graphable && G.state == 0 && (cycles >= 1 || !c->mgHistory.empty() || G.launches < 0)){
+				// everything the cycle needs exists after the first (eager) cycle: capture this one
+				unsigned long long seq0 = p->seq; long l0 = c->launches;
+				cudaGraph_t graph = nullptr;
+				cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+				if(e == cudaSuccess){
+					oneCycle(c, bottom, mgRho, mgPhi, mgRes, m, res, rho, phi);
+					unsigned long long nOps = p->seq - seq0;
+					k_seq_advance<<<1,1,0,c->stream>>>(P2P::flag(p->arena, 10), nOps);
+					e = cudaStreamEndCapture(c->stream, &graph);
+					if(e == cudaSuccess) e = cudaGraphInstantiate(&G.exec, graph, 0);
+					if(graph) cudaGraphDestroy(graph);
+					if(e == cudaSuccess){
+						G.nOps = nOps; G.launches = c->launches - l0; G.state = 1;
+						PINC_CUDA(cudaGraphLaunch(G.exec, c->stream));       // the captured cycle has not run yet
+						p->base += nOps;                                      // p->seq already counts its operations
+					}
+				}
+				if(e != cudaSuccess){
+					cudaGetLastError();
+					fprintf(stderr, "PINC-B200 WARNING: CUDA graph capture of the V-cycle failed (%s); staying with eager launches\n", cudaGetErrorString(e));
+					G.state = -1;
+					p->seq = seq0;                                        // nothing of the captured cycle ran
+					oneCycle(c, bottom, mgRho, mgPhi, mgRes, m, res, rho, phi);
+				}
+			} else {
+				oneCycle(c, bottom, mgRho, mgPhi, mgRes, m, res, rho, phi);
+			}
 			barRes = readScalar(c, 3);
 			barRes /= (double)gTotTruesize(mgRho->grids[0], m);
 			barRes = sqrt(barRes);
@@ -900,7 +952,11 @@ static void opsSolve(Ctx *c, funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, 
 	}
 }
 
-void mgForgetPlans(Ctx *c){ (void)c; }
+void mgForgetPlans(Ctx *c){
+	(void)c;
+	for(auto &kv : g_graphs) if(kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+	g_graphs.clear();
+}
 
 } // namespace pinc
 
