@@ -142,11 +142,13 @@ struct Msg { int peer; int tag; void *ptr; size_t bytes; };
 // every other rank (CUDA IPC), so a kernel addresses a neighbour's plane as peerArena[rank] + the same offset.
 #define P2P_PLANE_CAP (1L<<18)            // doubles per mailbox plane (faces up to 512 x 512)
 struct P2P {
-	char *arena = nullptr;                // local arena: [64 x u64 flags][6 planes x P2P_PLANE_CAP doubles]
+	char *arena = nullptr;                // local arena: [256 x u64 flags/scalars][6 planes x P2P_PLANE_CAP doubles]
 	std::vector<char*> peerArena;         // indexed by rank; [own rank] = arena
 	unsigned long long seq = 0;           // exchanges issued so far (identical on all ranks: same call sequence)
 	unsigned long long base = 0;          // host mirror of the device-side sequence base (flag slot 10)
-	static size_t flagBytes(){ return 64*sizeof(unsigned long long); }
+	static size_t flagBytes(){ return 256*sizeof(unsigned long long); }
+	// flag words: 0-5 arrival counters of the mailbox planes, 8 block ticket, 9 local generation, 10 sequence base,
+	// 11 all-reduce counter, 32-95 all-reduce arrival per rank, 128-255 all-reduce values [2][64]
 	static size_t bytes(){ return flagBytes() + 6*P2P_PLANE_CAP*sizeof(double); }
 	static double *plane(char *a, int i){ return (double*)(a + flagBytes()) + (size_t)i*P2P_PLANE_CAP; }
 	static unsigned long long *flag(char *a, int i){ return (unsigned long long*)a + i; }
@@ -175,13 +177,15 @@ void gridScale(Ctx *c, DevGrid *g, double num);
 void gridZero(Ctx *c, DevGrid *g);
 void gridHaloDim(Ctx *c, DevGrid *g, const MpiInfo *m, int d /*1..3*/, int add, int dir);
 void gridHalo(Ctx *c, DevGrid *g, const MpiInfo *m, int add, int dir);
-bool gridHaloP2P(Ctx *c, DevGrid *g, const MpiInfo *m);       // multigrid.cu: ghost fill over peer memory, false if unavailable
+bool gridHaloP2P(Ctx *c, DevGrid *g, const MpiInfo *m);
+bool allSumP2P(Ctx *c, const double *partial, int n, double *out, const MpiInfo *m);   // multigrid.cu: one-double all-reduce over peer memory       // multigrid.cu: ghost fill over peer memory, false if unavailable
 void gridHaloFaces(Ctx *c, DevGrid *g, const MpiInfo *m);      // faces of the decomposed dimensions only, one exchange
 void gridNeutralize(Ctx *c, DevGrid *g, const MpiInfo *m);
 void gridAddTo(Ctx *c, DevGrid *r, const DevGrid *a);
 // sum over the true grid of val (mode 0), val^2 after squaring in place (mode 1) or val*other (mode 2);
 // the result lands in c->d_scal[slot] (this rank only, no all-reduce)
 void gridSumTrue(Ctx *c, DevGrid *g, int mode, const DevGrid *other, int slot);
+void gridSumTrueAll(Ctx *c, DevGrid *g, int mode, int slot, const MpiInfo *m);       // the same over all ranks
 double readScalar(Ctx *c, int slot);           // D2H of d_scal[slot] + sync
 
 // ---- multigrid (multigrid.cu) ----

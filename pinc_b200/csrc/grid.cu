@@ -201,6 +201,25 @@ __global__ void k_final_sum(const double *__restrict__ partial, int n, double *_
 	if(threadIdx.x == 0) out[0] = acc;
 }
 
+// true-grid sum of val (or val^2 after squaring in place) over ALL ranks into d_scal[slot]
+void gridSumTrueAll(Ctx *c, DevGrid *g, int mode, int slot, const MpiInfo *m){
+	if(m->mpiSize > 1 && c->tp->p2p()){
+		if(mode == 1){
+			PINC_LAUNCH(c, K_GRIDOP, 16.0*g->n, (k_square<<<ewGrid(c,g->n),256,0,c->stream>>>(g->d, g->n)));
+			mode = 0;
+		}
+		long nt = (long)g->tsize[0]*g->tsize[1]*g->tsize[2];
+		int blocks = gridFor(nt, 256, c->numSMs*4);
+		double *partial = partialBuffer(c, blocks);
+		PINC_LAUNCH(c, K_REDUCE, 8.0*nt, (k_sum_true<<<blocks,256,0,c->stream>>>(g->d, nullptr, dimsOf(g), mode, partial)));
+		if(allSumP2P(c, partial, blocks, c->d_scal + slot, m)) return;
+		PINC_LAUNCH(c, K_REDUCE, 8.0*blocks, (k_final_sum<<<1,256,0,c->stream>>>(partial, blocks, c->d_scal + slot)));
+		c->tp->allreduceSum(c, c->d_scal + slot, 1);
+		return;
+	}
+	gridSumTrue(c, g, mode, nullptr, slot);
+	if(m->mpiSize > 1) c->tp->allreduceSum(c, c->d_scal + slot, 1);
+}
 void gridSumTrue(Ctx *c, DevGrid *g, int mode, const DevGrid *other, int slot){
 	if(g->nv != 1) fatal("true-grid sums are implemented for scalar grids");
 	if(mode == 1){
@@ -216,8 +235,7 @@ void gridSumTrue(Ctx *c, DevGrid *g, int mode, const DevGrid *other, int slot){
 
 // src/grid.c:730-779: mean over the global true grid subtracted from every element, ghosts included
 void gridNeutralize(Ctx *c, DevGrid *g, const MpiInfo *m){
-	gridSumTrue(c, g, 0, nullptr, 0);
-	if(m->mpiSize > 1) c->tp->allreduceSum(c, c->d_scal, 1);
+	gridSumTrueAll(c, g, 0, 0, m);
 	double denom = (double)((long)g->tsize[0]*g->tsize[1]*g->tsize[2])*m->mpiSize;
 	PINC_LAUNCH(c, K_GRIDOP, 16.0*g->n, (k_sub_mean<<<ewGrid(c,g->n),256,0,c->stream>>>(g->d, g->n, c->d_scal, denom)));
 }

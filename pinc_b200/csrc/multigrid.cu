@@ -318,23 +318,31 @@ __global__ void k_gs_p2p_loop(double *__restrict__ phi, const double *__restrict
 		if(h == nHalf) break;
 		if(pr) tA = clock64();
 		const int parity = (h & 1) ? 0 : 1;
-		long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
-		for(; i < nt; i += st){
-			int j, k, l; truePoint(i, t0, t1, j, k, l);
-			if(((j+k+l)&1) != parity) continue;
-			double a, b, c, d, e, f;
-			if(wrapMask&1){ a = ldg2(phi + ix(upI<true>(j,s0),k,l,s0,s1)); b = ldg2(phi + ix(dnI<true>(j,s0),k,l,s0,s1)); }
-			else { a = j == t0 ? ldv(A.myMail[1] + (k + (long)s1*l)) : ldg2(phi + ix(j+1,k,l,s0,s1)); b = j == 1 ? ldv(A.myMail[0] + (k + (long)s1*l)) : ldg2(phi + ix(j-1,k,l,s0,s1)); }
-			if(wrapMask&2){ c = ldg2(phi + ix(j,upI<true>(k,s1),l,s0,s1)); d = ldg2(phi + ix(j,dnI<true>(k,s1),l,s0,s1)); }
-			else { c = k == t1 ? ldv(A.myMail[3] + (j + (long)s0*l)) : ldg2(phi + ix(j,k+1,l,s0,s1)); d = k == 1 ? ldv(A.myMail[2] + (j + (long)s0*l)) : ldg2(phi + ix(j,k-1,l,s0,s1)); }
-			if(wrapMask&4){ e = ldg2(phi + ix(j,k,upI<true>(l,s2),s0,s1)); f = ldg2(phi + ix(j,k,dnI<true>(l,s2),s0,s1)); }
-			else { e = l == t2 ? ldv(A.myMail[5] + (j + (long)s0*k)) : ldg2(phi + ix(j,k,l+1,s0,s1)); f = l == 1 ? ldv(A.myMail[4] + (j + (long)s0*k)) : ldg2(phi + ix(j,k,l-1,s0,s1)); }
-			const double coeff = 1./6.;
-			double v = coeff*(a + b + c + d + e + f + ldg2(rho + ix(j,k,l,s0,s1)));
-			phi[ix(j,k,l,s0,s1)] = v;
-			if(!(wrapMask&1)){ if(j == t0) A.peerMail[0][k + (long)s1*l] = v; if(j == 1) A.peerMail[1][k + (long)s1*l] = v; }
-			if(!(wrapMask&2)){ if(k == t1) A.peerMail[2][j + (long)s0*l] = v; if(k == 1) A.peerMail[3][j + (long)s0*l] = v; }
-			if(!(wrapMask&4)){ if(l == t2) A.peerMail[4][j + (long)s0*k] = v; if(l == 1) A.peerMail[5][j + (long)s0*k] = v; }
+		// two passes: first the nodes on a decomposed boundary (their peer stores are in flight while the interior is
+		// swept, so the system fence at the end finds them acknowledged), then the rest
+		for(int pass = 0; pass < 2; pass++){
+			long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+			for(; i < nt; i += st){
+				int j, k, l; truePoint(i, t0, t1, j, k, l);
+				if(((j+k+l)&1) != parity) continue;
+				bool edge = (!(wrapMask&1) && (j == 1 || j == t0)) || (!(wrapMask&2) && (k == 1 || k == t1)) || (!(wrapMask&4) && (l == 1 || l == t2));
+				if(edge != (pass == 0)) continue;
+				double a, b, c, d, e, f;
+				if(wrapMask&1){ a = ldg2(phi + ix(upI<true>(j,s0),k,l,s0,s1)); b = ldg2(phi + ix(dnI<true>(j,s0),k,l,s0,s1)); }
+				else { a = j == t0 ? ldv(A.myMail[1] + (k + (long)s1*l)) : ldg2(phi + ix(j+1,k,l,s0,s1)); b = j == 1 ? ldv(A.myMail[0] + (k + (long)s1*l)) : ldg2(phi + ix(j-1,k,l,s0,s1)); }
+				if(wrapMask&2){ c = ldg2(phi + ix(j,upI<true>(k,s1),l,s0,s1)); d = ldg2(phi + ix(j,dnI<true>(k,s1),l,s0,s1)); }
+				else { c = k == t1 ? ldv(A.myMail[3] + (j + (long)s0*l)) : ldg2(phi + ix(j,k+1,l,s0,s1)); d = k == 1 ? ldv(A.myMail[2] + (j + (long)s0*l)) : ldg2(phi + ix(j,k-1,l,s0,s1)); }
+				if(wrapMask&4){ e = ldg2(phi + ix(j,k,upI<true>(l,s2),s0,s1)); f = ldg2(phi + ix(j,k,dnI<true>(l,s2),s0,s1)); }
+				else { e = l == t2 ? ldv(A.myMail[5] + (j + (long)s0*k)) : ldg2(phi + ix(j,k,l+1,s0,s1)); f = l == 1 ? ldv(A.myMail[4] + (j + (long)s0*k)) : ldg2(phi + ix(j,k,l-1,s0,s1)); }
+				const double coeff = 1./6.;
+				double v = coeff*(a + b + c + d + e + f + ldg2(rho + ix(j,k,l,s0,s1)));
+				phi[ix(j,k,l,s0,s1)] = v;
+				if(edge){
+					if(!(wrapMask&1)){ if(j == t0) A.peerMail[0][k + (long)s1*l] = v; if(j == 1) A.peerMail[1][k + (long)s1*l] = v; }
+					if(!(wrapMask&2)){ if(k == t1) A.peerMail[2][j + (long)s0*l] = v; if(k == 1) A.peerMail[3][j + (long)s0*l] = v; }
+					if(!(wrapMask&4)){ if(l == t2) A.peerMail[4][j + (long)s0*k] = v; if(l == 1) A.peerMail[5][j + (long)s0*k] = v; }
+				}
+			}
 		}
 		if(pr){ prof[26] += clock64() - tA; }                     // thread 0's own share of the sweep
 	}
@@ -872,6 +880,60 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 	c->mgHistPending = true;
 }
 
+// All-reduce of one double over peer memory (gNeutralizeGrid, residual norm): block-reduce the partial sums, store the
+// total into every rank's value slot, publish, wait for every rank, add the slots in rank order (identical bits on
+// all ranks).  The operation counter lives on the device and is bumped by the kernel itself: graph-replay safe.
+struct AllSumArgs { char *peer[64]; char *mine; int size, rank; };
+__global__ void k_allsum_p2p(const double *__restrict__ partial, int n, double *__restrict__ out, AllSumArgs A, int *flags){
+	__shared__ double sh[8];
+	__shared__ unsigned long long seqS;
+	double acc = 0;
+	for(int i = threadIdx.x; i < n; i += 256) acc += partial[i];
+	for(int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+	if((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if(threadIdx.x == 0){
+		double t = 0;
+		for(int w = 0; w < 8; w++) t += sh[w];
+		unsigned long long *ctr = (unsigned long long*)A.mine + 11;
+		unsigned long long seq = *ctr + 1; *ctr = seq; seqS = seq;
+		sh[0] = t;
+	}
+	__syncthreads();
+	const unsigned long long seq = seqS;
+	const int par = (int)(seq & 1);
+	if(threadIdx.x < A.size){
+		double *slot = (double*)((unsigned long long*)A.peer[threadIdx.x] + 128) + par*64 + A.rank;
+		*((volatile double*)slot) = sh[0];
+		__threadfence_system();
+		*((volatile unsigned long long*)((unsigned long long*)A.peer[threadIdx.x] + 32 + A.rank)) = seq;
+	}
+	__syncthreads();
+	if(threadIdx.x < A.size){
+		long long c0 = clock64();
+		while(*((volatile unsigned long long*)((unsigned long long*)A.mine + 32 + threadIdx.x)) < seq)
+			if(clock64() - c0 > 6000000000LL){ atomicOr(flags, ERR_P2P_TIMEOUT); break; }
+		__threadfence_system();
+	}
+	__syncthreads();
+	if(threadIdx.x == 0){
+		const volatile double *v = (const volatile double*)((unsigned long long*)A.mine + 128) + par*64;
+		double tot = v[0];
+		for(int r = 1; r < A.size; r++) tot += v[r];
+		out[0] = tot;
+	}
+}
+// replaces k_final_sum + ncclAllReduce when the peer arena exists; false if unavailable
+bool allSumP2P(Ctx *c, const double *partial, int n, double *out, const MpiInfo *m){
+	P2P *p = c->tp->p2p();
+	if(!p || m->mpiSize > 64 || mgMode() != 2) return false;
+	AllSumArgs A{};
+	for(int r = 0; r < m->mpiSize; r++) A.peer[r] = p->peerArena[r];
+	A.mine = p->arena; A.size = m->mpiSize; A.rank = m->mpiRank;
+	PINC_LAUNCH(c, K_REDUCE, 8.0*n, (k_allsum_p2p<<<1,256,0,c->stream>>>(partial, n, out, A, c->d_flags)));
+	return true;
+}
+
 __global__ void k_seq_advance(unsigned long long *base, unsigned long long n){ *base += n; }
 
 // One V-cycle + residual + norm of a multi-rank solve is ~230 small kernels and ~30 NCCL calls that never change from
@@ -885,8 +947,7 @@ static void oneCycle(Ctx *c, int bottom, Multigrid *mgRho, Multigrid *mgPhi, Mul
 	opVCycle(c, 0, bottom, 0, mgRho, mgPhi, mgRes, m);
 	opResidual(c, res, rho, phi);
 	gridHalo(c, res, m, 0, 0);
-	gridSumTrue(c, res, 1, nullptr, 3);
-	if(m->mpiSize > 1) c->tp->allreduceSum(c, c->d_scal + 3, 1);
+	gridSumTrueAll(c, res, 1, 3, m);
 }
 
 static void opsSolve(Ctx *c, funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *m, double tol, int maxCycles){
