@@ -75,6 +75,9 @@ struct ProfEvent { cudaEvent_t a, b; int cls; };
 
 struct Transport;
 
+// a captured V-cycle of a multi-rank solve (multigrid.cu): 0 not captured yet, 1 ready, -1 capture failed
+struct CycleGraph { cudaGraphExec_t exec = nullptr; unsigned long long nOps = 0; long launches = 0; int state = 0; };
+
 struct Ctx {
 	int device = 0, rank = 0, size = 1;
 	cudaStream_t stream = nullptr;
@@ -104,8 +107,10 @@ struct Ctx {
 	cudaEvent_t tStart = nullptr, tStop = nullptr;
 	// multigrid residual history of the most recent solve (device + pinned host: [0] = cycles, [1..] = barRes)
 	double *d_mgHist = nullptr, *h_mgHist = nullptr;
+	long long *d_mgProf = nullptr;                          // optional cycle accounting ($PINC_B200_MGPROF)
 	bool mgHistPending = false;
 	std::vector<double> mgHistory;
+	std::unordered_map<const void*, CycleGraph> cycleGraphs;     // keyed by the solver's mgRho
 	Transport *tp = nullptr;
 	std::string lastError;
 };

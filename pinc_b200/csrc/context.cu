@@ -254,6 +254,8 @@ void pincCtxDestroy(PincCtx *ctx){
 	cudaFree(c->d_scal); cudaFreeHost(c->h_scal); cudaFree(c->d_long); cudaFreeHost(c->h_long);
 	cudaFree(c->d_flags); cudaFreeHost(c->h_flags); cudaFree(c->d_bar);
 	if(c->d_partial) cudaFree(c->d_partial);
+	if(c->d_mgProf) cudaFree(c->d_mgProf);
+	if(c->d_mgHist){ cudaFree(c->d_mgHist); cudaFreeHost(c->h_mgHist); }
 	if(c->d_tmp) cudaFree(c->d_tmp);
 	for(auto e : c->evPool) cudaEventDestroy(e);
 	cudaEventDestroy(c->tStart); cudaEventDestroy(c->tStop);

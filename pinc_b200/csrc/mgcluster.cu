@@ -106,15 +106,12 @@ __global__ void __launch_bounds__(MC_BLOCK, 1) k_mg_cluster(CPlan P){
 	}
 }
 
-// cycle accounting of the cluster kernel ($PINC_B200_MGPROF=1): device buffer of 32 long longs, or null
-static long long *g_profBuf = nullptr;
+// cycle accounting of the multigrid kernels ($PINC_B200_MGPROF=1): per-context device buffer of 32 long longs, or null
 void *mgProfBuffer(Ctx *c){
-	static int on = -1;
-	if(on < 0) on = getenv("PINC_B200_MGPROF") ? 1 : 0;
+	static const bool on = getenv("PINC_B200_MGPROF") != nullptr;
 	if(!on) return nullptr;
-	if(!g_profBuf){ PINC_CUDA(cudaMalloc(&g_profBuf, 32*sizeof(long long))); PINC_CUDA(cudaMemset(g_profBuf, 0, 32*sizeof(long long))); }
-	(void)c;
-	return g_profBuf;
+	if(!c->d_mgProf){ PINC_CUDA(cudaMalloc(&c->d_mgProf, 32*sizeof(long long))); PINC_CUDA(cudaMemset(c->d_mgProf, 0, 32*sizeof(long long))); }
+	return c->d_mgProf;
 }
 // host side: returns false if this solve does not fit the cluster kernel (the caller falls back)
 bool clusterSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, double tol, int maxCycles, int exact){

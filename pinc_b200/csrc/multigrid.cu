@@ -940,8 +940,6 @@ __global__ void k_seq_advance(unsigned long long *base, unsigned long long n){ *
 // cycle to cycle: the second V-cycle of a solver is captured into a CUDA graph and every later one is a graph launch
 // (host enqueue cost was the bottleneck: 28 000 launches per time step).  The sequence numbers of the peer-memory
 // operations are offsets from a device word that the graph itself advances, so a replay continues the sequence.
-struct CycleGraph { cudaGraphExec_t exec = nullptr; unsigned long long nOps = 0; long launches = 0; int state = 0; /* 0 none, 1 ready, -1 disabled */ };
-static std::unordered_map<const void*, CycleGraph> g_graphs;
 
 static void oneCycle(Ctx *c, int bottom, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *m, DevGrid *res, DevGrid *rho, DevGrid *phi){
 	opVCycle(c, 0, bottom, 0, mgRho, mgPhi, mgRes, m);
@@ -963,7 +961,7 @@ static void opsSolve(Ctx *c, funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, 
 		static int noGraph = -1;
 		if(noGraph < 0) noGraph = getenv("PINC_B200_NO_GRAPH") ? 1 : 0;
 		const bool graphable = p && m->mpiSize > 1 && mgMode() == 2 && !noGraph && !c->profOn;
-		CycleGraph &G = g_graphs[mgRho];
+		CycleGraph &G = c->cycleGraphs[mgRho];         // per context: rank threads of one process never share it
 		while(barRes > tol && cycles < maxCycles){
 			if(graphable && G.state == 1){
 				PINC_CUDA(cudaGraphLaunch(G.exec, c->stream));
@@ -1014,9 +1012,8 @@ static void opsSolve(Ctx *c, funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, 
 }
 
 void mgForgetPlans(Ctx *c){
-	(void)c;
-	for(auto &kv : g_graphs) if(kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-	g_graphs.clear();
+	for(auto &kv : c->cycleGraphs) if(kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+	c->cycleGraphs.clear();
 }
 
 } // namespace pinc
