@@ -211,7 +211,7 @@ def run_ours(args, n_gpus, rank, world_size):
     L.pincSyncPopToHost(st.pop)          # the job's input state now lives in the host arrays
     n_live = sum(p.iStop[s] - p.iStart[s] for s in range(p.nSpecies))
     grid_bytes = sum(8 * int(g.contents.sizeProd[4]) for g in (st.rho, st.phi, st.E))
-    e2e_steps = max(2, min(args.steps, args.e2e_steps))
+    e2e_steps = max(2, args.steps if args.e2e_steps <= 0 else min(args.steps, args.e2e_steps))
     barrier()
     t0 = time.perf_counter()
     L.pincSyncPopToDevice(st.pop)                               # H2D: 48 B per live particle
@@ -318,7 +318,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="warm")
     ap.add_argument("--particles-scale", type=float, default=1.0)
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer job (0: the same K as --steps)")
     ap.add_argument("--cpu-sample", type=float, default=1.0, help="fraction of the 70 particles/cell used by the CPU arms")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--particle-pass", default="nodeposit", choices=["full", "nodeposit"],

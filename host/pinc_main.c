@@ -8,7 +8,7 @@
  * host structs with the plain-argument constructors, places particles (pPosLattice + pPosPerturb + pVelZero as
  * main.c:144-152 does, or uniform + Maxwellian when the ini gives thermal velocities), then time-steps.
  * Extensions (not PINC keys): population:thermalVelocityCells (sigma in cells/step), methods:fused = 1 (run
- * puAcc3D1KE + puMove + classification as one pass; 2: the deposition of the staying particles joins the pass), time:report = N.
+ * puAcc3D1KE + puMove + classification as one pass; 2: the deposition of the staying particles joins the pass), time:report = N, population:icOnDevice = 1 (initial conditions by the library's kernels), population:seed.
  * Multi-rank without MPI: RANK / WORLD_SIZE / LOCAL_RANK from the environment (as torchrun sets them) and the NCCL
  * id passed through the file $PINC_B200_ID_FILE. */
 #define _POSIX_C_SOURCE 200809L
@@ -245,10 +245,18 @@ int main(int argc, char **argv){
 	for(int i = 0; i < 3*c.nS; i++) if(c.pertA[i] != 0) anyPert = 1;
 	for(int s = 0; s < c.nS; s++) if(c.vth[s] != 0) anyVth = 1;
 	double tIC = nowSec();
-	if(anyVth && !anyPert) icMaxwell(&c, pop, iniHas(ini, "population:seed") ? (unsigned long long)iniGetInt(ini, "population:seed") : 1);
-	else icLattice(&c, pop);
+	unsigned long long seed = iniHas(ini, "population:seed") ? (unsigned long long)iniGetInt(ini, "population:seed") : 1;
+	if(iniHas(ini, "population:icOnDevice") && iniGetInt(ini, "population:icOnDevice")){
+		/* the same initial conditions generated by the library's kernels */
+		if(anyVth && !anyPert){ pincPosUniform(pop, mpiInfo, c.nPart, c.ts, seed); pincVelMaxwell(pop, mpiInfo, c.drift, c.vth, seed + 1); }
+		else { pincPosLattice(pop, mpiInfo, c.nPart, c.ts); pincPosPerturb(pop, mpiInfo, c.pertA, c.pertM, c.ts); pincVelZero(pop); }
+		pincDeviceSynchronize();
+	} else {
+		if(anyVth && !anyPert) icMaxwell(&c, pop, seed);
+		else icLattice(&c, pop);
+		pincSyncPopToDevice(pop);
+	}
 	tIC = nowSec() - tIC;
-	pincSyncPopToDevice(pop);
 
 	/* src/main.c:155-186 */
 	puExtractEmigrants3D(pop, mpiInfo);

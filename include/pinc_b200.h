@@ -141,6 +141,8 @@ void puMigrate(Population *pop, MpiInfo *mpiInfo, Grid *grid);                  
 int  puRankToNeighbor(MpiInfo *mpiInfo, int rank);                              /* pusher.h:186 (pusher.c:1214) */
 int  puNeighborToRank(MpiInfo *mpiInfo, int neighbor);                          /* pusher.h:187 (pusher.c:1194) */
 int  puNeighborToReciprocal(int neighbor, int nDims);                           /* pusher.h:188 (pusher.c:1181) */
+void pPosAssertInLocalFrame(const Population *pop, const Grid *grid);           /* population.h (population.c:316) */
+void pVelAssertMax(const Population *pop, double max);                          /* population.h (population.c:343) */
 void pSumKinEnergy(Population *pop);                                            /* population.h (population.c:700) */
 /* plain-argument form of puGet3DRotationParameters (pusher.c:485; the reference reads
  * BExt/charge/mass from the ini dictionary, which stays host code) */
@@ -226,6 +228,22 @@ void  pincCreateNeighborhood(MpiInfo *mpiInfo, const Grid *grid, const long int 
 Population *pincPopAlloc(int nSpecies, int nDims, const long int *nAllocPerRank,
                          const double *charge, const double *mass);
 void  pincPopFree(Population *pop);
+
+/* ---------------------------------------------------------------------------------
+ * Initial conditions on the device (src/population.c:110-276, 367-428 with plain arguments; the reference reads
+ * nParticles / trueSize / perturbAmplitude / perturbMode / drift / thermalVelocity from the ini).  Every rank
+ * walks all global particles and keeps its own, so the particle set does not depend on the decomposition.
+ * Random numbers: Philox4x32-10 (GSL's generators are not reproducible without GSL).  Host arrays are stale
+ * afterwards; pop->iStop[] is current.
+ * ------------------------------------------------------------------------------- */
+void pincPosLattice(Population *pop, const MpiInfo *mpiInfo, const long int *nParticles, const int *trueSize);      /* population.c:172 */
+void pincPosUniform(Population *pop, const MpiInfo *mpiInfo, const long int *nParticles, const int *trueSize,
+                    unsigned long long seed);                                                                       /* population.c:110 */
+void pincPosPerturb(Population *pop, const MpiInfo *mpiInfo, const double *amplitude, const double *mode,
+                    const int *trueSize);                                                                           /* population.c:242 */
+void pincVelMaxwell(Population *pop, const MpiInfo *mpiInfo, const double *drift, const double *thermalVelocity,
+                    unsigned long long seed);                                                                       /* population.c:367 */
+void pincVelZero(Population *pop);                                                                                  /* population.c:412 */
 
 /* ---------------------------------------------------------------------------------
  * Device context, coherence, transport, timing

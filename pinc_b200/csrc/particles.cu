@@ -415,6 +415,21 @@ __global__ void k_import(double *__restrict__ P, long cap, long dst0, long n, Im
 	}
 }
 
+// ---- debug scans of the driver loop (src/population.c:316-365) ------------------------------------------------
+// three planes starting at `P` are compared with lo <= v <= hi[d]; the first offender is recorded (species-local index,
+// dimension) by an atomicMin on index*4+dimension
+__global__ void k_assert_range(const double *__restrict__ P, long cap, long n, double lo0, double lo1, double lo2,
+		double hi0, double hi1, double hi2, int useLo, unsigned long long *first){
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	const double lo[3] = {lo0, lo1, lo2}, hi[3] = {hi0, hi1, hi2};
+	for(; i < n; i += st)
+		#pragma unroll
+		for(int d = 0; d < 3; d++){
+			double v = P[i + d*cap];
+			if(v > hi[d] || (useLo && v < lo[d])) atomicMin(first, (unsigned long long)i*4 + d);
+		}
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------
 static inline int pGrid(Ctx *c, long n){ return gridFor(n, 256, c->numSMs*8); }
 
@@ -720,6 +735,34 @@ void puDistr3D1(const Population *pop, Grid *rhoGrid){
 		PINC_LAUNCH(c, K_DEPOSIT, 32.0*rho->n, (k_distr_finalize<<<gridFor(rho->n,256,c->numSMs*8),256,0,c->stream>>>(rho->d, rho->d_fixS[s], rho->n, 1.0/pop->charge[s], pop->charge[s])));
 	}
 	dp->predep = nullptr;
+}
+
+static void assertScan(Ctx *c, const Population *pop, int which, const double *lo, const double *hi, int useLo, const char *what){
+	DevPop *dp = devPop(c, pop);
+	unsigned long long *first = (unsigned long long*)c->d_long;
+	for(int s = 0; s < dp->nS; s++){
+		long a = pop->iStart[s], n = pop->iStop[s] - a;
+		if(n <= 0) continue;
+		PINC_CUDA(cudaMemsetAsync(first, 0xff, sizeof(unsigned long long), c->stream));
+		PINC_LAUNCH(c, K_MOVE, 24.0*n, (k_assert_range<<<pGrid(c,n),256,0,c->stream>>>(dp->base + (size_t)(3*which)*dp->cap + a, dp->cap, n,
+			lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], useLo, first)));
+		PINC_CUDA(cudaMemcpyAsync(c->h_long, first, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+		streamSync(c);
+		unsigned long long f = (unsigned long long)c->h_long[0];
+		if(f != ~0ULL) fatal("Particle i=%llu (of specie %i) %s in dimension %i", (unsigned long long)(a + (long)(f/4)), s, what, (int)(f%4));
+	}
+}
+
+// src/population.c:316-341: every live particle inside [0, size-1] in every dimension, else msg(ERROR)
+void pPosAssertInLocalFrame(const Population *pop, const Grid *grid){
+	double lo[3] = {0, 0, 0}, hi[3];
+	for(int d = 0; d < 3; d++) hi[d] = (double)(grid->size[d+1] - 1);
+	assertScan(cur(), pop, 0, lo, hi, 1, "is out of bounds");
+}
+// src/population.c:343-365: no velocity component above max, else msg(ERROR)
+void pVelAssertMax(const Population *pop, double max){
+	double lo[3] = {0, 0, 0}, hi[3] = {max, max, max};
+	assertScan(cur(), pop, 1, lo, hi, 0, "travels too fast");
 }
 
 // src/population.c:700-710 (host arithmetic on the small per-species scalars)

@@ -33,6 +33,8 @@ SIGNATURES = {
     "puNeighborToRank": (C.c_int, [P(abi.MpiInfo), C.c_int]),
     "puNeighborToReciprocal": (C.c_int, [C.c_int, C.c_int]),
     "pSumKinEnergy": (None, [P(abi.Population)]),
+    "pPosAssertInLocalFrame": (None, [P(abi.Population), P(abi.Grid)]),
+    "pVelAssertMax": (None, [P(abi.Population), C.c_double]),
     "pincGet3DRotationParameters": (None, [C.c_int, abi.c_double_p, abi.c_double_p, abi.c_double_p, abi.c_double_p, abi.c_double_p]),
     "pincPuSanity": (C.c_int, [C.c_char_p, C.c_int, abi.c_int_p, abi.c_double_p, C.c_int, C.c_int, C.c_char_p, C.c_int]),
     # grid path
@@ -78,6 +80,12 @@ SIGNATURES = {
     "pincCreateNeighborhood": (None, [P(abi.MpiInfo), P(abi.Grid), abi.c_long_p, C.c_int, abi.c_double_p]),
     "pincPopAlloc": (P(abi.Population), [C.c_int, C.c_int, abi.c_long_p, abi.c_double_p, abi.c_double_p]),
     "pincPopFree": (None, [P(abi.Population)]),
+    # initial conditions on the device
+    "pincPosLattice": (None, [P(abi.Population), P(abi.MpiInfo), abi.c_long_p, abi.c_int_p]),
+    "pincPosUniform": (None, [P(abi.Population), P(abi.MpiInfo), abi.c_long_p, abi.c_int_p, C.c_ulonglong]),
+    "pincPosPerturb": (None, [P(abi.Population), P(abi.MpiInfo), abi.c_double_p, abi.c_double_p, abi.c_int_p]),
+    "pincVelMaxwell": (None, [P(abi.Population), P(abi.MpiInfo), abi.c_double_p, abi.c_double_p, C.c_ulonglong]),
+    "pincVelZero": (None, [P(abi.Population)]),
     # context, coherence, transport, timing
     "pincCtxCreate": (C.c_void_p, [C.c_int, C.c_int, C.c_int]),
     "pincCtxMakeCurrent": (None, [C.c_void_p]),

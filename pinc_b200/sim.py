@@ -156,6 +156,23 @@ class World:
         self.run(put)
         self._moved = False
 
+    def init_on_device(self, kind, seed=20261018):
+        """Initial conditions generated by the library's kernels (pincPosLattice/Perturb/VelZero or
+        pincPosUniform/VelMaxwell) instead of host arrays."""
+        L, cfg = self.lib, self.cfg
+
+        def gen(r, st):
+            n, ts = _la(cfg.nParticles), _ia(cfg.trueSize)
+            if kind == "lattice":
+                L.pincPosLattice(st.pop, st.mpi, n, ts)
+                L.pincPosPerturb(st.pop, st.mpi, _da(cfg.perturbAmplitude), _da(cfg.perturbMode), ts)
+                L.pincVelZero(st.pop)
+            else:
+                L.pincPosUniform(st.pop, st.mpi, n, ts, seed)
+                L.pincVelMaxwell(st.pop, st.mpi, _da(cfg.drift), _da(cfg.thermalVelocity), seed + 1)
+        self.run(gen)
+        self._moved = False
+
     def particles(self, r):
         st = self.ranks[r]
         self._on(r, lambda: self.lib.pincSyncPopToHost(st.pop))

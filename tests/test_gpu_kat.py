@@ -155,3 +155,33 @@ def test_everybody_emigrates(gpu_lib):
     exp = pos + np.array([4.0, 0.0, -4.0])
     assert np.array_equal(np.sort(got[:n], axis=0), np.sort(exp, axis=0))
     L.pincPopFree(p)
+
+
+def test_debug_scans_pass_and_fail_like_the_reference(gpu_lib):
+    """pPosAssertInLocalFrame / pVelAssertMax (src/population.c:316-365): silent when satisfied, msg(ERROR) + exit
+    otherwise (checked in a child process, because the error convention is exit(EXIT_FAILURE))."""
+    import subprocess, sys, textwrap
+    L = gpu_lib
+    true = (4, 4, 4)
+    rho = GridH(L, true, 1)
+    p = make_pop(L, [(np.array([[1.5, 2.5, 3.5], [4.9, 0.1, 2.0]]), np.array([[0.5, -2.0, 0.1], [0.9, 0.0, -0.9]]))], [1.0], [1.0])
+    L.pPosAssertInLocalFrame(p, rho.ptr)
+    L.pVelAssertMax(p, 1.0)
+    L.pincPopFree(p)
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        from pinc_b200 import lib as plib
+        from helpers import GridH
+        from test_gpu_kat import make_pop
+        L = plib.load()
+        rho = GridH(L, (4, 4, 4), 1)
+        p = make_pop(L, [(np.array([[1.5, 2.5, 3.5], [2.0, %s, 2.0]]), np.array([[0.5, 0.0, 0.1], [0.0, %s, 0.0]]))], [1.0], [1.0])
+        L.pPosAssertInLocalFrame(p, rho.ptr)
+        L.pVelAssertMax(p, 1.0)
+        print("survived")
+    """)
+    for posy, vely, msg in (("5.5", "0.0", "is out of bounds in dimension 1"), ("2.0", "1.5", "travels too fast in dimension 1")):
+        r = subprocess.run([sys.executable, "-c", code % (ROOT, os.path.join(ROOT, "tests"), posy, vely)], capture_output=True, text=True, timeout=300)
+        assert r.returncode != 0 and "survived" not in r.stdout
+        assert "Particle i=1 (of specie 0) " + msg in r.stderr, r.stderr[-500:]
