@@ -205,10 +205,12 @@ int pincMgLastHistory(double *barRes, int cap);
  *                    gBnd's mean subtraction applied once per smoother call (default; falls back to 1
  *                    when the levels do not fit the cluster's shared memory);
  *   3 cluster-exact  as 2 with gBnd after every half-sweep;
- *   4 cluster-always as 2, but the cluster kernel is used whenever the levels fit its shared memory.
+ *   4 cluster-always as 2, but the cluster kernel is used whenever the levels fit its shared memory;
+ *   5 allsm          as 2, but always the all-SM kernel (grid-wide levels smoothed block-resident in shared memory
+ *                    with the faces exchanged through tagged mailboxes in L2, small levels inside CTA 0).
  * Multi-rank solves: 2 = smoother and ghost fills over NVLink peer memory, V-cycle replayed as a CUDA graph;
  * 0/1/3 = one kernel and one exchange per reference call.
- * $PINC_B200_MG = ops | fused | cluster | cluster-exact selects the start-up value. */
+ * $PINC_B200_MG = ops | fused | cluster | cluster-exact | cluster-always | allsm selects the start-up value. */
 void pincMgSetMode(int mode);
 
 /* ---------------------------------------------------------------------------------

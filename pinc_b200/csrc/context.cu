@@ -255,6 +255,7 @@ void pincCtxDestroy(PincCtx *ctx){
 	cudaFree(c->d_flags); cudaFreeHost(c->h_flags); cudaFree(c->d_bar);
 	if(c->d_partial) cudaFree(c->d_partial);
 	if(c->d_mgProf) cudaFree(c->d_mgProf);
+	if(c->d_mgMail) cudaFree(c->d_mgMail);
 	if(c->d_mgHist){ cudaFree(c->d_mgHist); cudaFreeHost(c->h_mgHist); }
 	if(c->d_tmp) cudaFree(c->d_tmp);
 	for(auto e : c->evPool) cudaEventDestroy(e);
@@ -333,14 +334,14 @@ int pincProfGet(int idx, char *name, int namelen, double *ms, long int *launches
 	return 1;
 }
 long int pincLaunchCount(void){ return cur()->launches; }
-// cycle accounting of the cluster multigrid kernel ($PINC_B200_MGPROF=1): copies 16 (cycles, calls) pairs and clears
-int pincMgProfRead(long long *out32){
+// cycle accounting of the cluster multigrid kernel ($PINC_B200_MGPROF=1): copies 32 (cycles, calls) pairs and clears
+int pincMgProfRead(long long *out64){
 	Ctx *c = cur();
 	long long *d = (long long*)mgProfBuffer(c);
 	if(!d) return 0;
 	streamSync(c);
-	PINC_CUDA(cudaMemcpy(out32, d, 32*sizeof(long long), cudaMemcpyDeviceToHost));
-	PINC_CUDA(cudaMemset(d, 0, 32*sizeof(long long)));
+	PINC_CUDA(cudaMemcpy(out64, d, 64*sizeof(long long), cudaMemcpyDeviceToHost));
+	PINC_CUDA(cudaMemset(d, 0, 64*sizeof(long long)));
 	return 1;
 }
 const char *pincVersion(void){ return "pinc-b200 0.1 (sm_100a)"; }

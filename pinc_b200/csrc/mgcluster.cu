@@ -46,7 +46,7 @@ template<bool EXACT> __device__ void vcycle(const CPlan &P, CK &K){
 
 __global__ void __launch_bounds__(MC_BLOCK, 1) k_mg_cluster(CPlan P){
 	__shared__ double red[40];
-	CK K{ cg::this_cluster(), 0, P.nc, mgS, red, 0, P.prof };
+	CK K{ cg::this_cluster(), 0, P.nc, mgS, red, 0, P.prof, -1 };
 	K.rank = (int)K.cl.block_rank();
 	const int b = P.nLevels - 1;
 	// phi of every level, and rho of the levels that keep it in shared memory: global -> shared (own planes)
@@ -106,11 +106,11 @@ __global__ void __launch_bounds__(MC_BLOCK, 1) k_mg_cluster(CPlan P){
 	}
 }
 
-// cycle accounting of the multigrid kernels ($PINC_B200_MGPROF=1): per-context device buffer of 32 long longs, or null
+// cycle accounting of the multigrid kernels ($PINC_B200_MGPROF=1): per-context device buffer of 64 long longs, or null
 void *mgProfBuffer(Ctx *c){
 	static const bool on = getenv("PINC_B200_MGPROF") != nullptr;
 	if(!on) return nullptr;
-	if(!c->d_mgProf){ PINC_CUDA(cudaMalloc(&c->d_mgProf, 32*sizeof(long long))); PINC_CUDA(cudaMemset(c->d_mgProf, 0, 32*sizeof(long long))); }
+	if(!c->d_mgProf){ PINC_CUDA(cudaMalloc(&c->d_mgProf, 64*sizeof(long long))); PINC_CUDA(cudaMemset(c->d_mgProf, 0, 64*sizeof(long long))); }
 	return c->d_mgProf;
 }
 // host side: returns false if this solve does not fit the cluster kernel (the caller falls back)

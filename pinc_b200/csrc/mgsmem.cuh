@@ -39,6 +39,7 @@ struct CK {
 	double *red;         // static shared: [0..1] cluster-sum slots, [2] block total, [4..35] per-warp scratch
 	int flip;
 	long long *prof;     // optional cycle accounting (thread 0 of CTA 0): [2*slot] cycles, [2*slot+1] calls
+	int offZ;            // exchange buffer of sGS16 (doubles into mgS), or < 0
 };
 
 struct ProfScope {
@@ -46,6 +47,7 @@ struct ProfScope {
 	__device__ __forceinline__ ProfScope(const CK &K, int s) : p((K.prof && K.rank == 0 && threadIdx.x == 0) ? K.prof : nullptr), slot(s), t0(0) { if(p) t0 = clock64(); }
 	__device__ __forceinline__ ~ProfScope(){ if(p){ p[2*slot] += clock64() - t0; p[2*slot+1] += 1; } }
 };
+static __device__ __forceinline__ int psLvl(const CLvl &L, int kind){ int t = L.nx >= 16 ? 0 : (L.nx >= 8 ? 1 : (L.nx >= 4 ? 2 : 3)); return 16 + 4*t + kind; }
 enum { PS_NEUT_RHO = 0, PS_GS_BIG, PS_GS_SMALL, PS_RESTRICT, PS_PROLONG, PS_NEUT_PHI, PS_NORM, PS_GS_BIG_SYNC, PS_LEVEL0 = 8 };
 
 static __device__ __forceinline__ int upW(int j, int n){ return j == n ? 1 : j+1; }
@@ -73,7 +75,7 @@ static __device__ __forceinline__ void wrRho(const CLvl &L, const CK &K, int j, 
 	else planePtr(L, K, L.offRho, l)[(k-1)*L.nx + (j-1)] = v;
 }
 
-static __device__ __forceinline__ double blockSumC(CK &K, double v){
+static __device__ __noinline__ double blockSumC(CK &K, double v){
 	int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
 	for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 	if(lane == 0) K.red[4 + w] = v;
@@ -152,6 +154,10 @@ template<bool SMALL> static __device__ __noinline__ void cNeutralizePhi(const CL
 	for(int i = threadIdx.x; i < n; i += blockDim.x) P[i] -= avg;
 	syncAll<SMALL>(K);
 }
+
+} // namespace pinc
+#include "mgsmall.cuh"
+namespace pinc {
 
 // one Gauss-Seidel node: 1/6 * (x+ + x- + y+ + y- + z+ + z- + rho), summed left to right (src/multigrid.c:711-714)
 template<bool EXACT> static __device__ __forceinline__ double gsVal(double a, double b, double c, double d, double e, double f, double rho, double sR){
@@ -250,6 +256,13 @@ template<bool EXACT> static __device__ __noinline__ void cGSBig(const CLvl &Lref
 template<bool EXACT> static __device__ __noinline__ void cGSSmall(const CLvl &Lref, int nCycles, double sIn, CK &K){
 	const CLvl L = Lref;
 	ProfScope ps(K, PS_GS_SMALL);
+	ProfScope psl(K, psLvl(L, 0));
+	if(!EXACT && nCycles > 0 && L.nx == L.ny && L.ny == L.nz && blockDim.x == 512 && K.rank == 0){
+		// the benchmark pyramid's levels have routines of their own (mgsmall.cuh)
+		if(L.nx == 16 && K.offZ >= 0){ sGS16(mgS + L.offPhi, mgS + L.offRho, mgS + K.offZ, nCycles, sIn, K); return; }
+		if(L.nx == 8){ sGSOne<8>(mgS + L.offPhi, mgS + L.offRho, nCycles, sIn, K); return; }
+		if(L.nx == 4){ sGSOne<4>(mgS + L.offPhi, mgS + L.offRho, nCycles, sIn, K); return; }
+	}
 	const int nx = L.nx, ny = L.ny, nz = L.nz, pl = nx*ny;
 	double *P = mgS + L.offPhi;
 	const double *R = mgS + L.offRho;
@@ -348,6 +361,7 @@ template<bool SMALL, bool EXACT> static __device__ __noinline__ void cDown(const
 	cNeutralizeRho<SMALL>(L, K);
 	cGS<SMALL,EXACT>(L, P.nPre, 0.0, K);
 	ProfScope ps(K, PS_RESTRICT);
+	ProfScope psl(K, SMALL ? psLvl(L, 1) : 15);
 	int l0, nl; ownPlanes(L, K, l0, nl);
 	int Lz0 = l0/2 + 1;                       // first coarse plane with 2*Lz-1 >= l0
 	int Lz1 = (l0 + nl)/2;                    // last coarse plane with 2*Lz-1 <= l0+nl-1
@@ -367,7 +381,7 @@ template<bool SMALL, bool EXACT> static __device__ __noinline__ void cDown(const
 	}
 	syncAll<SMALL>(K);
 }
-template<bool SMALL, bool EXACT> __device__ void cBottom(const CPlan &P, CK &K){
+template<bool SMALL, bool EXACT> __device__ __noinline__ void cBottom(const CPlan &P, CK &K){
 	const CLvl &L = P.L[P.nLevels-1];
 	cNeutralizeRho<SMALL>(L, K);
 	cGS<SMALL,EXACT>(L, P.nCoarse, 0.0, K);
@@ -390,6 +404,7 @@ static __device__ __forceinline__ double cProl(const CLvl &C, const CK &K, int j
 template<bool SMALL, bool EXACT> static __device__ __noinline__ void cUp(const CPlan &P, int q, CK &K){
 	const CLvl &L = P.L[q], &C = P.L[q+1];
 	ProfScope ps(K, PS_PROLONG);
+	long long tP = clock64();
 	int l0, nl; ownPlanes(L, K, l0, nl);
 	int n = L.nx*L.ny*nl;
 	double *S = mgS + L.offPhi;
@@ -404,6 +419,7 @@ template<bool SMALL, bool EXACT> static __device__ __noinline__ void cUp(const C
 	}
 	double avg = sumAll<SMALL>(K, acc)/((double)L.nx*L.ny*L.nz);
 	ps.~ProfScope(); ps.p = nullptr;
+	if(SMALL && K.prof && K.rank == 0 && threadIdx.x == 0){ K.prof[2*psLvl(L, 2)] += clock64() - tP; K.prof[2*psLvl(L, 2)+1] += 1; }
 	cGS<SMALL,EXACT>(L, P.nPost, avg, K);
 	if(EXACT || P.nPost <= 0) cNeutralizePhi<SMALL>(L, K);
 }

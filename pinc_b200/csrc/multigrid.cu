@@ -394,13 +394,14 @@ bool gridHaloP2P(Ctx *c, DevGrid *g, const MpiInfo *m){
 	return true;
 }
 
-extern int g_mgMode, g_mgForceCluster;
+extern int g_mgMode, g_mgForceCluster, g_mgNoCluster;
 // 0 ops, 1 fused-exact, 2 auto, 3 auto-exact (resolved from $PINC_B200_MG at first use; pincMgSetMode overrides)
 static int mgMode(){
 	if(g_mgMode < 0){
 		const char *e = getenv("PINC_B200_MG");
 		g_mgMode = !e ? 2 : !strcmp(e, "ops") ? 0 : !strcmp(e, "fused") ? 1 : !strcmp(e, "cluster-exact") ? 3 : 2;
 		if(e && !strcmp(e, "cluster-always")) g_mgForceCluster = 1;
+		if(e && !strcmp(e, "allsm")) g_mgNoCluster = 1;
 	}
 	return g_mgMode;
 }
@@ -497,8 +498,17 @@ static void opVCycle(Ctx *c, int level, int bottom, int top, Multigrid *mgRho, M
 #define MG_MAXLEV 10
 #define MG_BLOCK 512
 #define MG_SMALL MC_SMALL    // levels with at most this many true nodes run inside CTA 0 (shared memory)
+// Block-resident smoothing of a grid-wide level: CTA 1+b keeps block b (bx x by x bz true nodes + one halo layer) of phi
+// in its shared memory for a whole mgGS3D call; the faces travel through per-CTA mailboxes in L2 (see bGS).
+struct BLvl {
+	int on, bx, by, bz, nbx, nby, nbz, nb;
+	int offPhi, offRho;      // shared-memory offsets in doubles; offRho < 0: rho is read from global memory
+	uint4 *mail;             // nb x 2(by*bz + bx*bz + bx*by) slots
+};
 struct MgPlan {
 	Lvl L[MG_MAXLEV];
+	BLvl B[MG_MAXLEV];
+	unsigned *seqWord;       // running half-sweep number of the mailbox protocol (persists across launches)
 	int nLevels, nPre, nPost, nCoarse, qSmall, maxCycles;
 	double tol, totTrue;
 	double *partial;         // 2*gridDim doubles
@@ -507,6 +517,7 @@ struct MgPlan {
 	unsigned barBase;
 	int exact;               // gBnd after every half-sweep (pending shifts) instead of once per smoother call
 	int smemSmall;           // small levels live in CTA 0's shared memory (descriptors in C)
+	int offZ;                // exchange buffer of the 16^3 smoother in CTA 0's shared memory (doubles), or < 0
 	long long *prof;         // optional cycle accounting ($PINC_B200_MGPROF)
 	CPlan C;
 };
@@ -523,7 +534,7 @@ struct Scope {
 	// before the arrival orders this CTA's stores; readers fetch other CTAs' data with ld.global.cg (L2), so no
 	// L1 invalidation is needed afterwards.  Measured (tools/ubench_gridbar.cu): 2780 cycles against 4820 for the
 	// fence + counter + generation + fence scheme.
-	__device__ __forceinline__ void sync(){
+	__device__ __noinline__ void sync(){
 		__syncthreads();
 		if(single) return;
 		if(threadIdx.x == 0){
@@ -538,7 +549,7 @@ struct Scope {
 		__syncthreads();
 	}
 	// sum over all participating threads; the same bits in every thread; acts as a barrier
-	__device__ __forceinline__ double allSum(double v){
+	__device__ __noinline__ double allSum(double v){
 		int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
 		for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 		if(lane == 0) sh[w] = v;
@@ -568,7 +579,7 @@ struct Scope {
 };
 
 // gNeutralizeGrid on the true nodes: returns after the subtraction is visible to everyone
-__device__ void fNeutralize(double *v, int s0, int s1, int s2, Scope &S){
+__device__ __noinline__ void fNeutralize(double *v, int s0, int s1, int s2, Scope &S){
 	int t0 = s0-2, t1 = s1-2, t2 = s2-2; long nt = (long)t0*t1*t2;
 	double acc = 0;
 	for(long i = S.tid(); i < nt; i += S.nthr()){ int j,k,l; truePoint(i,t0,t1,j,k,l); acc += ldg2(v + ix(j,k,l,s0,s1)); }
@@ -578,7 +589,7 @@ __device__ void fNeutralize(double *v, int s0, int s1, int s2, Scope &S){
 }
 
 // mgGS3D with gBnd's mean subtraction carried as pending shifts.  sIn: shift still pending on every value at entry.
-__device__ void fGS(const Lvl &L, int nCycles, double sIn, int exact, Scope &S){
+__device__ __noinline__ void fGS(const Lvl &L, int nCycles, double sIn, int exact, Scope &S){
 	ProfScope ps(*S.K, S.single ? PS_GS_SMALL : PS_GS_BIG);
 	int s0 = L.s0, s1 = L.s1, s2 = L.s2;
 	int t0 = s0-2, t1 = s1-2, t2 = s2-2; long nt = (long)t0*t1*t2;
@@ -638,10 +649,260 @@ __device__ void fGS(const Lvl &L, int nCycles, double sIn, int exact, Scope &S){
 	S.sync();
 }
 
-__device__ void fDown(const MgPlan &P, int q, Scope &S){
+
+// ---- block-resident mgGS3D ---------------------------------------------------------------------------------------
+// One mailbox slot = {value.lo, tag, value.hi, tag}: a 16-byte store whose two halves each carry the tag, so a reader
+// that sees both tags has the whole value (8-byte single-copy atomicity is all this needs).  No fence, no barrier: the
+// data is its own flag.  .cg accesses go to L2, the coherence point (measured, tools/ubench_gridbar.cu: 1500 cycles per
+// exchange of 512 slots per CTA against 2780 for a grid barrier + 300 for the dependent L2 loads behind it; volatile
+// accesses are 800 cycles slower).
+__device__ __forceinline__ void llStore(uint4 *p, double v, unsigned tag){
+	unsigned lo = (unsigned)__double_as_longlong(v), hi = (unsigned)(__double_as_longlong(v) >> 32);
+	asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
+}
+__constant__ unsigned c_llSleep;
+__device__ __forceinline__ double llWait(const uint4 *p, unsigned tag){
+	unsigned a, b, c, d, spins = 0;
+	for(;;){
+		asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+		if(b == tag && d == tag) break;
+		if(c_llSleep) __nanosleep(c_llSleep);
+		if(++spins > (1u << 22)) __trap();             // ~2 s: a lost neighbour must not hang the device
+	}
+	return __longlong_as_double(((long long)c << 32) | (long long)a);
+}
+// ---- the inner loop of the block smoother for small blocks: everything a thread needs is in registers ------------
+#define LL_NONE 0xffffffffu
+struct FastNode { int idx; unsigned t0, t1, t2; double rho; };      // idx 0: no node; t*: mailbox slots (from B.mail) it is sent to
+__device__ __forceinline__ double fastVal(const double *Ph, int idx, int ex, int pl, double rho){
+	const double coeff = 1./6.;
+	double a = Ph[idx+1], b = Ph[idx-1], c = Ph[idx+ex], d = Ph[idx-ex], e = Ph[idx+pl], f = Ph[idx-pl];
+	return coeff*(a + b + c + d + e + f + rho);
+}
+__device__ __forceinline__ void fastSend(uint4 *mail, const FastNode &n, double v, unsigned stag){
+	if(n.t0 != LL_NONE) llStore(mail + n.t0, v, stag);
+	if(n.t1 != LL_NONE) llStore(mail + n.t1, v, stag);
+	if(n.t2 != LL_NONE) llStore(mail + n.t2, v, stag);
+}
+__device__ __forceinline__ void fastHalf(double *Ph, int ex, int pl, uint4 *mail, const uint4 *pAddr, int pIdx, bool recv, unsigned tagIn,
+		const FastNode &a, const FastNode &b, unsigned stag, bool send){
+	if(recv && pAddr) Ph[pIdx] = llWait(pAddr, tagIn);
+	__syncthreads();
+	double va = 0, vb = 0;
+	if(a.idx) va = fastVal(Ph, a.idx, ex, pl, a.rho);
+	if(b.idx) vb = fastVal(Ph, b.idx, ex, pl, b.rho);
+	if(a.idx){ Ph[a.idx] = va; if(send) fastSend(mail, a, va, stag); }
+	if(b.idx){ Ph[b.idx] = vb; if(send) fastSend(mail, b, vb, stag); }
+}
+// c0*: nodes of colour 0 and the halo node of colour 0 this thread receives; same for colour 1.  Half-sweep h updates
+// colour 1 (h even) or 0 (h odd) and first receives the other colour's face nodes of half-sweep h-1.
+__device__ __noinline__ void bSmoothFast(double *Ph, int ex, int pl, uint4 *mail, const uint4 *p0Addr, int p0Idx, const uint4 *p1Addr, int p1Idx,
+		FastNode a0, FastNode b0, FastNode a1, FastNode b1, int nCycles, unsigned seq, long long *pf, long long tEnter){
+	long long tW = 0;
+	if(pf){ pf[2*9] += clock64() - tEnter; pf[2*9+1] += 1; tW = clock64(); }
+	for(int h2 = 0; h2 < nCycles; h2++){
+		const unsigned t = seq + 2u*(unsigned)h2;
+		fastHalf(Ph, ex, pl, mail, p0Addr, p0Idx, h2 > 0, t, a1, b1, t + 1u, true);
+		fastHalf(Ph, ex, pl, mail, p1Addr, p1Idx, true, t + 1u, a0, b0, t + 2u, h2 + 1 < nCycles);
+	}
+	if(pf){ pf[2*10] += clock64() - tW; pf[2*10+1] += 2*nCycles; }
+}
+// mgGS3D (src/multigrid.c:683-767) followed by the batched gBnd, on a level that is split into blocks.  The update of a
+// node reads the six neighbours of the other colour, so a half-sweep needs from the neighbouring blocks exactly the
+// face nodes they updated in the previous half-sweep: each CTA sends the boundary nodes it updates straight into the
+// mailboxes of the (up to) three neighbours that need them, tagged with the running half-sweep number, and before the
+// next half-sweep copies the tagged values it was sent into its halo layer.  A slot is rewritten two half-sweeps later,
+// which needs the value its reader produces in between: the protocol is its own back-pressure.  Same arithmetic per
+// node as fGS, hence the same bits.
+__device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, double sIn, Scope &S, unsigned &seq){
+	ProfScope ps(*S.K, PS_GS_BIG);
+	const int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2;
+	const int bid = (int)blockIdx.x - 1;
+	const bool act = bid >= 0 && bid < B.nb;
+	const int bx = B.bx, by = B.by, bz = B.bz, ex = bx+2, ey = by+2, pl = ex*ey;
+	const int nA = by*bz, nB = bx*bz, nC = bx*by;
+	double *Ph = mgS + B.offPhi;
+	const double *Rh = mgS + B.offRho;
+	double bsum = 0;
+	const long long tEnter = clock64();
+	int ox = 0, oy = 0, oz = 0;
+	if(act){
+		const int cx = bid % B.nbx, cr = bid / B.nbx, cy = cr % B.nby, cz = cr / B.nby;
+		ox = cx*bx; oy = cy*by; oz = cz*bz;
+		const int slots = 2*(nA + nB + nC);
+		const int fb[6] = {0, nA, 2*nA, 2*nA + nB, 2*nA + 2*nB, 2*nA + 2*nB + nC};
+		const uint4 *mine = B.mail + (size_t)bid*slots;
+		// where my boundary nodes go: the neighbour across face f receives them on its face f^1
+		unsigned out[6];                               // slot offsets from B.mail
+		{
+			int xm = (cx + B.nbx - 1) % B.nbx, xp = (cx + 1) % B.nbx, ym = (cy + B.nby - 1) % B.nby, yp = (cy + 1) % B.nby;
+			int zm = (cz + B.nbz - 1) % B.nbz, zp = (cz + 1) % B.nbz;
+			out[0] = (unsigned)(xm + B.nbx*(cy + B.nby*cz))*slots + fb[1];
+			out[1] = (unsigned)(xp + B.nbx*(cy + B.nby*cz))*slots + fb[0];
+			out[2] = (unsigned)(cx + B.nbx*(ym + B.nby*cz))*slots + fb[3];
+			out[3] = (unsigned)(cx + B.nbx*(yp + B.nby*cz))*slots + fb[2];
+			out[4] = (unsigned)(cx + B.nbx*(cy + B.nby*zm))*slots + fb[5];
+			out[5] = (unsigned)(cx + B.nbx*(cy + B.nby*zp))*slots + fb[4];
+		}
+		// block + halo layer from global memory (periodic image), with the pending mean shift applied
+		const int ne = pl*(bz+2);
+		auto srcOf = [&](int i) -> const double* {
+			int jl = i % ex, r = i / ex, kl = r % ey, ll = r / ey;
+			int gj = ox + jl, gk = oy + kl, gl = oz + ll;
+			gj = gj == 0 ? t0 : (gj == t0+1 ? 1 : gj);
+			gk = gk == 0 ? t1 : (gk == t1+1 ? 1 : gk);
+			gl = gl == 0 ? t2 : (gl == t2+1 ? 1 : gl);
+			return L.phi + ix(gj,gk,gl,L.s0,L.s1);
+		};
+		if(ne <= 8*(int)blockDim.x){
+			// all loads in flight before the first use: one L2 latency instead of eight
+			double v[8];
+			#pragma unroll
+			for(int u = 0; u < 8; u++){ int i = threadIdx.x + u*(int)blockDim.x; v[u] = i < ne ? ldg2(srcOf(i)) : 0.0; }
+			#pragma unroll
+			for(int u = 0; u < 8; u++){ int i = threadIdx.x + u*(int)blockDim.x; if(i < ne) Ph[i] = sIn != 0.0 ? v[u] - sIn : v[u]; }
+		} else
+			for(int i = threadIdx.x; i < ne; i += blockDim.x){
+				double v = ldg2(srcOf(i));
+				if(sIn != 0.0) v -= sIn;
+				Ph[i] = v;
+			}
+		const int hx = bx/2, items = hx*by*bz;
+		const int nHalo = nA + nB + nC;                 // halo nodes of one colour over the six faces
+		const bool fast = B.on == 1 && items <= 2*(int)blockDim.x && nHalo <= (int)blockDim.x;
+		if(B.offRho >= 0 && !fast)
+			for(int i = threadIdx.x; i < bx*by*bz; i += blockDim.x){
+				int jl = i % bx, r = i / bx, kl = r % by, ll = r / by;
+				mgS[B.offRho + i] = ldg2(L.rho + ix(ox+jl+1, oy+kl+1, oz+ll+1, L.s0, L.s1));
+			}
+		const double coeff = 1./6.;
+		// halo node i (0 <= i < nHalo) of colour c: mailbox slot and index into the block array
+		auto haloNode = [&](int i, int c, int &slot, int &hidx){
+			int f, w, j, k, l;
+			if(i < nA){
+				f = i >= nA/2; w = i - f*(nA/2);
+				int uu = w % (by/2); l = w / (by/2) + 1; j = f ? bx+1 : 0;
+				k = 2*uu + 1; k += ((j + k + l) & 1) != c;
+				slot = fb[f] + (k-1) + by*(l-1);
+			} else if(i < nA + nB){
+				w = i - nA; f = w >= nB/2; w -= f*(nB/2);
+				int uu = w % hx; l = w / hx + 1; k = f ? by+1 : 0;
+				j = 2*uu + 1; j += ((j + k + l) & 1) != c;
+				slot = fb[2+f] + (j-1) + bx*(l-1);
+			} else {
+				w = i - nA - nB; f = w >= nC/2; w -= f*(nC/2);
+				int uu = w % hx; k = w / hx + 1; l = f ? bz+1 : 0;
+				j = 2*uu + 1; j += ((j + k + l) & 1) != c;
+				slot = fb[4+f] + (j-1) + bx*(k-1);
+			}
+			hidx = j + ex*(k + ey*l);
+		};
+		auto sendNode = [&](int j, int k, int l, double v, unsigned stag){
+			if(j == 1)  llStore(B.mail + out[0] + (k-1) + by*(l-1), v, stag);
+			if(j == bx) llStore(B.mail + out[1] + (k-1) + by*(l-1), v, stag);
+			if(k == 1)  llStore(B.mail + out[2] + (j-1) + bx*(l-1), v, stag);
+			if(k == by) llStore(B.mail + out[3] + (j-1) + bx*(l-1), v, stag);
+			if(l == 1)  llStore(B.mail + out[4] + (j-1) + bx*(k-1), v, stag);
+			if(l == bz) llStore(B.mail + out[5] + (j-1) + bx*(k-1), v, stag);
+		};
+		if(fast){
+			// fast path (at most two nodes per thread and colour, one halo node per thread and colour): node addresses,
+			// rho and mailbox slots are worked out once per call and handed to a lean routine, so that a half-sweep is
+			// wait -> barrier -> 12 shared loads -> 14 additions -> stores
+			FastNode nd[2][2]; const uint4 *pAddr[2]; int pIdx[2];
+			#pragma unroll
+			for(int c = 0; c < 2; c++){
+				pAddr[c] = nullptr; pIdx[c] = 0;
+				if((int)threadIdx.x < nHalo){ int slot; haloNode(threadIdx.x, c, slot, pIdx[c]); pAddr[c] = mine + slot; }
+				#pragma unroll
+				for(int w = 0; w < 2; w++){
+					int iw = threadIdx.x + w*(int)blockDim.x;
+					FastNode &n = nd[c][w];
+					n.idx = 0; n.t0 = n.t1 = n.t2 = LL_NONE; n.rho = 0;
+					if(iw < items){
+						int m = iw % hx, r = iw / hx, k = r % by + 1, l = r / by + 1;
+						int j = ((((1+k+l)&1) == c) ? 1 : 2) + 2*m;
+						n.idx = j + ex*(k + ey*l);
+						n.rho = ldg2(L.rho + ix(ox+j, oy+k, oz+l, L.s0, L.s1));
+						// a node lies on at most one face per dimension unless the block is two nodes wide, where the second
+						// face of that dimension takes a slot of its own
+						unsigned t[6]; int nt = 0;
+						if(j == 1)  t[nt++] = out[0] + (k-1) + by*(l-1);
+						if(j == bx) t[nt++] = out[1] + (k-1) + by*(l-1);
+						if(k == 1)  t[nt++] = out[2] + (j-1) + bx*(l-1);
+						if(k == by) t[nt++] = out[3] + (j-1) + bx*(l-1);
+						if(l == 1)  t[nt++] = out[4] + (j-1) + bx*(k-1);
+						if(l == bz) t[nt++] = out[5] + (j-1) + bx*(k-1);
+						if(nt > 0) n.t0 = t[0];
+						if(nt > 1) n.t1 = t[1];
+						if(nt > 2) n.t2 = t[2];
+					}
+				}
+			}
+			bSmoothFast(Ph, ex, pl, B.mail, pAddr[0], pIdx[0], pAddr[1], pIdx[1], nd[0][0], nd[0][1], nd[1][0], nd[1][1], nCycles, seq,
+				(S.K->prof && bid == 0 && threadIdx.x == 0) ? S.K->prof : nullptr, tEnter);
+		} else
+		for(int h = 0; h < 2*nCycles; h++){
+			const int parity = (h & 1) ? 0 : 1;
+			if(h > 0){
+				// receive the other colour's face nodes of half-sweep h-1
+				const unsigned tag = seq + (unsigned)h;
+				const int c = 1 - parity;
+				for(int i = threadIdx.x; i < nHalo; i += blockDim.x){
+					int slot, hidx;
+					haloNode(i, c, slot, hidx);
+					Ph[hidx] = llWait(mine + slot, tag);
+				}
+			}
+			__syncthreads();
+			const bool send = h + 1 < 2*nCycles;
+			const unsigned stag = seq + (unsigned)h + 1u;
+			// two nodes per trip: all loads before the stores (own-colour stores never alias other-colour loads)
+			for(int i = threadIdx.x; i < items; i += 2*blockDim.x){
+				double vn[2]; int id[2], jj[2], kk[2], lq[2]; bool ok[2];
+				#pragma unroll
+				for(int w = 0; w < 2; w++){
+					int iw = i + w*(int)blockDim.x;
+					ok[w] = iw < items;
+					if(!ok[w]) continue;
+					int m = iw % hx, r = iw / hx, k = r % by + 1, l = r / by + 1;
+					int j = ((((1+k+l)&1) == parity) ? 1 : 2) + 2*m;
+					int idx = j + ex*(k + ey*l);
+					double rho = B.offRho >= 0 ? Rh[(j-1) + bx*((k-1) + by*(l-1))] : ldg2(L.rho + ix(ox+j, oy+k, oz+l, L.s0, L.s1));
+					vn[w] = coeff*(Ph[idx+1] + Ph[idx-1] + Ph[idx+ex] + Ph[idx-ex] + Ph[idx+pl] + Ph[idx-pl] + rho);
+					id[w] = idx; jj[w] = j; kk[w] = k; lq[w] = l;
+				}
+				#pragma unroll
+				for(int w = 0; w < 2; w++){
+					if(!ok[w]) continue;
+					Ph[id[w]] = vn[w];
+					if(send) sendNode(jj[w], kk[w], lq[w], vn[w], stag);
+				}
+			}
+		}
+		__syncthreads();
+		for(int i = threadIdx.x; i < bx*by*bz; i += blockDim.x){
+			int jl = i % bx, r = i / bx, kl = r % by, ll = r / by;
+			bsum += Ph[(jl+1) + ex*((kl+1) + ey*(ll+1))];
+		}
+	}
+	seq += 2u*(unsigned)nCycles;
+	const long long tTail = clock64();
+	// the 2*nCycles gBnd calls, applied once (as fGS does in batched mode), on the way back to global memory
+	double avg = S.allSum(bsum)/((double)t0*t1*t2);
+	if(act)
+		for(int i = threadIdx.x; i < bx*by*bz; i += blockDim.x){
+			int jl = i % bx, r = i / bx, kl = r % by, ll = r / by;
+			L.phi[ix(ox+jl+1, oy+kl+1, oz+ll+1, L.s0, L.s1)] = Ph[(jl+1) + ex*((kl+1) + ey*(ll+1))] - avg;
+		}
+	S.sync();
+	if(S.K->prof && bid == 0 && threadIdx.x == 0){ S.K->prof[2*12] += clock64() - tTail; S.K->prof[2*12+1] += 1; }
+}
+
+__device__ __noinline__ void fDown(const MgPlan &P, int q, Scope &S, unsigned &seq){
 	const Lvl &L = P.L[q], &C = P.L[q+1];
 	fNeutralize(L.rho, L.s0, L.s1, L.s2, S);
-	fGS(L, P.nPre, 0.0, P.exact, S);
+	if(P.B[q].on && !S.single && P.nPre > 0) bGS(L, P.B[q], P.nPre, 0.0, S, seq); else fGS(L, P.nPre, 0.0, P.exact, S);
 	{
 		int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2; long nt = (long)t0*t1*t2;
 		for(long i = S.tid(); i < nt; i += S.nthr()){ int j,k,l; truePoint(i,t0,t1,j,k,l);
@@ -655,14 +916,14 @@ __device__ void fDown(const MgPlan &P, int q, Scope &S){
 		S.sync();
 	}
 }
-__device__ void fBottom(const MgPlan &P, Scope &S){
+__device__ __noinline__ void fBottom(const MgPlan &P, Scope &S){
 	const Lvl &L = P.L[P.nLevels-1];
 	fNeutralize(L.rho, L.s0, L.s1, L.s2, S);
 	fGS(L, P.nCoarse, 0.0, P.exact, S);
 	if(P.exact || P.nCoarse <= 0) fNeutralize(L.phi, L.s0, L.s1, L.s2, S);      // batched mode: fGS just ended with this gBnd
 }
 // res(q) := P(phi(q+1)); phi(q) += res(q); gBnd; post-smooth; gBnd
-__device__ void fUp(const MgPlan &P, int q, Scope &S){
+__device__ __noinline__ void fUp(const MgPlan &P, int q, Scope &S, unsigned &seq){
 	const Lvl &L = P.L[q], &C = P.L[q+1];
 	int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2; long nt = (long)t0*t1*t2;
 	double acc = 0;
@@ -675,10 +936,10 @@ __device__ void fUp(const MgPlan &P, int q, Scope &S){
 		acc += v;
 	}
 	double avg = S.allSum(acc)/(double)nt;
-	fGS(L, P.nPost, avg, P.exact, S);
+	if(P.B[q].on && !S.single && P.nPost > 0) bGS(L, P.B[q], P.nPost, avg, S, seq); else fGS(L, P.nPost, avg, P.exact, S);
 	if(P.exact || P.nPost <= 0) fNeutralize(L.phi, L.s0, L.s1, L.s2, S);
 }
-__device__ void fGhosts(double *v, int s0, int s1, int s2, Scope &S){
+__device__ __noinline__ void fGhosts(double *v, int s0, int s1, int s2, Scope &S){
 	long n = (long)s0*s1*s2;
 	for(long i = S.tid(); i < n; i += S.nthr()){
 		int j = (int)(i % s0); long r = i / s0; int k = (int)(r % s1); int l = (int)(r / s1);
@@ -690,7 +951,7 @@ __device__ void fGhosts(double *v, int s0, int s1, int s2, Scope &S){
 }
 
 // small levels of the all-SM kernel: CTA 0, shared memory, the routines of mgsmem.cuh
-template<bool EXACT> __device__ void smallSection(const MgPlan &P, CK &K){
+template<bool EXACT> __device__ __noinline__ void smallSection(const MgPlan &P, CK &K){
 	const CPlan &C = P.C;
 	const int b = C.nLevels - 1, qs = P.qSmall;
 	{	// rho(qs) was restricted into global memory by the grid-wide part
@@ -712,7 +973,7 @@ template<bool EXACT> __device__ void smallSection(const MgPlan &P, CK &K){
 __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
 	__shared__ double sh[18];
 	__shared__ double red[40];
-	CK K{ cg::this_cluster(), (int)blockIdx.x, 1, mgS, red, 0, P.prof };
+	CK K{ cg::this_cluster(), (int)blockIdx.x, 1, mgS, red, 0, P.prof, P.offZ };
 	if(P.smemSmall && blockIdx.x == 0){
 		for(int q = P.qSmall; q < P.nLevels; q++){
 			const CLvl &L = P.C.L[q];
@@ -733,22 +994,23 @@ __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
 	int qs = P.qSmall < 0 ? 0 : P.qSmall;
 	double barRes = 2.;
 	int cycles = 0;
+	unsigned seq = *((volatile unsigned*)P.seqWord);       // rewritten only after the last grid barrier of this launch
 	while(barRes > P.tol && cycles < P.maxCycles){
-		for(int q = 0; q <= b && q < qs; q++){ if(q < b) fDown(P, q, Sg); else fBottom(P, Sg); }
+		for(int q = 0; q <= b && q < qs; q++){ if(q < b) fDown(P, q, Sg, seq); else fBottom(P, Sg); }
 		if(qs <= b){
 			if(blockIdx.x == 0){
 				ProfScope pss(K, PS_LEVEL0);
 				if(P.smemSmall){
 					if(P.exact) smallSection<true>(P, K); else smallSection<false>(P, K);
 				} else {
-					for(int q = qs; q < b; q++) fDown(P, q, S1);
+					for(int q = qs; q < b; q++) fDown(P, q, S1, seq);
 					fBottom(P, S1);
-					for(int q = b-1; q >= qs; q--) fUp(P, q, S1);
+					for(int q = b-1; q >= qs; q--) fUp(P, q, S1, seq);
 				}
 			}
 			Sg.sync();
 		}
-		for(int q = (qs <= b ? qs : b) - 1; q >= 0; q--) fUp(P, q, Sg);
+		for(int q = (qs <= b ? qs : b) - 1; q >= 0; q--) fUp(P, q, Sg, seq);
 		// mgSolveRaw :1700-1704: residual, square in place, true-grid sum, RMS
 		const Lvl &L = P.L[0];
 		int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2; long nt = (long)t0*t1*t2;
@@ -767,6 +1029,7 @@ __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
 		cycles++;
 	}
 	if(blockIdx.x == 0 && threadIdx.x == 0) P.hist[0] = (double)cycles;
+	const unsigned seqEnd = seq;
 	if(P.smemSmall){
 		if(blockIdx.x == 0)
 			for(int q = P.qSmall; q <= b; q++){
@@ -785,12 +1048,14 @@ __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
 		fGhosts(P.L[q].rho, P.L[q].s0, P.L[q].s1, P.L[q].s2, Sg);
 		fGhosts(P.L[q].res, P.L[q].s0, P.L[q].s1, P.L[q].s2, Sg);
 	}
+	if(blockIdx.x == 0 && threadIdx.x == 0) *P.seqWord = seqEnd;
 }
 
 int g_mgMode = -1;
 // -1: from $PINC_B200_MG at first use; 0 ops; 1 fused (grid-wide persistent kernel, gBnd per half-sweep);
 // 2 cluster (DSMEM-resident, gBnd batched per smoother call; default); 3 cluster with gBnd per half-sweep
 int g_mgForceCluster = 0;     // $PINC_B200_MG=cluster-always: use the cluster kernel whenever it fits
+int g_mgNoCluster = 0;        // $PINC_B200_MG=allsm: use the all-SM kernel whatever the size
 static void ensureHist(Ctx *c){
 	if(c->d_mgHist) return;
 	PINC_CUDA(cudaMalloc(&c->d_mgHist, 256*sizeof(double)));
@@ -815,11 +1080,39 @@ static bool fusedEligible(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid 
 	return true;
 }
 
+// Decomposition of a t0 x t1 x t2 level into at most maxBlocks equal blocks with even edges: as many blocks as
+// possible, then the smallest surface, then the longest x edge.
+static bool planBlocks(int t0, int t1, int t2, int maxBlocks, long smemCap, BLvl &B){
+	B = BLvl{};
+	long bestSurf = 0; int bestNb = 0;
+	for(int nx = 1; nx <= t0; nx++){
+		if(t0 % nx || ((t0/nx) & 1)) continue;
+		for(int ny = 1; ny <= t1 && nx*ny <= maxBlocks; ny++){
+			if(t1 % ny || ((t1/ny) & 1)) continue;
+			for(int nz = 1; nz <= t2 && nx*ny*nz <= maxBlocks; nz++){
+				if(t2 % nz || ((t2/nz) & 1)) continue;
+				int bx = t0/nx, by = t1/ny, bz = t2/nz, nb = nx*ny*nz;
+				long phiB = (long)(bx+2)*(by+2)*(bz+2)*8;
+				if(phiB > smemCap) continue;
+				long surf = (long)by*bz + (long)bx*bz + (long)bx*by;
+				bool better = nb > bestNb || (nb == bestNb && (surf < bestSurf || (surf == bestSurf && bx > B.bx)));
+				if(!better) continue;
+				bestNb = nb; bestSurf = surf;
+				B.bx = bx; B.by = by; B.bz = bz; B.nbx = nx; B.nby = ny; B.nbz = nz; B.nb = nb;
+				B.offPhi = 0;
+				B.offRho = (phiB + (long)bx*by*bz*8 <= smemCap) ? (bx+2)*(by+2)*(bz+2) : -1;
+			}
+		}
+	}
+	B.on = bestNb >= 8;
+	return B.on != 0;
+}
+
 static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, double tol, int maxCycles, int exact){
 	MgPlan P{};
 	int nL = mgRho->nLevels;
 	P.nLevels = nL; P.nPre = mgRho->nPreSmooth; P.nPost = mgRho->nPostSmooth; P.nCoarse = mgRho->nCoarseSolve;
-	P.qSmall = nL;
+	P.qSmall = nL; P.offZ = -1;
 	double work = 0;
 	for(int q = 0; q < nL; q++){
 		DevGrid *r = devGrid(c, mgRho->grids[q]), *p = devGrid(c, mgPhi->grids[q]), *e = devGrid(c, mgRes->grids[q]);
@@ -852,18 +1145,54 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 			L.offPhi = (int)off; off += nt;
 			L.offRho = (int)off; off += nt;
 		}
+		P.offZ = -1;
+		for(int q = P.qSmall; q < nL; q++) if(P.C.L[q].nx == 16 && P.C.L[q].ny == 16 && P.C.L[q].nz == 16){ P.offZ = (int)off; off += MS_ZBUF; break; }
 		smem = (size_t)off*sizeof(double);
-		static size_t attrSet = 0;
-		if(ok && smem > attrSet){
-			if(cudaFuncSetAttribute((const void*)k_mg_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) attrSet = smem;
-			else { cudaGetLastError(); ok = false; }
-		}
 		P.smemSmall = ok ? 1 : 0;
 		if(!ok) smem = 0;
 	}
 	DevGrid *r0 = devGrid(c, mgRho->grids[0]);
 	P.totTrue = (double)trueCount(r0);
 	int grid = P.qSmall == 0 ? 1 : c->numSMs;
+	// block-resident smoothing of the grid-wide levels (batched gBnd only; CTA 0 is left to the small levels)
+	P.seqWord = c->d_bar + 16;
+	{ static bool once = false; if(!once){ once = true; unsigned ns = getenv("PINC_B200_MG_SLEEP") ? atoi(getenv("PINC_B200_MG_SLEEP")) : 0; PINC_CUDA(cudaMemcpyToSymbol(c_llSleep, &ns, sizeof(ns))); } }
+	static const bool blocksOff = getenv("PINC_B200_MG_BLOCKS") && atoi(getenv("PINC_B200_MG_BLOCKS")) == 0;
+	if(!exact && grid > 8 && !blocksOff){
+		int smemOptin = 0;
+		PINC_CUDA(cudaDeviceGetAttribute(&smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+		const long smemCap = smemOptin - 4096;
+		size_t mailSlots = 0, blockSmem = 0, mailOff[MG_MAXLEV] = {0};
+		for(int q = 0; q < P.qSmall && q < nL; q++){
+			DevGrid *r = devGrid(c, mgRho->grids[q]);
+			BLvl &B = P.B[q];
+			if(!planBlocks(r->tsize[0], r->tsize[1], r->tsize[2], grid-1, smemCap, B)) continue;
+			if(B.bx > 1000 || B.by > 1000 || B.bz > 1000){ B.on = 0; continue; }        // packed node coordinates in bGS
+			static const bool noFast = getenv("PINC_B200_MG_FAST") && atoi(getenv("PINC_B200_MG_FAST")) == 0;
+			if(noFast) B.on = 2;
+			mailOff[q] = mailSlots;
+			mailSlots += (size_t)B.nb*2*(B.by*B.bz + B.bx*B.bz + B.bx*B.by);
+			size_t need = (size_t)(B.offRho >= 0 ? B.offRho + B.bx*B.by*B.bz : (B.bx+2)*(B.by+2)*(B.bz+2))*sizeof(double);
+			if(need > blockSmem) blockSmem = need;
+		}
+		if(mailSlots){
+			if(mailSlots*sizeof(uint4) > c->mgMailBytes){
+				if(c->d_mgMail) PINC_CUDA(cudaFree(c->d_mgMail));
+				c->mgMailBytes = mailSlots*sizeof(uint4);
+				PINC_CUDA(cudaMalloc(&c->d_mgMail, c->mgMailBytes));
+				PINC_CUDA(cudaMemsetAsync(c->d_mgMail, 0, c->mgMailBytes, c->stream));
+			}
+			for(int q = 0; q < P.qSmall && q < nL; q++) if(P.B[q].on) P.B[q].mail = (uint4*)c->d_mgMail + mailOff[q];
+			if(blockSmem > smem) smem = blockSmem;
+		}
+	}
+	{	// one high-water mark for the kernel's dynamic shared memory
+		static size_t attrSet = 0;
+		if(smem > attrSet){
+			if(cudaFuncSetAttribute((const void*)k_mg_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) attrSet = smem;
+			else { cudaGetLastError(); for(int q = 0; q < nL; q++) P.B[q].on = 0; P.smemSmall = 0; smem = 0; }
+		}
+	}
 	P.partial = partialBuffer(c, 2L*grid);
 	P.bar = c->d_bar;
 	PINC_CUDA(cudaMemsetAsync(c->d_bar, 0, 2*sizeof(unsigned), c->stream));
@@ -1061,7 +1390,7 @@ void mgSolveRaw(funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 		// (measured: 32^3 304 vs 526 us per V-cycle, 64^3 908 vs 805); larger grids go to the all-SM kernel
 		const Grid *g0 = mgRho->grids[0];
 		long nt0 = (long)g0->trueSize[1]*g0->trueSize[2]*g0->trueSize[3];
-		bool preferCluster = g_mgMode == 3 || g_mgForceCluster || nt0 <= 65536;
+		bool preferCluster = (g_mgMode == 3 || g_mgForceCluster || nt0 <= 65536) && !g_mgNoCluster;
 		if(g_mgMode >= 2 && preferCluster && clusterSolve(c, mgRho, mgPhi, mgRes, tol, maxCycles, g_mgMode == 3)) return;
 		fusedSolve(c, mgRho, mgPhi, mgRes, tol, maxCycles, g_mgMode == 1 || g_mgMode == 3);
 	} else opsSolve(c, mgAlgo, mgRho, mgPhi, mgRes, mpiInfo, tol, maxCycles);
@@ -1078,7 +1407,7 @@ void mgSolver(void (**solve)(), MultigridSolver *(**solverAlloc)(), void (**solv
 	*solverFree = (void(*)())mgFreeSolver;
 }
 
-void pincMgSetMode(int mode){ pinc::g_mgForceCluster = mode == 4; if(mode == 4) mode = 2; pinc::g_mgMode = mode < 0 ? 0 : (mode > 3 ? 3 : mode); }
+void pincMgSetMode(int mode){ pinc::g_mgForceCluster = mode == 4; pinc::g_mgNoCluster = mode == 5; if(mode == 4 || mode == 5) mode = 2; pinc::g_mgMode = mode < 0 ? 0 : (mode > 3 ? 3 : mode); }
 
 int pincMgLastHistory(double *barRes, int cap){
 	Ctx *c = cur();

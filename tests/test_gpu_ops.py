@@ -186,7 +186,7 @@ def _mg_problem(L, true, levels, seed):
 
 
 # 2 = default (cluster kernel up to 65536 nodes, all-SM kernel above), 4 = cluster kernel whenever it fits
-MG_MODES = {"ops": 0, "fused": 1, "cluster": 2, "cluster-exact": 3, "cluster-always": 4}
+MG_MODES = {"ops": 0, "fused": 1, "cluster": 2, "cluster-exact": 3, "cluster-always": 4, "allsm": 5}
 
 
 @pytest.mark.parametrize("mode", sorted(MG_MODES))

@@ -17,7 +17,7 @@ from helpers import GridH, single_mpi  # noqa: E402
 from pinc_b200 import lib as plib  # noqa: E402
 
 PI = 3.14159265
-MODES = {0: "ops", 1: "fused-exact", 2: "auto", 3: "auto-exact", 4: "cluster-always"}
+MODES = {0: "ops", 1: "fused-exact", 2: "auto", 3: "auto-exact", 4: "cluster-always", 5: "allsm"}
 
 
 def main():
@@ -68,13 +68,14 @@ def main():
             rec = {"N": N, "levels": levels, "mode": MODES[mode], "rho": kind, "vcycles": ncyc, "barRes_last": last,
                    "ms_per_solve": min(times), "us_per_vcycle": 1e3 * min(times) / max(ncyc, 1), "rms_error_vs_analytic": err}
             if os.environ.get("PINC_B200_MGPROF"):
-                buf = (C.c_longlong * 32)()
+                buf = (C.c_longlong * 64)()
                 L.pincMgProfRead.argtypes = [C.POINTER(C.c_longlong)]
                 if L.pincMgProfRead(buf):
-                    names = ["neut_rho", "gs_big", "gs_small", "restrict", "prolong", "neut_phi", "norm", "gs_big_sync", "small_section"]
+                    names = ["neut_rho", "gs_big", "gs_small", "restrict", "prolong", "neut_phi", "norm", "gs_big_sync", "small_section", "b_load", "b_wait", "b_compute", "b_tail", "-", "-", "-",
+                             "gs16", "res16", "pro16", "-", "gs8", "res8", "pro8", "-", "gs4", "res4", "pro4", "-"]
                     solves = 3
-                    rec["prof_us_per_vcycle"] = {n: round(buf[2 * i] / 1965.0 / (solves * max(ncyc, 1)), 2) for i, n in enumerate(names)}
-                    rec["prof_calls_per_vcycle"] = {n: round(buf[2 * i + 1] / (solves * max(ncyc, 1)), 1) for i, n in enumerate(names)}
+                    rec["prof_us_per_vcycle"] = {n: round(buf[2 * i] / 1965.0 / (solves * max(ncyc, 1)), 2) for i, n in enumerate(names) if n != "-"}
+                    rec["prof_calls_per_vcycle"] = {n: round(buf[2 * i + 1] / (solves * max(ncyc, 1)), 1) for i, n in enumerate(names) if n != "-"}
             print(json.dumps(rec), flush=True)
             out.append(rec)
             L.mgFreeSolver(solver)
