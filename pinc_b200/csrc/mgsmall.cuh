@@ -113,4 +113,84 @@ template<int N> static __device__ __noinline__ void sGSOne(double *P, const doub
 	__syncthreads();
 }
 
+// ---- the rest of the V-cycle on the cubic levels N = 16, 8, 4: compile-time sizes, masks instead of divisions ----------
+template<int N> static __device__ __forceinline__ int sIdx(int x, int y, int z){ return (x & (N-1)) + N*((y & (N-1)) + N*(z & (N-1))); }
+// gNeutralizeGrid (src/grid.c:730-779)
+template<int N> static __device__ __forceinline__ void sNeutralize(double *A, CK &K){
+	constexpr int NN = N*N*N;
+	double acc = 0;
+	for(int i = threadIdx.x; i < NN; i += blockDim.x) acc += A[i];
+	const double avg = blockSumC(K, acc)/(double)NN;
+	for(int i = threadIdx.x; i < NN; i += blockDim.x) A[i] -= avg;
+	__syncthreads();
+}
+// residual at (x,y,z): -6 phi; += six neighbours; += rho (src/grid.c:318-322, src/multigrid.c:1400)
+template<int N> static __device__ __forceinline__ double sResAt(const double *P, const double *R, int x, int y, int z){
+	const int c = sIdx<N>(x,y,z);
+	double r = -6.*P[c];
+	r += P[sIdx<N>(x+1,y,z)] + P[sIdx<N>(x-1,y,z)] + P[sIdx<N>(x,y+1,z)] + P[sIdx<N>(x,y-1,z)] + P[sIdx<N>(x,y,z+1)] + P[sIdx<N>(x,y,z-1)];
+	r += R[c];
+	return r;
+}
+// mgResidual + mgHalfRestrict3D (src/multigrid.c:844-911) into the coarse rho, followed by the coarse level's gBnd(rho)
+template<int N> static __device__ __noinline__ void sRestrict(const double *P, const double *R, double *Rc, CK &K){
+	constexpr int H = N/2, HH = H*H*H, U = (HH + 511)/512;
+	double mine[U];
+	double acc = 0;
+	#pragma unroll
+	for(int u = 0; u < U; u++){
+		const int i = threadIdx.x + u*512;
+		mine[u] = 0;
+		if(i < HH){
+			const int X = i & (H-1), Y = (i / H) & (H-1), Z = i / (H*H);
+			const int x = 2*X, y = 2*Y, z = 2*Z;
+			const double coeff = 1./12.;
+			double v = coeff*(6*sResAt<N>(P,R,x,y,z)
+				+ sResAt<N>(P,R,x+1,y,z) + sResAt<N>(P,R,x-1,y,z)
+				+ sResAt<N>(P,R,x,y+1,z) + sResAt<N>(P,R,x,y-1,z)
+				+ sResAt<N>(P,R,x,y,z+1) + sResAt<N>(P,R,x,y,z-1));
+			mine[u] = v; acc += v;
+		}
+	}
+	const double avg = blockSumC(K, acc)/(double)HH;
+	#pragma unroll
+	for(int u = 0; u < U; u++){ const int i = threadIdx.x + u*512; if(i < HH) Rc[i] = mine[u] - avg; }
+	__syncthreads();
+}
+// trilinear prolongation in the nesting of the reference's three passes (z, then y, then x; multigrid.c:1127-1238);
+// H = coarse size, (x,y,z) = 0-based fine node
+template<int H> static __device__ __forceinline__ double sProlZ(const double *C, int X, int Y, int z){
+	if(!(z & 1)) return C[sIdx<H>(X, Y, z/2)];
+	return 0.5*(C[sIdx<H>(X, Y, (z-1)/2)] + C[sIdx<H>(X, Y, (z+1)/2)]);
+}
+template<int H> static __device__ __forceinline__ double sProlY(const double *C, int X, int y, int z){
+	if(!(y & 1)) return sProlZ<H>(C, X, y/2, z);
+	return 0.5*(sProlZ<H>(C, X, (y-1)/2, z) + sProlZ<H>(C, X, (y+1)/2, z));
+}
+template<int H> static __device__ __forceinline__ double sProl(const double *C, int x, int y, int z){
+	if(!(x & 1)) return sProlY<H>(C, x/2, y, z);
+	return 0.5*(sProlY<H>(C, (x-1)/2, y, z) + sProlY<H>(C, (x+1)/2, y, z));
+}
+// res := P(phi coarse); phi += res; returns the mean of the new phi (the gBnd that follows is applied by the smoother)
+template<int N> static __device__ __noinline__ double sProlongAdd(double *P, const double *Pc, double *resG, int s0, int s1, CK &K){
+	constexpr int NN = N*N*N, U = (NN + 511)/512;
+	double acc = 0;
+	#pragma unroll
+	for(int u = 0; u < U; u++){
+		const int i = threadIdx.x + u*512;
+		if(i < NN){
+			const int x = i & (N-1), y = (i / N) & (N-1), z = i / (N*N);
+			const double p = sProl<N/2>(Pc, x, y, z);
+			resG[(x+1) + (long)s0*((y+1) + (long)s1*(z+1))] = p;
+			double v = P[i]; v += p;
+			P[i] = v;
+			acc += v;
+		}
+	}
+	return blockSumC(K, acc)/(double)NN;
+}
+template<int N> static __device__ __forceinline__ void sSmooth(double *P, const double *R, double *Z, int nCycles, double sIn, CK &K){
+	if(N == 16) sGS16(P, R, Z, nCycles, sIn, K); else sGSOne<N>(P, R, nCycles, sIn, K);
+}
+
 } // namespace pinc

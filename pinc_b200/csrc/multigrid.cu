@@ -518,6 +518,7 @@ struct MgPlan {
 	int exact;               // gBnd after every half-sweep (pending shifts) instead of once per smoother call
 	int smemSmall;           // small levels live in CTA 0's shared memory (descriptors in C)
 	int offZ;                // exchange buffer of the 16^3 smoother in CTA 0's shared memory (doubles), or < 0
+	int pyramid;             // small levels are cubic 16/8/4: specialised routines (mgsmall.cuh)
 	long long *prof;         // optional cycle accounting ($PINC_B200_MGPROF)
 	CPlan C;
 };
@@ -650,6 +651,14 @@ __device__ __noinline__ void fGS(const Lvl &L, int nCycles, double sIn, int exac
 }
 
 
+// division by a run-time divisor that is used many times: q = umulhi(n, ceil(2^32/d)), exact while n*d < 2^32
+struct FD {
+	unsigned m, d;
+	__device__ __forceinline__ explicit FD(int dd) : m(dd > 1 ? 0xFFFFFFFFu/(unsigned)dd + 1u : 0u), d((unsigned)dd) {}
+	__device__ __forceinline__ int div(int n) const { return d > 1 ? (int)__umulhi((unsigned)n, m) : n; }
+	__device__ __forceinline__ void divmod(int n, int &q, int &r) const { q = div(n); r = n - q*(int)d; }
+};
+
 // ---- block-resident mgGS3D ---------------------------------------------------------------------------------------
 // One mailbox slot = {value.lo, tag, value.hi, tag}: a 16-byte store whose two halves each carry the tag, so a reader
 // that sees both tags has the whole value (8-byte single-copy atomicity is all this needs).  No fence, no barrier: the
@@ -721,6 +730,7 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 	const bool act = bid >= 0 && bid < B.nb;
 	const int bx = B.bx, by = B.by, bz = B.bz, ex = bx+2, ey = by+2, pl = ex*ey;
 	const int nA = by*bz, nB = bx*bz, nC = bx*by;
+	const FD dEx(ex), dEy(ey), dBx(bx), dBy(by), dHx(bx/2), dHy(by/2);
 	double *Ph = mgS + B.offPhi;
 	const double *Rh = mgS + B.offRho;
 	double bsum = 0;
@@ -735,8 +745,8 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 		// where my boundary nodes go: the neighbour across face f receives them on its face f^1
 		unsigned out[6];                               // slot offsets from B.mail
 		{
-			int xm = (cx + B.nbx - 1) % B.nbx, xp = (cx + 1) % B.nbx, ym = (cy + B.nby - 1) % B.nby, yp = (cy + 1) % B.nby;
-			int zm = (cz + B.nbz - 1) % B.nbz, zp = (cz + 1) % B.nbz;
+			int xm = cx ? cx-1 : B.nbx-1, xp = cx+1 < B.nbx ? cx+1 : 0, ym = cy ? cy-1 : B.nby-1, yp = cy+1 < B.nby ? cy+1 : 0;
+			int zm = cz ? cz-1 : B.nbz-1, zp = cz+1 < B.nbz ? cz+1 : 0;
 			out[0] = (unsigned)(xm + B.nbx*(cy + B.nby*cz))*slots + fb[1];
 			out[1] = (unsigned)(xp + B.nbx*(cy + B.nby*cz))*slots + fb[0];
 			out[2] = (unsigned)(cx + B.nbx*(ym + B.nby*cz))*slots + fb[3];
@@ -747,7 +757,7 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 		// block + halo layer from global memory (periodic image), with the pending mean shift applied
 		const int ne = pl*(bz+2);
 		auto srcOf = [&](int i) -> const double* {
-			int jl = i % ex, r = i / ex, kl = r % ey, ll = r / ey;
+			int jl, r, kl, ll; dEx.divmod(i, r, jl); dEy.divmod(r, ll, kl);
 			int gj = ox + jl, gk = oy + kl, gl = oz + ll;
 			gj = gj == 0 ? t0 : (gj == t0+1 ? 1 : gj);
 			gk = gk == 0 ? t1 : (gk == t1+1 ? 1 : gk);
@@ -772,7 +782,7 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 		const bool fast = B.on == 1 && items <= 2*(int)blockDim.x && nHalo <= (int)blockDim.x;
 		if(B.offRho >= 0 && !fast)
 			for(int i = threadIdx.x; i < bx*by*bz; i += blockDim.x){
-				int jl = i % bx, r = i / bx, kl = r % by, ll = r / by;
+				int jl, r, kl, ll; dBx.divmod(i, r, jl); dBy.divmod(r, ll, kl);
 				mgS[B.offRho + i] = ldg2(L.rho + ix(ox+jl+1, oy+kl+1, oz+ll+1, L.s0, L.s1));
 			}
 		const double coeff = 1./6.;
@@ -781,17 +791,17 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 			int f, w, j, k, l;
 			if(i < nA){
 				f = i >= nA/2; w = i - f*(nA/2);
-				int uu = w % (by/2); l = w / (by/2) + 1; j = f ? bx+1 : 0;
+				int uu; dHy.divmod(w, l, uu); l += 1; j = f ? bx+1 : 0;
 				k = 2*uu + 1; k += ((j + k + l) & 1) != c;
 				slot = fb[f] + (k-1) + by*(l-1);
 			} else if(i < nA + nB){
 				w = i - nA; f = w >= nB/2; w -= f*(nB/2);
-				int uu = w % hx; l = w / hx + 1; k = f ? by+1 : 0;
+				int uu; dHx.divmod(w, l, uu); l += 1; k = f ? by+1 : 0;
 				j = 2*uu + 1; j += ((j + k + l) & 1) != c;
 				slot = fb[2+f] + (j-1) + bx*(l-1);
 			} else {
 				w = i - nA - nB; f = w >= nC/2; w -= f*(nC/2);
-				int uu = w % hx; k = w / hx + 1; l = f ? bz+1 : 0;
+				int uu; dHx.divmod(w, k, uu); k += 1; l = f ? bz+1 : 0;
 				j = 2*uu + 1; j += ((j + k + l) & 1) != c;
 				slot = fb[4+f] + (j-1) + bx*(k-1);
 			}
@@ -820,7 +830,7 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 					FastNode &n = nd[c][w];
 					n.idx = 0; n.t0 = n.t1 = n.t2 = LL_NONE; n.rho = 0;
 					if(iw < items){
-						int m = iw % hx, r = iw / hx, k = r % by + 1, l = r / by + 1;
+						int m, r, k, l; dHx.divmod(iw, r, m); dBy.divmod(r, l, k); k += 1; l += 1;
 						int j = ((((1+k+l)&1) == c) ? 1 : 2) + 2*m;
 						n.idx = j + ex*(k + ey*l);
 						n.rho = ldg2(L.rho + ix(ox+j, oy+k, oz+l, L.s0, L.s1));
@@ -865,7 +875,7 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 					int iw = i + w*(int)blockDim.x;
 					ok[w] = iw < items;
 					if(!ok[w]) continue;
-					int m = iw % hx, r = iw / hx, k = r % by + 1, l = r / by + 1;
+					int m, r, k, l; dHx.divmod(iw, r, m); dBy.divmod(r, l, k); k += 1; l += 1;
 					int j = ((((1+k+l)&1) == parity) ? 1 : 2) + 2*m;
 					int idx = j + ex*(k + ey*l);
 					double rho = B.offRho >= 0 ? Rh[(j-1) + bx*((k-1) + by*(l-1))] : ldg2(L.rho + ix(ox+j, oy+k, oz+l, L.s0, L.s1));
@@ -882,7 +892,7 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 		}
 		__syncthreads();
 		for(int i = threadIdx.x; i < bx*by*bz; i += blockDim.x){
-			int jl = i % bx, r = i / bx, kl = r % by, ll = r / by;
+			int jl, r, kl, ll; dBx.divmod(i, r, jl); dBy.divmod(r, ll, kl);
 			bsum += Ph[(jl+1) + ex*((kl+1) + ey*(ll+1))];
 		}
 	}
@@ -892,7 +902,7 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 	double avg = S.allSum(bsum)/((double)t0*t1*t2);
 	if(act)
 		for(int i = threadIdx.x; i < bx*by*bz; i += blockDim.x){
-			int jl = i % bx, r = i / bx, kl = r % by, ll = r / by;
+			int jl, r, kl, ll; dBx.divmod(i, r, jl); dBy.divmod(r, ll, kl);
 			L.phi[ix(ox+jl+1, oy+kl+1, oz+ll+1, L.s0, L.s1)] = Ph[(jl+1) + ex*((kl+1) + ey*(ll+1))] - avg;
 		}
 	S.sync();
@@ -966,7 +976,55 @@ template<bool EXACT> __device__ __noinline__ void smallSection(const MgPlan &P, 
 	{	// phi(qs) back to global for the grid-wide prolongation
 		const CLvl &L = C.L[qs];
 		int n = L.nx*L.ny*L.nz;
-		for(int i = threadIdx.x; i < n; i += blockDim.x){ int j,k,l; ownNode(L,1,i,j,k,l); L.phiG[gix(L,j,k,l)] = mgS[L.offPhi + i]; }
+		for(int i = threadIdx.x; i < n; i += blockDim.x){
+			int j,k,l; ownNode(L,1,i,j,k,l);
+			L.phiG[gix(L,j,k,l)] = mgS[L.offPhi + i];
+			if(qs == 0) L.rho[gix(L,j,k,l)] = mgS[L.offRho + i];      // the residual norm reads the neutralised rho
+		}
+	}
+}
+
+// small levels of the benchmark pyramid (cubic, 16^3 / 8^3 / 4^3, gBnd batched): the routines of mgsmall.cuh
+template<int N> __device__ __forceinline__ void pyDown(const CPlan &C, int q, CK &K, double *Z){
+	const CLvl &L = C.L[q];
+	{ ProfScope ps(K, PS_GS_SMALL); ProfScope psl(K, psLvl(L, 0)); sSmooth<N>(mgS + L.offPhi, mgS + L.offRho, Z, C.nPre, 0.0, K); }
+	{ ProfScope ps(K, PS_RESTRICT); ProfScope psl(K, psLvl(L, 1)); sRestrict<N>(mgS + L.offPhi, mgS + L.offRho, mgS + C.L[q+1].offRho, K); }
+}
+template<int N> __device__ __forceinline__ void pyUp(const CPlan &C, int q, CK &K, double *Z){
+	const CLvl &L = C.L[q];
+	double avg;
+	{ ProfScope ps(K, PS_PROLONG); ProfScope psl(K, psLvl(L, 2)); avg = sProlongAdd<N>(mgS + L.offPhi, mgS + C.L[q+1].offPhi, L.res, L.s0, L.s1, K); }
+	{ ProfScope ps(K, PS_GS_SMALL); ProfScope psl(K, psLvl(L, 0)); sSmooth<N>(mgS + L.offPhi, mgS + L.offRho, Z, C.nPost, avg, K); }
+}
+__device__ __noinline__ void smallPyramid(const MgPlan &P, CK &K){
+	const CPlan &C = P.C;
+	const int b = C.nLevels - 1, qs = P.qSmall;
+	double *Z = mgS + (P.offZ >= 0 ? P.offZ : 0);
+	{	// rho(qs) was restricted into global memory by the grid-wide part (or is the solver's input); gBnd(rho)
+		const CLvl &L = C.L[qs];
+		const int N = L.nx, n = N*N*N;
+		for(int i = threadIdx.x; i < n; i += blockDim.x){ int x = i % N, r = i / N, y = r % N, z = r / N; mgS[L.offRho + i] = __ldcg(L.rho + gix(L,x+1,y+1,z+1)); }
+		__syncthreads();
+		ProfScope ps(K, PS_NEUT_RHO);
+		if(N == 16) sNeutralize<16>(mgS + L.offRho, K); else if(N == 8) sNeutralize<8>(mgS + L.offRho, K); else sNeutralize<4>(mgS + L.offRho, K);
+	}
+	for(int q = qs; q < b; q++){ if(C.L[q].nx == 16) pyDown<16>(C, q, K, Z); else pyDown<8>(C, q, K, Z); }
+	{
+		const CLvl &L = C.L[b];
+		ProfScope ps(K, PS_GS_SMALL); ProfScope psl(K, psLvl(L, 0));
+		if(L.nx == 16) sSmooth<16>(mgS + L.offPhi, mgS + L.offRho, Z, C.nCoarse, 0.0, K);
+		else if(L.nx == 8) sSmooth<8>(mgS + L.offPhi, mgS + L.offRho, Z, C.nCoarse, 0.0, K);
+		else sSmooth<4>(mgS + L.offPhi, mgS + L.offRho, Z, C.nCoarse, 0.0, K);
+	}
+	for(int q = b-1; q >= qs; q--){ if(C.L[q].nx == 16) pyUp<16>(C, q, K, Z); else pyUp<8>(C, q, K, Z); }
+	{	// phi(qs) back to global for the grid-wide prolongation / the residual norm
+		const CLvl &L = C.L[qs];
+		const int N = L.nx, n = N*N*N;
+		for(int i = threadIdx.x; i < n; i += blockDim.x){
+			int x = i % N, r = i / N, y = r % N, z = r / N;
+			L.phiG[gix(L,x+1,y+1,z+1)] = mgS[L.offPhi + i];
+			if(qs == 0) L.rho[gix(L,x+1,y+1,z+1)] = mgS[L.offRho + i];
+		}
 	}
 }
 
@@ -1000,7 +1058,8 @@ __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
 		if(qs <= b){
 			if(blockIdx.x == 0){
 				ProfScope pss(K, PS_LEVEL0);
-				if(P.smemSmall){
+				if(P.pyramid) smallPyramid(P, K);
+				else if(P.smemSmall){
 					if(P.exact) smallSection<true>(P, K); else smallSection<false>(P, K);
 				} else {
 					for(int q = qs; q < b; q++) fDown(P, q, S1, seq);
@@ -1130,7 +1189,7 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 	// small levels in CTA 0's shared memory (needs at least one grid-wide level above them)
 	size_t smem = 0;
 	P.smemSmall = 0;
-	if(P.qSmall >= 1 && P.qSmall < nL){
+	if(P.qSmall >= 0 && P.qSmall < nL){
 		long off = 0;
 		bool ok = true;
 		P.C.nLevels = nL; P.C.nBig = P.qSmall; P.C.nPre = P.nPre; P.C.nPost = P.nPost; P.C.nCoarse = P.nCoarse; P.C.nc = 1;
@@ -1149,6 +1208,15 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 		for(int q = P.qSmall; q < nL; q++) if(P.C.L[q].nx == 16 && P.C.L[q].ny == 16 && P.C.L[q].nz == 16){ P.offZ = (int)off; off += MS_ZBUF; break; }
 		smem = (size_t)off*sizeof(double);
 		P.smemSmall = ok ? 1 : 0;
+		bool pyr = ok && !exact && P.nPre > 0 && P.nPost > 0 && P.nCoarse > 0;
+		for(int q = P.qSmall; q < nL; q++){
+			const CLvl &L = P.C.L[q];
+			if(L.nx != L.ny || L.ny != L.nz || (L.nx != 16 && L.nx != 8 && L.nx != 4)) pyr = false;
+			if(L.nx == 4 && q != nL-1) pyr = false;
+			if(L.nx == 16 && P.offZ < 0) pyr = false;
+		}
+		static const bool noPyr = getenv("PINC_B200_MG_PYRAMID") && atoi(getenv("PINC_B200_MG_PYRAMID")) == 0;
+		P.pyramid = pyr && !noPyr ? 1 : 0;
 		if(!ok) smem = 0;
 	}
 	DevGrid *r0 = devGrid(c, mgRho->grids[0]);
@@ -1190,7 +1258,7 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 		static size_t attrSet = 0;
 		if(smem > attrSet){
 			if(cudaFuncSetAttribute((const void*)k_mg_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) attrSet = smem;
-			else { cudaGetLastError(); for(int q = 0; q < nL; q++) P.B[q].on = 0; P.smemSmall = 0; smem = 0; }
+			else { cudaGetLastError(); for(int q = 0; q < nL; q++) P.B[q].on = 0; P.smemSmall = 0; P.pyramid = 0; smem = 0; }
 		}
 	}
 	P.partial = partialBuffer(c, 2L*grid);
@@ -1390,7 +1458,17 @@ void mgSolveRaw(funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 		// (measured: 32^3 304 vs 526 us per V-cycle, 64^3 908 vs 805); larger grids go to the all-SM kernel
 		const Grid *g0 = mgRho->grids[0];
 		long nt0 = (long)g0->trueSize[1]*g0->trueSize[2]*g0->trueSize[3];
-		bool preferCluster = (g_mgMode == 3 || g_mgForceCluster || nt0 <= 65536) && !g_mgNoCluster;
+		// ... unless its small levels are the cubic 16/8/4 pyramid, which the all-SM kernel runs through specialised
+		// routines (measured us per V-cycle, all-SM vs cluster: 16^3 65 vs 123, 32^3 148 vs 288)
+		bool pyramid = g_mgMode == 2;
+		for(int q = 0; q < mgRho->nLevels; q++){
+			const Grid *g = mgRho->grids[q];
+			long nt = (long)g->trueSize[1]*g->trueSize[2]*g->trueSize[3];
+			if(nt > MG_SMALL) continue;
+			int n = g->trueSize[1];
+			if(g->trueSize[2] != n || g->trueSize[3] != n || (n != 16 && n != 8 && n != 4) || (n == 4 && q != mgRho->nLevels-1)) pyramid = false;
+		}
+		bool preferCluster = (g_mgMode == 3 || g_mgForceCluster || (nt0 <= 65536 && !pyramid)) && !g_mgNoCluster;
 		if(g_mgMode >= 2 && preferCluster && clusterSolve(c, mgRho, mgPhi, mgRes, tol, maxCycles, g_mgMode == 3)) return;
 		fusedSolve(c, mgRho, mgPhi, mgRes, tol, maxCycles, g_mgMode == 1 || g_mgMode == 3);
 	} else opsSolve(c, mgAlgo, mgRho, mgPhi, mgRes, mpiInfo, tol, maxCycles);
