@@ -581,6 +581,7 @@ struct Scope {
 
 // gNeutralizeGrid on the true nodes: returns after the subtraction is visible to everyone
 __device__ __noinline__ void fNeutralize(double *v, int s0, int s1, int s2, Scope &S){
+	ProfScope psn(*S.K, S.single ? 27 : 28);
 	int t0 = s0-2, t1 = s1-2, t2 = s2-2; long nt = (long)t0*t1*t2;
 	double acc = 0;
 	for(long i = S.tid(); i < nt; i += S.nthr()){ int j,k,l; truePoint(i,t0,t1,j,k,l); acc += ldg2(v + ix(j,k,l,s0,s1)); }
@@ -909,17 +910,52 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 	if(S.K->prof && bid == 0 && threadIdx.x == 0){ S.K->prof[2*12] += clock64() - tTail; S.K->prof[2*12+1] += 1; }
 }
 
+// gBnd(rho) = gNeutralizeGrid (src/grid.c:730-779) ahead of a block-resident smoother call: every block CTA handles the
+// rho of its own nodes with the thread <-> node mapping of bGS's fast path, so the smoother reads what the same thread
+// wrote and no grid barrier is needed after the subtraction (readers in other CTAs come after the smoother's barriers)
+__device__ __noinline__ void bNeutRho(const Lvl &L, const BLvl &B, Scope &S){
+	ProfScope psn(*S.K, 28);
+	const int bid = (int)blockIdx.x - 1;
+	const bool act = bid >= 0 && bid < B.nb;
+	const int bx = B.bx, by = B.by, bz = B.bz, hx = bx/2, items = hx*by*bz;
+	const FD dHx(hx), dBy(by);
+	long g[4] = {-1, -1, -1, -1}; double r[4] = {0, 0, 0, 0};
+	double acc = 0;
+	if(act){
+		const int cx = bid % B.nbx, cr = bid / B.nbx, cy = cr % B.nby, cz = cr / B.nby;
+		const int ox = cx*bx, oy = cy*by, oz = cz*bz;
+		#pragma unroll
+		for(int u = 0; u < 4; u++){
+			const int c = u >> 1, iw = threadIdx.x + (u & 1)*(int)blockDim.x;
+			if(iw < items){
+				int m, q, k, l; dHx.divmod(iw, q, m); dBy.divmod(q, l, k); k += 1; l += 1;
+				int j = ((((1+k+l)&1) == c) ? 1 : 2) + 2*m;
+				g[u] = ix(ox+j, oy+k, oz+l, L.s0, L.s1);
+			}
+		}
+		#pragma unroll
+		for(int u = 0; u < 4; u++) if(g[u] >= 0) r[u] = ldg2(L.rho + g[u]);
+		#pragma unroll
+		for(int u = 0; u < 4; u++) acc += r[u];
+	}
+	const double avg = S.allSum(acc)/((double)(L.s0-2)*(L.s1-2)*(L.s2-2));
+	#pragma unroll
+	for(int u = 0; u < 4; u++) if(g[u] >= 0) L.rho[g[u]] = r[u] - avg;
+}
 __device__ __noinline__ void fDown(const MgPlan &P, int q, Scope &S, unsigned &seq){
 	const Lvl &L = P.L[q], &C = P.L[q+1];
-	fNeutralize(L.rho, L.s0, L.s1, L.s2, S);
-	if(P.B[q].on && !S.single && P.nPre > 0) bGS(L, P.B[q], P.nPre, 0.0, S, seq); else fGS(L, P.nPre, 0.0, P.exact, S);
+	const bool blk = P.B[q].on && !S.single && P.nPre > 0;
+	if(blk && P.B[q].on == 1) bNeutRho(L, P.B[q], S); else fNeutralize(L.rho, L.s0, L.s1, L.s2, S);
+	if(blk) bGS(L, P.B[q], P.nPre, 0.0, S, seq); else fGS(L, P.nPre, 0.0, P.exact, S);
 	{
+		ProfScope psr(*S.K, S.single ? 27 : 29);
 		int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2; long nt = (long)t0*t1*t2;
 		for(long i = S.tid(); i < nt; i += S.nthr()){ int j,k,l; truePoint(i,t0,t1,j,k,l);
 			L.res[ix(j,k,l,L.s0,L.s1)] = resPoint<true>(L.phi, L.rho, j, k, l, L.s0, L.s1, L.s2); }
 		S.sync();
 	}
 	{
+		ProfScope psr(*S.K, S.single ? 27 : 30);
 		int t0 = C.s0-2, t1 = C.s1-2, t2 = C.s2-2; long nt = (long)t0*t1*t2;
 		for(long i = S.tid(); i < nt; i += S.nthr()){ int J,K,Lz; truePoint(i,t0,t1,J,K,Lz);
 			C.rho[ix(J,K,Lz,C.s0,C.s1)] = restrictPoint<true>(L.res, J, K, Lz, L.s0, L.s1, L.s2); }
@@ -936,6 +972,7 @@ __device__ __noinline__ void fBottom(const MgPlan &P, Scope &S){
 __device__ __noinline__ void fUp(const MgPlan &P, int q, Scope &S, unsigned &seq){
 	const Lvl &L = P.L[q], &C = P.L[q+1];
 	int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2; long nt = (long)t0*t1*t2;
+	const long long tUp = clock64();
 	double acc = 0;
 	for(long i = S.tid(); i < nt; i += S.nthr()){
 		int j,k,l; truePoint(i,t0,t1,j,k,l); long g = ix(j,k,l,L.s0,L.s1);
@@ -946,6 +983,7 @@ __device__ __noinline__ void fUp(const MgPlan &P, int q, Scope &S, unsigned &seq
 		acc += v;
 	}
 	double avg = S.allSum(acc)/(double)nt;
+	if(S.K->prof && blockIdx.x == 0 && threadIdx.x == 0 && !S.single){ S.K->prof[2*31] += clock64() - tUp; S.K->prof[2*31+1] += 1; }
 	if(P.B[q].on && !S.single && P.nPost > 0) bGS(L, P.B[q], P.nPost, avg, S, seq); else fGS(L, P.nPost, avg, P.exact, S);
 	if(P.exact || P.nPost <= 0) fNeutralize(L.phi, L.s0, L.s1, L.s2, S);
 }
@@ -1072,6 +1110,7 @@ __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
 		for(int q = (qs <= b ? qs : b) - 1; q >= 0; q--) fUp(P, q, Sg, seq);
 		// mgSolveRaw :1700-1704: residual, square in place, true-grid sum, RMS
 		const Lvl &L = P.L[0];
+		ProfScope psn(K, PS_NORM);
 		int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2; long nt = (long)t0*t1*t2;
 		double acc = 0;
 		for(long i = Sg.tid(); i < nt; i += Sg.nthr()){
@@ -1237,7 +1276,7 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 			if(!planBlocks(r->tsize[0], r->tsize[1], r->tsize[2], grid-1, smemCap, B)) continue;
 			if(B.bx > 1000 || B.by > 1000 || B.bz > 1000){ B.on = 0; continue; }        // packed node coordinates in bGS
 			static const bool noFast = getenv("PINC_B200_MG_FAST") && atoi(getenv("PINC_B200_MG_FAST")) == 0;
-			if(noFast) B.on = 2;
+			if(noFast || (B.bx/2)*B.by*B.bz > 2*MG_BLOCK || B.by*B.bz + B.bx*B.bz + B.bx*B.by > MG_BLOCK) B.on = 2;      // 1: fast path of bGS
 			mailOff[q] = mailSlots;
 			mailSlots += (size_t)B.nb*2*(B.by*B.bz + B.bx*B.bz + B.bx*B.by);
 			size_t need = (size_t)(B.offRho >= 0 ? B.offRho + B.bx*B.by*B.bz : (B.bx+2)*(B.by+2)*(B.bz+2))*sizeof(double);

@@ -191,6 +191,38 @@ template<int MODE> void runLL2(int grid, long long *out, int perFace = 85){
 	printf("%-46s grid=%3d slots/face=%2d : %7.1f cycles per phase  %s\n", nm[MODE], grid, perFace, (double)h/n, cudaGetErrorString(cudaGetLastError()));
 	cudaFree(mail); cudaFree(flags); cudaFree(plain);
 }
+// S: how long does the ISSUE of three 16-byte stores to three different lines take (clock before/after, no wait)?
+__device__ int g_act = 512;
+template<int KIND> __global__ void kStoreIssue(uint4 *buf, long long *out, int n){
+	const bool on = (int)threadIdx.x < g_act;
+	long long tot = 0;
+	for(int i = 0; i < n; i++){
+		__syncthreads();
+		long long t0 = clock64();
+		#pragma unroll
+		for(int q = 0; q < 3; q++){
+			if(!on) continue;
+			uint4 *p = buf + ((size_t)((blockIdx.x*7 + q*41 + i) % 148)*4096 + threadIdx.x + q*1024);
+			unsigned a = i, b = i + 1;
+			if(KIND == 0) asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(a), "r"(b), "r"(a), "r"(b) : "memory");
+			if(KIND == 1) asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(a), "r"(b), "r"(a), "r"(b) : "memory");
+			if(KIND == 2) asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(a), "r"(b), "r"(a), "r"(b) : "memory");
+			if(KIND == 3) asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(a), "r"(b), "r"(a), "r"(b) : "memory");
+		}
+		tot += clock64() - t0;
+	}
+	if(threadIdx.x == 0 && blockIdx.x == 0) out[0] = tot;
+}
+template<int KIND> void runStoreIssue(long long *out, int act = 512){
+	cudaMemcpyToSymbol(g_act, &act, sizeof(int));
+	uint4 *buf; cudaMalloc(&buf, (size_t)148*4096*16);
+	int n = 1000; long long h = 0;
+	for(int rep = 0; rep < 2; rep++){ kStoreIssue<KIND><<<128, 512>>>(buf, out, n); cudaDeviceSynchronize(); }
+	cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);
+	const char *nm[] = {"st.relaxed.gpu", "st.global.cg", "st.volatile", "st.global (default)"};
+	printf("S issue of 3 x 16-byte %-20s active threads %3d : %7.1f cycles  %s\n", nm[KIND], act, (double)h/n, cudaGetErrorString(cudaGetLastError()));
+	cudaFree(buf);
+}
 template<int NB, int ACTIVE> void runLL(int grid, long long *out){
 	uint4 *mail; cudaMalloc(&mail, (size_t)148*6*512*16);
 	const int n = 2000; long long h = 0;
@@ -206,6 +238,7 @@ template<int NB, int ACTIVE> void runLL(int grid, long long *out){
 }
 int main(){
 	{ long long *o; cudaMalloc(&o, 16);
+	  runStoreIssue<0>(o); runStoreIssue<1>(o); runStoreIssue<0>(o, 1); runStoreIssue<0>(o, 32); runStoreIssue<0>(o, 128); runStoreIssue<3>(o, 32);
 	  runLL<2,32>(16, o); runLL<2,32>(128, o); runLL<6,32>(128, o); runLL<6,128>(128, o); runLL<6,512>(128, o); runLL<6,512>(148, o); runLL<2,512>(128, o);
 	  runLL2<0>(128, o); runLL2<1>(128, o); runLL2<2>(128, o); runLL2<3>(128, o); runLL2<4>(128, o);
 	  for(int pf : {1, 5, 21, 42}){ runLL2<0>(128, o, pf); runLL2<4>(128, o, pf); } runLL2<0>(16, o, 85); runLL2<0>(64, o, 85); cudaFree(o); }
