@@ -200,14 +200,14 @@ void mgFreeSolver(MultigridSolver *solver);                                     
 int pincMgLastHistory(double *barRes, int cap);
 /* execution mode of single-rank periodic solves (same arithmetic per node in all of them):
  *   0 ops            one kernel per reference call, ghost layers exchanged as the reference does;
- *   1 fused          one persistent cooperative kernel over all SMs, gBnd after every half-sweep;
- *   2 cluster        one kernel on one 16-CTA cluster, phi of all levels in distributed shared memory,
- *                    gBnd's mean subtraction applied once per smoother call (default; falls back to 1
- *                    when the levels do not fit the cluster's shared memory);
- *   3 cluster-exact  as 2 with gBnd after every half-sweep;
+ *   1 fused          one persistent cooperative kernel over all SMs, a grid barrier and gBnd after every half-sweep;
+ *   2 auto           (default) the same kernel with gBnd's mean subtraction applied once per smoother call, grid-wide
+ *                    levels smoothed block-resident in shared memory (faces exchanged through tagged mailboxes in L2)
+ *                    and levels of <= 4096 nodes inside one CTA; grids of <= 65536 nodes whose small levels are not
+ *                    the cubic 16/8/4 pyramid run on one 16-CTA cluster with phi in distributed shared memory;
+ *   3 cluster-exact  the cluster kernel with gBnd after every half-sweep;
  *   4 cluster-always as 2, but the cluster kernel is used whenever the levels fit its shared memory;
- *   5 allsm          as 2, but always the all-SM kernel (grid-wide levels smoothed block-resident in shared memory
- *                    with the faces exchanged through tagged mailboxes in L2, small levels inside CTA 0).
+ *   5 allsm          as 2, but always the all-SM kernel.
  * Multi-rank solves: 2 = smoother and ghost fills over NVLink peer memory, V-cycle replayed as a CUDA graph;
  * 0/1/3 = one kernel and one exchange per reference call.
  * $PINC_B200_MG = ops | fused | cluster | cluster-exact | cluster-always | allsm selects the start-up value. */

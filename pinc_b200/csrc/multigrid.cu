@@ -6,17 +6,17 @@
 //
 //  ops    one kernel per reference call, ghost layers kept current by gHaloOp/gBnd exactly as the
 //         reference does.  Used for the individual entry points and whenever the solve spans several ranks.
-//  fused  single-rank periodic solves: ONE persistent cooperative kernel runs the whole tolerance loop.
-//         Ghost layers are not touched inside (neighbours are read at the periodic image of the true node,
-//         which is bit-identical to reading a ghost that setSlice just filled), the mean subtraction of
-//         gBnd is carried as a pending shift that is applied when a value is next read (each value is still
-//         rounded by one subtraction per gBnd, as in the reference), true-grid sums are fused into the sweep
-//         that precedes them, and levels of <= 8192 nodes run inside one CTA on __syncthreads instead of
-//         grid barriers.  Ghosts of every level are filled once at the end, so the arrays are left in the
-//         state the reference leaves them in.
+//  fused  single-rank periodic solves: ONE persistent cooperative kernel (k_mg_solve) runs the whole tolerance loop.
+//         Ghost layers are not touched inside (neighbours are read at the periodic image of the true node, which is
+//         bit-identical to reading a ghost that setSlice just filled) and are filled once at the end, so the arrays are
+//         left in the state the reference leaves them in.  Grid-wide levels are smoothed block-resident in shared
+//         memory with the faces exchanged through tagged mailboxes in L2 (bGS); levels of <= 4096 nodes run inside
+//         CTA 0 (mgsmem.cuh, mgsmall.cuh); transfers are grid-stride phases between grid barriers.  gBnd's mean
+//         subtraction is applied once per smoother call (mode 2) or carried bit-faithfully as a pending shift that is
+//         applied when a value is next read (modes 1, 3).
 //
-// The grids of a level are tiny (<= 2.2 M nodes): the solver is bound by the latency of ~45 dependent
-// half-sweeps per level per V-cycle, not by HBM, which is why the fused mode exists.
+// The grids of a level are tiny (<= 2.2 M nodes): the solver is bound by the latency of 180 dependent half-sweeps per
+// V-cycle and ~50 V-cycles per solve, not by HBM, which is why the fused mode exists.
 #include "common.h"
 #include <cmath>
 #include "mgsmem.cuh"
