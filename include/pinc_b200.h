@@ -41,6 +41,9 @@ typedef PINC_HID_T pinc_hid_t;
  * src/grid.h:22-25, src/multigrid.h:27-57)
  * ------------------------------------------------------------------------------- */
 typedef void (*funPtr)();                       /* core.h:467 */
+#ifndef _DICTIONARY_H_
+typedef struct _dictionary_ dictionary;         /* lib/iniparser/src/dictionary.h:41-47; opaque here: read through the host's iniGet* */
+#endif
 
 typedef enum { PERIODIC = 0x01, DIRICHLET = 0x02, NEUMANN = 0x03, NONE = 0x10 } bndType; /* core.h:146-151 */
 typedef enum { TOHALO = 0, FROMHALO = 1 } opDirection;                                  /* grid.h:22-25 */
@@ -152,6 +155,15 @@ void pincGet3DRotationParameters(int nSpecies, const double *BExt, const double 
  * returns 0 if the configuration is acceptable, else an error code and a message. */
 int  pincPuSanity(const char *name, int nDims, const int *nGhostLayers, const double *thresholds,
                   int dim, int order, char *errbuf, int errlen);
+/* The X_set(ini) selectors that io.h:105 select() calls, mgSolver_set and mgAllocSolver, puGet3DRotationParameters: same
+ * names, signatures and checks as the reference.  They read `ini` through the host's own iniGetInt / iniGetStr /
+ * iniGetIntArr / iniGetDoubleArr (src/io.h:228-240, weak references resolved from the PINC executable's io.o); a
+ * host without PINC's ini layer uses the pinc* plain-argument forms above and below. */
+funPtr puAcc3D1_set(dictionary *ini);                                           /* pusher.h:119 (pusher.c:143) */
+funPtr puAcc3D1KE_set(dictionary *ini);                                         /* pusher.h:120 (pusher.c:174) */
+funPtr puDistr3D1_set(dictionary *ini);                                         /* pusher.h:163 (pusher.c:508) */
+funPtr puExtractEmigrants3D_set(const dictionary *ini);                         /* pusher.h:180 (pusher.c:777) */
+void puGet3DRotationParameters(dictionary *ini, double *T, double *S);          /* pusher.h:128 (pusher.c:485) */
 
 /* ---------------------------------------------------------------------------------
  * Grid path (src/grid.h)
@@ -189,7 +201,9 @@ void mgHalfRestrict3D(const Grid *fine, Grid *coarse);                          
 void mgBilinProl3D(Grid *fine, const Grid *coarse, const MpiInfo *mpiInfo);     /* multigrid.c:1127 */
 void mgResidual(Grid *res, const Grid *rho, const Grid *phi, const MpiInfo *mpiInfo); /* multigrid.c:1385 */
 double mgSumTrueSquared(Grid *error, const MpiInfo *mpiInfo);                   /* multigrid.c:1471 */
-void mgSolver(void (**solve)(), MultigridSolver *(**solverAlloc)(), void (**solverFree)()); /* multigrid.c:392 */
+void mgSolver(void (**solve)(), MultigridSolver *(**solverAlloc)(), void (**solverFree)()); /* multigrid.c:392: hands out mgSolve, mgAllocSolver, mgFreeSolver */
+funPtr mgSolver_set(const dictionary *ini);                                     /* multigrid.h:92 (multigrid.c:398) */
+MultigridSolver *mgAllocSolver(const dictionary *ini, Grid *rho, Grid *phi);    /* multigrid.h:93 (multigrid.c:364): reads [multigrid] through the host's iniGet* */
 /* plain-argument form of mgAllocSolver/mgAlloc/mgAllocSubGrids (multigrid.c:128-382);
  * the reference reads the five integers from [multigrid] of the ini file. */
 MultigridSolver *pincMgAllocSolver(Grid *rho, Grid *phi, int mgLevels, int mgCycles,

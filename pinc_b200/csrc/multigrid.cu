@@ -1520,7 +1520,7 @@ void mgSolve(const MultigridSolver *solver, const Grid *rho, const Grid *phi, co
 
 void mgSolver(void (**solve)(), MultigridSolver *(**solverAlloc)(), void (**solverFree)()){
 	*solve = (void(*)())mgSolve;
-	*solverAlloc = (MultigridSolver*(*)())pincMgAllocSolver;
+	*solverAlloc = (MultigridSolver*(*)())mgAllocSolver;          // the reference's signature (ini, rho, phi): inihost.cpp
 	*solverFree = (void(*)())mgFreeSolver;
 }
 

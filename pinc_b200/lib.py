@@ -72,6 +72,14 @@ SIGNATURES = {
     "mgFreeSolver": (None, [P(abi.MultigridSolver)]),
     "pincMgLastHistory": (C.c_int, [abi.c_double_p, C.c_int]),
     "pincMgSetMode": (None, [C.c_int]),
+    # entry points that take PINC's dictionary *ini (need the host's iniGet*; typed for the symbol check)
+    "puAcc3D1_set": (C.c_void_p, [C.c_void_p]),
+    "puAcc3D1KE_set": (C.c_void_p, [C.c_void_p]),
+    "puDistr3D1_set": (C.c_void_p, [C.c_void_p]),
+    "puExtractEmigrants3D_set": (C.c_void_p, [C.c_void_p]),
+    "puGet3DRotationParameters": (None, [C.c_void_p, abi.c_double_p, abi.c_double_p]),
+    "mgSolver_set": (C.c_void_p, [C.c_void_p]),
+    "mgAllocSolver": (P(abi.MultigridSolver), [C.c_void_p, P(abi.Grid), P(abi.Grid)]),
     # host-struct constructors
     "pincGridAlloc": (P(abi.Grid), [C.c_int, abi.c_int_p, abi.c_int_p, C.c_int, abi.c_int_p]),
     "pincGridFree": (None, [P(abi.Grid)]),

@@ -133,6 +133,31 @@ def test_rotation_parameters_and_solver_structs_on_host():
     L.pincGridFree(rho); L.pincGridFree(phi)
 
 
+def test_ini_entry_points_from_a_pinc_style_host(tmp_path):
+    """The entry points that take `dictionary *ini` (X_set selectors of io.h:105 select(), the mgSolver triple,
+    mgAllocSolver, puGet3DRotationParameters) driven from a C host that brings its own iniGet* layer, as PINC's
+    main.c:55-99 does; wrong configurations end like msg(ERROR)."""
+    exe = str(tmp_path / "ini_host")
+    so_dir = os.path.join(ROOT, "pinc_b200")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "ini_host.c"),
+                           "-o", exe, "-L", so_dir, "-lpinc_b200", "-Wl,-rpath," + so_dir])
+    r = subprocess.run([exe, "ok"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "ini-host-ok" in r.stdout, (r.returncode, r.stderr)
+    r = subprocess.run([exe, "badcycle"], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "PINC-B200 ERROR" in r.stderr and "mgVRecursive only" in r.stderr
+    r = subprocess.run([exe, "baddims"], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "only supports grid:nDims=3" in r.stderr
+
+
+def test_ini_entry_points_need_the_hosts_ini_layer():
+    """Without iniGet* in the process (this Python host) the ini-taking entry points fail loudly instead of guessing."""
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from pinc_b200 import lib\n"
+            "L = lib.load()\nL.puAcc3D1_set(None)\nprint('survived')\n") % ROOT
+    r = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "survived" not in r.stdout and "ini layer" in r.stderr
+
+
 def test_missing_device_fails_loudly():
     """No CPU fallback: without a GPU a compute entry point terminates with the reference's ERROR convention."""
     code = ("import sys; sys.path.insert(0, %r)\n"
