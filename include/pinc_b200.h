@@ -147,6 +147,8 @@ int  puNeighborToReciprocal(int neighbor, int nDims);                           
 void pPosAssertInLocalFrame(const Population *pop, const Grid *grid);           /* population.h (population.c:316) */
 void pVelAssertMax(const Population *pop, double max);                          /* population.h (population.c:343) */
 void pSumKinEnergy(Population *pop);                                            /* population.h (population.c:700) */
+void pNew(Population *pop, int s, const double *pos, const double *vel);        /* population.h:108 (population.c:430) */
+void pCut(Population *pop, int s, long int p, double *pos, double *vel);        /* population.h:128 (population.c:452) */
 /* plain-argument form of puGet3DRotationParameters (pusher.c:485; the reference reads
  * BExt/charge/mass from the ini dictionary, which stays host code) */
 void pincGet3DRotationParameters(int nSpecies, const double *BExt, const double *charge,

@@ -62,6 +62,9 @@ def load():
     lib.orc_rotation_parameters.argtypes = [C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]
     lib.orc_distr3d1.argtypes = [c_double_p, C.c_int, c_long_p, c_long_p, c_double_p, c_double_p, c_int_p]
     lib.orc_extract3d.argtypes = [c_double_p, c_double_p, C.c_int, c_long_p, c_long_p, c_double_p, PP, c_long_p]
+    lib.orc_pnew.argtypes = [c_double_p, c_double_p, c_long_p, c_long_p, C.c_int, c_double_p, c_double_p]
+    lib.orc_pnew.restype = C.c_int
+    lib.orc_pcut.argtypes = [c_double_p, c_double_p, c_long_p, C.c_int, C.c_long, c_double_p, c_double_p]
     lib.orc_neighbor_to_rank.argtypes = [P(OrcTopo), C.c_int, C.c_int]
     lib.orc_neighbor_to_reciprocal.argtypes = [C.c_int]
     lib.orc_rank_to_neighbor.argtypes = [P(OrcTopo), C.c_int, C.c_int]

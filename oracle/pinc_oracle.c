@@ -573,3 +573,24 @@ void orc_step(OrcSim *s){
 	for(int r=0;r<R;r++) pe += orc_pot_energy(s->rho[r],s->phi[r],s->size);
 	s->potEnergy = pe;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * pNew / pCut (src/population.c:430-466): the reference's single-particle insert and the
+ * extract-with-back-fill that puExtractEmigrants3D's serial loop is built on; pinned by
+ * test/population.test.c:10-56.  p is the FLAT index of the particle's first coordinate.
+ * ---------------------------------------------------------------------------------------- */
+int orc_pnew(double *pos, double *vel, const long *iStart, long *iStop, int s, const double *p3, const double *v3){
+	if(iStop[s] >= iStart[s+1]) return 0;                 /* "New particle ignored" */
+	long p = iStop[s]*3;
+	for(int d=0;d<3;d++){ pos[p+d] = p3[d]; vel[p+d] = v3[d]; }
+	iStop[s]++;
+	return 1;
+}
+void orc_pcut(double *pos, double *vel, long *iStop, int s, long p, double *p3, double *v3){
+	long pLast = (iStop[s]-1)*3;
+	for(int d=0;d<3;d++){
+		p3[d] = pos[p+d]; v3[d] = vel[p+d];
+		pos[p+d] = pos[pLast+d]; vel[p+d] = vel[pLast+d];
+	}
+	iStop[s]--;
+}

@@ -42,6 +42,8 @@ void orc_distr3d1(const double *pos, int nSpecies, const long *iStart, const lon
                   const double *charge, double *rho, const int *size);
 void orc_extract3d(double *pos, double *vel, int nSpecies, const long *iStart, long *iStop,
                    const double *thresholds, double **emigrants /*27*/, long *nEmigrants /*27*nSpecies*/);
+int  orc_pnew(double *pos, double *vel, const long *iStart, long *iStop, int s, const double *p3, const double *v3);
+void orc_pcut(double *pos, double *vel, long *iStop, int s, long p, double *p3, double *v3);
 int  orc_neighbor_to_rank(const OrcTopo *t, int rank, int ne);
 int  orc_neighbor_to_reciprocal(int ne);
 int  orc_rank_to_neighbor(const OrcTopo *t, int rank, int other);

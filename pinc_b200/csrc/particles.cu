@@ -461,6 +461,13 @@ static void setupCells(Ctx *c, DevPop *dp, const MpiInfo *m){
 	dp->nCells = nCells;
 	dp->keysValid = false;
 }
+// pNew / pCut (src/population.c:430-466): one particle in or out of the SoA planes
+__global__ void k_particle_put(double *__restrict__ P, long cap, long i, double x, double y, double z, double vx, double vy, double vz){
+	if(threadIdx.x == 0){ P[i] = x; P[i + cap] = y; P[i + 2*cap] = z; P[i + 3*cap] = vx; P[i + 4*cap] = vy; P[i + 5*cap] = vz; }
+}
+__global__ void k_particle_cut(double *__restrict__ P, long cap, long i, long last, double *__restrict__ out){
+	if(threadIdx.x < 6){ long o = threadIdx.x*cap; out[threadIdx.x] = P[i + o]; P[i + o] = P[last + o]; }
+}
 static CellSpace cellsOf(const DevPop *dp){ return CellSpace{ dp->nc[0], dp->nc[1], dp->nc[2], dp->nCells }; }
 
 static void dropPredeposit(DevPop *dp);
@@ -754,6 +761,34 @@ static void assertScan(Ctx *c, const Population *pop, int which, const double *l
 }
 
 // src/population.c:316-341: every live particle inside [0, size-1] in every dimension, else msg(ERROR)
+/* population.c:430-450: append one particle to species s (ignored with a warning when the species is full) */
+void pNew(Population *pop, int s, const double *pos, const double *vel){
+	Ctx *c = cur(); DevPop *dp = devPop(c, pop);
+	if(pop->nDims != 3) fatal("pNew: only nDims=3 is implemented");
+	if(pop->iStop[s] >= pop->iStart[s+1]){
+		fprintf(stderr, "PINC-B200 WARNING: Not enough allocated memory to add new particle to specie %i. New particle ignored.\n", s);
+		return;
+	}
+	invalidateOrder(dp);
+	PINC_LAUNCH(c, K_MOVE, 48.0, (k_particle_put<<<1,32,0,c->stream>>>(dp->base, dp->cap, pop->iStop[s], pos[0], pos[1], pos[2], vel[0], vel[1], vel[2])));
+	pop->iStop[s]++;
+}
+/* population.c:452-466: take the particle whose first coordinate sits at flat index p (= particle index * nDims) out of
+ * species s, return its position and velocity and fill the hole with the species' last particle */
+void pCut(Population *pop, int s, long int p, double *pos, double *vel){
+	Ctx *c = cur(); DevPop *dp = devPop(c, pop);
+	if(pop->nDims != 3) fatal("pCut: only nDims=3 is implemented");
+	long i = p/3, last = pop->iStop[s] - 1;
+	if(p % 3 || i < pop->iStart[s] || i > last) fatal("pCut: flat index %ld is not a live particle of specie %i", p, s);
+	invalidateOrder(dp);
+	double *d_out = (double*)c->d_long;
+	PINC_LAUNCH(c, K_MOVE, 96.0, (k_particle_cut<<<1,32,0,c->stream>>>(dp->base, dp->cap, i, last, d_out)));
+	double h[6];
+	PINC_CUDA(cudaMemcpyAsync(h, d_out, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+	streamSync(c);
+	for(int d = 0; d < 3; d++){ pos[d] = h[d]; vel[d] = h[3+d]; }
+	pop->iStop[s]--;
+}
 void pPosAssertInLocalFrame(const Population *pop, const Grid *grid){
 	double lo[3] = {0, 0, 0}, hi[3];
 	for(int d = 0; d < 3; d++) hi[d] = (double)(grid->size[d+1] - 1);

@@ -35,6 +35,8 @@ SIGNATURES = {
     "pSumKinEnergy": (None, [P(abi.Population)]),
     "pPosAssertInLocalFrame": (None, [P(abi.Population), P(abi.Grid)]),
     "pVelAssertMax": (None, [P(abi.Population), C.c_double]),
+    "pNew": (None, [P(abi.Population), C.c_int, abi.c_double_p, abi.c_double_p]),
+    "pCut": (None, [P(abi.Population), C.c_int, C.c_long, abi.c_double_p, abi.c_double_p]),
     "pincGet3DRotationParameters": (None, [C.c_int, abi.c_double_p, abi.c_double_p, abi.c_double_p, abi.c_double_p, abi.c_double_p]),
     "pincPuSanity": (C.c_int, [C.c_char_p, C.c_int, abi.c_int_p, abi.c_double_p, C.c_int, C.c_int, C.c_char_p, C.c_int]),
     # grid path

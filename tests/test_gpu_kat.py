@@ -185,3 +185,24 @@ def test_debug_scans_pass_and_fail_like_the_reference(gpu_lib):
         r = subprocess.run([sys.executable, "-c", code % (ROOT, os.path.join(ROOT, "tests"), posy, vely)], capture_output=True, text=True, timeout=300)
         assert r.returncode != 0 and "survived" not in r.stdout
         assert "Particle i=1 (of specie 0) " + msg in r.stderr, r.stderr[-500:]
+
+
+def test_kat_pnew_pcut(gpu_lib):
+    """test/population.test.c:10-56 through the device population: pNew x 4, pCut(pop,1,33) twice."""
+    L = gpu_lib
+    k = KAT["pcut"]
+    p = L.pincPopAlloc(2, 3, la(k["nAlloc"]), da([-1.0, 1.0]), da([1.0, 100.0]))
+    L.pincSyncPopToDevice(p)
+    for p3, v3 in k["new"]:
+        L.pNew(p, 1, da(p3), da(v3))
+    assert p.contents.iStop[1] == k["nAlloc"][0] + 4
+    for which in ("first", "second"):
+        p3, v3 = (C.c_double * 3)(), (C.c_double * 3)()
+        L.pCut(p, 1, k["cut_flat_index"], p3, v3)
+        assert list(p3) == k[which]["pos"] and list(v3) == k[which]["vel"] and p.contents.iStop[1] == k[which]["iStop1"]
+    # what is left is particles 0 and 2 of the four, in the reference's back-filled order
+    L.pincSyncPopToHost(p)
+    pos, vel = abi.pop_arrays(p.contents)
+    a = p.contents.iStart[1]
+    assert pos[a:a + 2].tolist() == [[0, 1, 2], [6, 7, 8]] and vel[a:a + 2].tolist() == [[0, 10, 20], [60, 70, 80]]
+    L.pincPopFree(p)

@@ -161,3 +161,23 @@ def test_gradient_and_laplacian_analytic():
     O.orc_residual(orc.dp(res), orc.dp(np.zeros(f.size)), orc.dp(f), orc.ip(size))
     rv = res.reshape(size[2], size[1], size[0])[1:-1, 1:-1, 1:-1]
     assert np.abs(rv - (-4 + 24 * z)[1:-1, 1:-1, 1:-1]).max() < 1e-11
+
+
+def test_pnew_pcut_backfill():
+    """test/population.test.c:10-56: pNew appends at iStop[s]; pCut returns the particle and back-fills with the last."""
+    k = KAT["pcut"]
+    O = orc.load()
+    cap = k["nAlloc"]
+    iStart = i64([0, cap[0], cap[0] + cap[1]])
+    iStop = i64([0, cap[0]])
+    pos, vel = np.zeros(3 * (cap[0] + cap[1])), np.zeros(3 * (cap[0] + cap[1]))
+    for p3, v3 in k["new"]:
+        assert O.orc_pnew(orc.dp(pos), orc.dp(vel), orc.lp(iStart), orc.lp(iStop), 1, orc.dp(f64(p3)), orc.dp(f64(v3))) == 1
+    assert iStop[1] == cap[0] + 4
+    for which in ("first", "second"):
+        p3, v3 = np.zeros(3), np.zeros(3)
+        O.orc_pcut(orc.dp(pos), orc.dp(vel), orc.lp(iStop), 1, k["cut_flat_index"], orc.dp(p3), orc.dp(v3))
+        assert list(p3) == k[which]["pos"] and list(v3) == k[which]["vel"] and iStop[1] == k[which]["iStop1"]
+    # a full species ignores the new particle (population.c:436-438)
+    iStop[1] = iStart[2]
+    assert O.orc_pnew(orc.dp(pos), orc.dp(vel), orc.lp(iStart), orc.lp(iStop), 1, orc.dp(f64([1, 1, 1])), orc.dp(f64([0, 0, 0]))) == 0
