@@ -670,13 +670,11 @@ __device__ __forceinline__ void llStore(uint4 *p, double v, unsigned tag){
 	unsigned lo = (unsigned)__double_as_longlong(v), hi = (unsigned)(__double_as_longlong(v) >> 32);
 	asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
 }
-__constant__ unsigned c_llSleep;
 __device__ __forceinline__ double llWait(const uint4 *p, unsigned tag){
 	unsigned a, b, c, d, spins = 0;
 	for(;;){
 		asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
 		if(b == tag && d == tag) break;
-		if(c_llSleep) __nanosleep(c_llSleep);
 		if(++spins > (1u << 22)) __trap();             // ~2 s: a lost neighbour must not hang the device
 	}
 	return __longlong_as_double(((long long)c << 32) | (long long)a);
@@ -1263,7 +1261,6 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 	int grid = P.qSmall == 0 ? 1 : c->numSMs;
 	// block-resident smoothing of the grid-wide levels (batched gBnd only; CTA 0 is left to the small levels)
 	P.seqWord = c->d_bar + 16;
-	{ static bool once = false; if(!once){ once = true; unsigned ns = getenv("PINC_B200_MG_SLEEP") ? atoi(getenv("PINC_B200_MG_SLEEP")) : 0; PINC_CUDA(cudaMemcpyToSymbol(c_llSleep, &ns, sizeof(ns))); } }
 	static const bool blocksOff = getenv("PINC_B200_MG_BLOCKS") && atoi(getenv("PINC_B200_MG_BLOCKS")) == 0;
 	if(!exact && grid > 8 && !blocksOff){
 		int smemOptin = 0;
