@@ -312,7 +312,10 @@ def run_ours(args, n_gpus, rank, world_size):
                                    f"{n_live} particles (Maxwellian, sigma_v={cfg.thermalVelocity} cells/step), nSubdomains={cfg.nSubdomains}",
                        "global_particles": int(n_global), "mgLevels": cfg.mgLevels, "parallelism": f"domain-decomposition x{world_size}",
                        "l2": "particle arrays (48 B x particles per GPU) exceed the 126 MB L2; no explicit flush",
-                       "vcycles_last_solve": len(hist), "ic_seconds": t_ic},
+                       "vcycles_last_solve": len(hist), "ic_seconds": t_ic,
+                       "mg_path": {0: "distributed, one kernel per reference call", 1: "all-SM persistent kernel", 2: "cluster kernel",
+                                   5: "replicated: global problem on every rank, all-SM persistent kernel",
+                                   6: "replicated: global problem on every rank, cluster kernel"}.get(W.mg_path(), "?")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels}
     W.close()
     return line

@@ -214,6 +214,10 @@ void mgFreeSolver(MultigridSolver *solver);                                     
 /* residual history of the most recent mgSolve on this rank: returns the V-cycle count and
  * copies up to `cap` values of barRes (multigrid.c:1700-1704), one per V-cycle. */
 int pincMgLastHistory(double *barRes, int cap);
+/* which implementation ran the most recent mgSolve on this rank: 0 one kernel per reference call (distributed), 1 the
+ * all-SM persistent kernel, 2 the cluster kernel; +4: a multi-rank solve done by replication (every rank gathers rho and
+ * phi, solves the global problem with the single-GPU kernel and keeps its own sub-domain) */
+int pincMgLastPath(void);
 /* execution mode of single-rank periodic solves (same arithmetic per node in all of them):
  *   0 ops            one kernel per reference call, ghost layers exchanged as the reference does;
  *   1 fused          one persistent cooperative kernel over all SMs, a grid barrier and gBnd after every half-sweep;

@@ -112,6 +112,9 @@ struct Ctx {
 	bool mgHistPending = false;
 	std::vector<double> mgHistory;
 	std::unordered_map<const void*, CycleGraph> cycleGraphs;     // keyed by the solver's mgRho
+	std::unordered_map<const void*, void*> mgGlobal;             // replicated global hierarchies of multi-rank solves (multigrid.cu)
+	bool mgGlobalBusy = false;
+	int mgLastPath = 0;                                          // pincMgLastPath: 0 ops, 1 all-SM kernel, 2 cluster kernel, +4 replicated
 	Transport *tp = nullptr;
 	std::string lastError;
 };

@@ -501,7 +501,7 @@ static void opVCycle(Ctx *c, int level, int bottom, int top, Multigrid *mgRho, M
 // Block-resident smoothing of a grid-wide level: CTA 1+b keeps block b (bx x by x bz true nodes + one halo layer) of phi
 // in its shared memory for a whole mgGS3D call; the faces travel through per-CTA mailboxes in L2 (see bGS).
 struct BLvl {
-	int on, bx, by, bz, nbx, nby, nbz, nb;
+	int on, bx, by, bz, nbx, nby, nbz, nb, rows;
 	int offPhi, offRho;      // shared-memory offsets in doubles; offRho < 0: rho is read from global memory
 	uint4 *mail;             // nb x 2(by*bz + bx*bz + bx*by) slots
 };
@@ -785,6 +785,8 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 				mgS[B.offRho + i] = ldg2(L.rho + ix(ox+jl+1, oy+kl+1, oz+ll+1, L.s0, L.s1));
 			}
 		const double coeff = 1./6.;
+		int hxShift = 0; while((1 << hxShift) < hx) hxShift++;
+		const bool rowLanes = B.rows && hx >= 1 && hx <= 32 && (1 << hxShift) == hx;
 		// halo node i (0 <= i < nHalo) of colour c: mailbox slot and index into the block array
 		auto haloNode = [&](int i, int c, int &slot, int &hidx){
 			int f, w, j, k, l;
@@ -853,19 +855,70 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 		} else
 		for(int h = 0; h < 2*nCycles; h++){
 			const int parity = (h & 1) ? 0 : 1;
+			long long *pfg = (S.K->prof && bid == 0 && threadIdx.x == 0) ? S.K->prof : nullptr;
+			long long tg0 = pfg ? clock64() : 0;
 			if(h > 0){
 				// receive the other colour's face nodes of half-sweep h-1
 				const unsigned tag = seq + (unsigned)h;
 				const int c = 1 - parity;
-				for(int i = threadIdx.x; i < nHalo; i += blockDim.x){
+				// a thread's (up to four) slots are read together, only the ones that have not arrived yet are polled again
+				int hs[4], hi[4]; unsigned ra[4], rb[4], rc[4], rd[4];
+				#pragma unroll
+				for(int w = 0; w < 4; w++){
+					int i = threadIdx.x + w*(int)blockDim.x;
+					hs[w] = -1;
+					if(i < nHalo){
+						haloNode(i, c, hs[w], hi[w]);
+						asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ra[w]), "=r"(rb[w]), "=r"(rc[w]), "=r"(rd[w]) : "l"(mine + hs[w]) : "memory");
+					}
+				}
+				#pragma unroll
+				for(int w = 0; w < 4; w++){
+					if(hs[w] < 0) continue;
+					if(rb[w] == tag && rd[w] == tag) Ph[hi[w]] = __longlong_as_double(((long long)rc[w] << 32) | (long long)ra[w]);
+					else Ph[hi[w]] = llWait(mine + hs[w], tag);
+				}
+				for(int i = threadIdx.x + 4*(int)blockDim.x; i < nHalo; i += blockDim.x){
 					int slot, hidx;
 					haloNode(i, c, slot, hidx);
 					Ph[hidx] = llWait(mine + slot, tag);
 				}
 			}
 			__syncthreads();
+			if(pfg){ long long t = clock64(); pfg[2*13] += t - tg0; pfg[2*13+1] += 1; tg0 = t; }
 			const bool send = h + 1 < 2*nCycles;
 			const unsigned stag = seq + (unsigned)h + 1u;
+			if(rowLanes){
+				// rows of the block across the lanes (hx <= 32 own-colour nodes per row, 32/hx rows per warp and trip): one
+				// divmod per trip instead of two per node, the face tests on k and l are uniform per row, rho is read coalesced.
+				// Four trips at a time: their rho and neighbour loads are in flight together, then the stores and sends.
+				const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+				const int m = lane & (hx - 1), sub = lane >> hxShift, rpt = 32 >> hxShift;       // rows per trip
+				const int nTrips = (by*bz + rpt - 1) >> (5 - hxShift);
+				for(int t0 = warp; t0 < nTrips; t0 += 4*nWarps){
+					double vn[4]; int id[4], jj[4], kk[4], lq[4];
+					#pragma unroll
+					for(int u = 0; u < 4; u++){
+						const int row = (t0 + u*nWarps)*rpt + sub;
+						id[u] = 0;
+						if(t0 + u*nWarps >= nTrips || row >= by*bz) continue;
+						int k, l; dBy.divmod(row, l, k); k += 1; l += 1;
+						const int j = ((((1+k+l)&1) == parity) ? 1 : 2) + 2*m;
+						const int idx = j + ex*(k + ey*l);
+						const double rho = B.offRho >= 0 ? Rh[(j-1) + bx*((k-1) + by*(l-1))] : ldg2(L.rho + ix(ox+j, oy+k, oz+l, L.s0, L.s1));
+						const double *q = Ph + idx;
+						const double a = q[1], b2 = q[-1], c2 = q[ex], d = q[-ex], e = q[pl], f = q[-pl];
+						vn[u] = coeff*(a + b2 + c2 + d + e + f + rho);
+						id[u] = idx; jj[u] = j; kk[u] = k; lq[u] = l;
+					}
+					#pragma unroll
+					for(int u = 0; u < 4; u++){
+						if(!id[u]) continue;
+						Ph[id[u]] = vn[u];
+						if(send) sendNode(jj[u], kk[u], lq[u], vn[u], stag);
+					}
+				}
+			} else
 			// two nodes per trip: all loads before the stores (own-colour stores never alias other-colour loads)
 			for(int i = threadIdx.x; i < items; i += 2*blockDim.x){
 				double vn[2]; int id[2], jj[2], kk[2], lq[2]; bool ok[2];
@@ -888,6 +941,7 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 					if(send) sendNode(jj[w], kk[w], lq[w], vn[w], stag);
 				}
 			}
+			if(pfg){ pfg[2*14] += clock64() - tg0; pfg[2*14+1] += 1; }
 		}
 		__syncthreads();
 		for(int i = threadIdx.x; i < bx*by*bz; i += blockDim.x){
@@ -1272,6 +1326,8 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 			BLvl &B = P.B[q];
 			if(!planBlocks(r->tsize[0], r->tsize[1], r->tsize[2], grid-1, smemCap, B)) continue;
 			if(B.bx > 1000 || B.by > 1000 || B.bz > 1000){ B.on = 0; continue; }        // packed node coordinates in bGS
+			static const bool noRows = getenv("PINC_B200_MG_ROWS") && atoi(getenv("PINC_B200_MG_ROWS")) == 0;
+			B.rows = noRows ? 0 : 1;
 			static const bool noFast = getenv("PINC_B200_MG_FAST") && atoi(getenv("PINC_B200_MG_FAST")) == 0;
 			if(noFast || (B.bx/2)*B.by*B.bz > 2*MG_BLOCK || B.by*B.bz + B.bx*B.bz + B.bx*B.by > MG_BLOCK) B.on = 2;      // 1: fast path of bGS
 			mailOff[q] = mailSlots;
@@ -1444,9 +1500,176 @@ static void opsSolve(Ctx *c, funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, 
 	}
 }
 
+// =================================================================================================
+// multi-rank solves by replication
+// =================================================================================================
+// The distributed solve is bound by ~180 cross-GPU round trips per V-cycle (6.9 us each over NVLink against 1.5 us for a
+// half-sweep inside one GPU) and the grids are tiny, so for every multi-rank configuration that fits one GPU it is faster
+// to NOT distribute it: every rank gathers rho and all levels of phi of all ranks (one grouped exchange of a few MB over
+// NVLink), solves the GLOBAL problem redundantly with the single-GPU persistent kernel, and copies its own sub-domain of
+// every level (ghost layers included) back into the rank-local grids, which are left exactly as the distributed
+// algorithm leaves them (same arithmetic per node; only gBnd's and the norm's sums are taken in another order).
+struct GlobalMg {
+	Grid *rho = nullptr, *phi = nullptr;
+	MultigridSolver *solver = nullptr;
+	double *d_pack = nullptr;
+	long seg = 0;                   // doubles per rank in d_pack: rho(0) then phi(0..L-1), true nodes, x fastest
+	int nLevels = 0, t[3] = {0,0,0}, ns[3] = {0,0,0};
+};
+__global__ void k_rep_pack(const double *__restrict__ g, int s0, int s1, int t0, int t1, int t2, double *__restrict__ seg){
+	long nt = (long)t0*t1*t2, st = (long)gridDim.x*blockDim.x;
+	for(long i = blockIdx.x*(long)blockDim.x + threadIdx.x; i < nt; i += st){ int j,k,l; truePoint(i,t0,t1,j,k,l); seg[i] = g[ix(j,k,l,s0,s1)]; }
+}
+// global true node <- the owning rank's segment
+__global__ void k_rep_unpack(double *__restrict__ G, int S0, int S1, const double *__restrict__ pack, long segStride, long segOff,
+		int t0, int t1, int t2, int nsx, int nsy, int nsz){
+	int T0 = t0*nsx, T1 = t1*nsy; long nT = (long)T0*T1*t2*nsz, st = (long)gridDim.x*blockDim.x;
+	for(long i = blockIdx.x*(long)blockDim.x + threadIdx.x; i < nT; i += st){
+		int J,K,Lz; truePoint(i,T0,T1,J,K,Lz);
+		int bx = (J-1)/t0, by = (K-1)/t1, bz = (Lz-1)/t2;
+		int j = (J-1) - bx*t0, k = (K-1) - by*t1, l = (Lz-1) - bz*t2;
+		long r = bx + (long)nsx*(by + (long)nsy*bz);
+		G[ix(J,K,Lz,S0,S1)] = pack[r*segStride + segOff + j + (long)t0*(k + (long)t1*l)];
+	}
+}
+// rank-local grid, ghost layers included <- the global grid at the periodic image of (offset + local index)
+__global__ void k_rep_extract(double *__restrict__ g, int s0, int s1, int s2, const double *__restrict__ G, int S0, int S1, int T0, int T1, int T2,
+		int ox, int oy, int oz){
+	long n = (long)s0*s1*s2, st = (long)gridDim.x*blockDim.x;
+	for(long i = blockIdx.x*(long)blockDim.x + threadIdx.x; i < n; i += st){
+		int j = (int)(i % s0); long r = i / s0; int k = (int)(r % s1); int l = (int)(r / s1);
+		int J = ox + j, K = oy + k, Lz = oz + l;
+		J = J < 1 ? J + T0 : (J > T0 ? J - T0 : J); K = K < 1 ? K + T1 : (K > T1 ? K - T1 : K); Lz = Lz < 1 ? Lz + T2 : (Lz > T2 ? Lz - T2 : Lz);
+		g[i] = G[ix(J,K,Lz,S0,S1)];
+	}
+}
+static void freeGlobalMg(GlobalMg *G){
+	if(!G) return;
+	if(G->d_pack) cudaFree(G->d_pack);
+	if(G->solver) mgFreeSolver(G->solver);
+	if(G->rho) pincGridFree(G->rho);
+	if(G->phi) pincGridFree(G->phi);
+	delete G;
+}
+static bool replicaEligible(Ctx *c, Multigrid *mgRho, const MpiInfo *m){
+	static const bool off = getenv("PINC_B200_MG_REPLICA") && atoi(getenv("PINC_B200_MG_REPLICA")) == 0;
+	if(off || mgMode() != 2 || m->mpiSize < 2 || !c->tp) return false;
+	int nL = mgRho->nLevels;
+	if(nL < 2 || nL > MG_MAXLEV) return false;
+	long nGlobal = 1;
+	for(int q = 0; q < nL; q++){
+		const Grid *g = mgRho->grids[q];
+		if(g->rank != 4 || g->size[0] != 1) return false;
+		for(int d = 1; d < 4; d++){
+			if(g->trueSize[d] < 1 || g->nGhostLayers[d] != 1 || g->nGhostLayers[d+g->rank] != 1) return false;
+			if(g->bnd[d] != PERIODIC || g->bnd[d+g->rank] != PERIODIC) return false;
+			if(((long)g->trueSize[d]*m->nSubdomains[d-1]) & 1) return false;
+			if(q == 0) nGlobal *= (long)g->trueSize[d]*m->nSubdomains[d-1];
+		}
+	}
+	return nGlobal <= (1L << 24);          // 16 M nodes = 128 MB per array: far below what one GPU holds, and still L2-friendly
+}
+static void solveSingle(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, double tol, int maxCycles);
+static void replicaSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *m, double tol, int maxCycles){
+	const int nL = mgRho->nLevels, R = m->mpiSize, me = m->mpiRank;
+	const Grid *g0 = mgRho->grids[0];
+	GlobalMg *G = nullptr;
+	auto it = c->mgGlobal.find(mgRho);
+	if(it != c->mgGlobal.end()){
+		G = (GlobalMg*)it->second;
+		bool same = G->nLevels == nL;
+		for(int d = 0; d < 3; d++) same = same && G->t[d] == g0->trueSize[d+1] && G->ns[d] == m->nSubdomains[d];
+		if(!same){ c->mgGlobal.erase(it); freeGlobalMg(G); G = nullptr; }
+	}
+	if(!G){
+		G = new GlobalMg();
+		G->nLevels = nL;
+		int ts[3], gl[6] = {1,1,1,1,1,1}, bnd[6] = {PERIODIC,PERIODIC,PERIODIC,PERIODIC,PERIODIC,PERIODIC};
+		for(int d = 0; d < 3; d++){ G->t[d] = g0->trueSize[d+1]; G->ns[d] = m->nSubdomains[d]; ts[d] = G->t[d]*G->ns[d]; }
+		G->rho = pincGridAlloc(3, ts, gl, 1, bnd);
+		G->phi = pincGridAlloc(3, ts, gl, 1, bnd);
+		G->solver = pincMgAllocSolver(G->rho, G->phi, nL, mgRho->nMGCycles, mgRho->nPreSmooth, mgRho->nPostSmooth, mgRho->nCoarseSolve);
+		long seg = trueCount(devGrid(c, mgRho->grids[0]));
+		for(int q = 0; q < nL; q++) seg += trueCount(devGrid(c, mgPhi->grids[q]));
+		G->seg = seg;
+		PINC_CUDA(cudaMalloc(&G->d_pack, (size_t)seg*R*sizeof(double)));
+		c->mgGlobal[mgRho] = G;
+	}
+	Multigrid *gRho = G->solver->mgRho, *gPhi = G->solver->mgPhi, *gRes = G->solver->mgRes;
+	// 1. pack my true nodes: rho(0), phi(0..L-1)
+	double *mine = G->d_pack + (long)me*G->seg;
+	long off = 0;
+	std::vector<long> segOff(nL + 1);
+	for(int q = -1; q < nL; q++){
+		DevGrid *g = devGrid(c, q < 0 ? mgRho->grids[0] : mgPhi->grids[q]);
+		long nt = trueCount(g);
+		segOff[q+1] = off;
+		PINC_LAUNCH(c, K_GRIDOP, 16.0*nt, (k_rep_pack<<<tGrid(c,nt),256,0,c->stream>>>(g->d, g->size[0], g->size[1], g->tsize[0], g->tsize[1], g->tsize[2], mine + off)));
+		off += nt;
+	}
+	// 2. everybody's segment to everybody
+	std::vector<Msg> sends, recvs;
+	for(int r = 0; r < R; r++){
+		if(r == me) continue;
+		sends.push_back(Msg{ r, 7100, (void*)mine, (size_t)G->seg*sizeof(double) });
+		recvs.push_back(Msg{ r, 7100, (void*)(G->d_pack + (long)r*G->seg), (size_t)G->seg*sizeof(double) });
+	}
+	c->tp->exchange(c, sends, recvs);
+	// 3. assemble the global rho(0) and phi(q)
+	for(int q = -1; q < nL; q++){
+		DevGrid *loc = devGrid(c, q < 0 ? mgRho->grids[0] : mgPhi->grids[q]);
+		DevGrid *glo = devGrid(c, q < 0 ? gRho->grids[0] : gPhi->grids[q]);
+		long nT = trueCount(glo);
+		PINC_LAUNCH(c, K_GRIDOP, 16.0*nT, (k_rep_unpack<<<tGrid(c,nT),256,0,c->stream>>>(glo->d, glo->size[0], glo->size[1], G->d_pack, G->seg, segOff[q+1],
+			loc->tsize[0], loc->tsize[1], loc->tsize[2], G->ns[0], G->ns[1], G->ns[2])));
+	}
+	// 4. the global problem, redundantly on every rank
+	solveSingle(c, gRho, gPhi, gRes, tol, maxCycles);
+	const int path = c->mgLastPath + 4;
+	// 5. my sub-domain of every level of phi, rho and res, ghost layers included
+	for(int q = 0; q < nL; q++){
+		Multigrid *locs[3] = {mgPhi, mgRho, mgRes}, *glos[3] = {gPhi, gRho, gRes};
+		for(int a = 0; a < 3; a++){
+			DevGrid *loc = devGrid(c, locs[a]->grids[q]), *glo = devGrid(c, glos[a]->grids[q]);
+			PINC_LAUNCH(c, K_GRIDOP, 16.0*loc->n, (k_rep_extract<<<tGrid(c,loc->n),256,0,c->stream>>>(loc->d, loc->size[0], loc->size[1], loc->size[2],
+				glo->d, glo->size[0], glo->size[1], glo->tsize[0], glo->tsize[1], glo->tsize[2],
+				m->subdomain[0]*loc->tsize[0], m->subdomain[1]*loc->tsize[1], m->subdomain[2]*loc->tsize[2])));
+		}
+	}
+	c->mgLastPath = path;
+}
+
+// which single-GPU kernel runs a periodic solve (the caller has checked fusedEligible's shape conditions)
+static void solveSingle(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, double tol, int maxCycles){
+	// the cluster kernel runs on 16 SMs: it wins while the finest level is small enough to be latency-bound
+	// (measured: 32^3 304 vs 526 us per V-cycle, 64^3 908 vs 805); larger grids go to the all-SM kernel
+	const Grid *g0 = mgRho->grids[0];
+	long nt0 = (long)g0->trueSize[1]*g0->trueSize[2]*g0->trueSize[3];
+	// ... unless its small levels are the cubic 16/8/4 pyramid, which the all-SM kernel runs through specialised
+	// routines (measured us per V-cycle, all-SM vs cluster: 16^3 65 vs 123, 32^3 148 vs 288)
+	bool pyramid = g_mgMode == 2;
+	for(int q = 0; q < mgRho->nLevels; q++){
+		const Grid *g = mgRho->grids[q];
+		long nt = (long)g->trueSize[1]*g->trueSize[2]*g->trueSize[3];
+		if(nt > MG_SMALL) continue;
+		int n = g->trueSize[1];
+		if(g->trueSize[2] != n || g->trueSize[3] != n || (n != 16 && n != 8 && n != 4) || (n == 4 && q != mgRho->nLevels-1)) pyramid = false;
+	}
+	bool preferCluster = (g_mgMode == 3 || g_mgForceCluster || (nt0 <= 65536 && !pyramid)) && !g_mgNoCluster;
+	if(g_mgMode >= 2 && preferCluster && clusterSolve(c, mgRho, mgPhi, mgRes, tol, maxCycles, g_mgMode == 3)){ c->mgLastPath = 2; return; }
+	fusedSolve(c, mgRho, mgPhi, mgRes, tol, maxCycles, g_mgMode == 1 || g_mgMode == 3);
+	c->mgLastPath = 1;
+}
+
 void mgForgetPlans(Ctx *c){
 	for(auto &kv : c->cycleGraphs) if(kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
 	c->cycleGraphs.clear();
+	if(c->mgGlobalBusy) return;                      // freeing a replica's own grids comes back here
+	c->mgGlobalBusy = true;
+	std::unordered_map<const void*, void*> gone;
+	gone.swap(c->mgGlobal);
+	for(auto &kv : gone) freeGlobalMg((GlobalMg*)kv.second);
+	c->mgGlobalBusy = false;
 }
 
 } // namespace pinc
@@ -1489,25 +1712,9 @@ void mgSolveRaw(funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 	Ctx *c = cur();
 	const double tol = 1.E-10;                       // src/multigrid.c:1695
 	const int maxCycles = 200;                       // the reference has no bound; this one reports instead of hanging
-	if(fusedEligible(c, mgRho, mgPhi, mgRes, mpiInfo)){
-		// the cluster kernel runs on 16 SMs: it wins while the finest level is small enough to be latency-bound
-		// (measured: 32^3 304 vs 526 us per V-cycle, 64^3 908 vs 805); larger grids go to the all-SM kernel
-		const Grid *g0 = mgRho->grids[0];
-		long nt0 = (long)g0->trueSize[1]*g0->trueSize[2]*g0->trueSize[3];
-		// ... unless its small levels are the cubic 16/8/4 pyramid, which the all-SM kernel runs through specialised
-		// routines (measured us per V-cycle, all-SM vs cluster: 16^3 65 vs 123, 32^3 148 vs 288)
-		bool pyramid = g_mgMode == 2;
-		for(int q = 0; q < mgRho->nLevels; q++){
-			const Grid *g = mgRho->grids[q];
-			long nt = (long)g->trueSize[1]*g->trueSize[2]*g->trueSize[3];
-			if(nt > MG_SMALL) continue;
-			int n = g->trueSize[1];
-			if(g->trueSize[2] != n || g->trueSize[3] != n || (n != 16 && n != 8 && n != 4) || (n == 4 && q != mgRho->nLevels-1)) pyramid = false;
-		}
-		bool preferCluster = (g_mgMode == 3 || g_mgForceCluster || (nt0 <= 65536 && !pyramid)) && !g_mgNoCluster;
-		if(g_mgMode >= 2 && preferCluster && clusterSolve(c, mgRho, mgPhi, mgRes, tol, maxCycles, g_mgMode == 3)) return;
-		fusedSolve(c, mgRho, mgPhi, mgRes, tol, maxCycles, g_mgMode == 1 || g_mgMode == 3);
-	} else opsSolve(c, mgAlgo, mgRho, mgPhi, mgRes, mpiInfo, tol, maxCycles);
+	if(fusedEligible(c, mgRho, mgPhi, mgRes, mpiInfo)) pinc::solveSingle(c, mgRho, mgPhi, mgRes, tol, maxCycles);
+	else if(pinc::replicaEligible(c, mgRho, mpiInfo)) pinc::replicaSolve(c, mgRho, mgPhi, mgRes, mpiInfo, tol, maxCycles);
+	else { opsSolve(c, mgAlgo, mgRho, mgPhi, mgRes, mpiInfo, tol, maxCycles); c->mgLastPath = 0; }
 }
 
 void mgSolve(const MultigridSolver *solver, const Grid *rho, const Grid *phi, const MpiInfo *mpiInfo){
@@ -1523,6 +1730,7 @@ void mgSolver(void (**solve)(), MultigridSolver *(**solverAlloc)(), void (**solv
 
 void pincMgSetMode(int mode){ pinc::g_mgForceCluster = mode == 4; pinc::g_mgNoCluster = mode == 5; if(mode == 4 || mode == 5) mode = 2; pinc::g_mgMode = mode < 0 ? 0 : (mode > 3 ? 3 : mode); }
 
+int pincMgLastPath(void){ return cur()->mgLastPath; }
 int pincMgLastHistory(double *barRes, int cap){
 	Ctx *c = cur();
 	if(c->mgHistPending){

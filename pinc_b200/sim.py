@@ -291,5 +291,12 @@ class World:
         self._on(r, get)
         return out["h"]
 
+    def mg_path(self, r=None):
+        """pincMgLastPath of rank r: 0 distributed ops, 1 all-SM kernel, 2 cluster kernel, +4 replicated global solve."""
+        r = self.local[0] if r is None else r
+        out = {}
+        self._on(r, lambda: out.__setitem__("p", self.lib.pincMgLastPath()))
+        return out["p"]
+
     def sync(self):
         self.run(lambda r, st: self.lib.pincDeviceSynchronize())

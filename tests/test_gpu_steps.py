@@ -67,6 +67,7 @@ def test_cold_langmuir_four_subdomains():
             assert abs(kw - ko) <= 1e-10 * abs(ko) and abs(pw - po) <= 1e-10 * abs(po)
             pe.append(pw)
         assert max(pe) > 0
+        assert W.mg_path(0) >= 4          # the multi-rank solve ran replicated (global problem on every rank)
     finally:
         W.close()
 
