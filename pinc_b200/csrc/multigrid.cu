@@ -1326,6 +1326,8 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 			BLvl &B = P.B[q];
 			if(!planBlocks(r->tsize[0], r->tsize[1], r->tsize[2], grid-1, smemCap, B)) continue;
 			if(B.bx > 1000 || B.by > 1000 || B.bz > 1000){ B.on = 0; continue; }        // packed node coordinates in bGS
+			{ static const int maxItems = getenv("PINC_B200_MG_MAXITEMS") ? atoi(getenv("PINC_B200_MG_MAXITEMS")) : 1024;     // bigger blocks are throughput-bound and the grid-wide sweep (fGS) is as fast or faster (us per V-cycle, fGS vs blocks: 64x64x128 532 vs 532, 64x128x128 736 vs 820, 128^3 1122 vs 1367)
+			  if((B.bx/2)*B.by*B.bz > maxItems){ B.on = 0; continue; } }
 			static const bool noRows = getenv("PINC_B200_MG_ROWS") && atoi(getenv("PINC_B200_MG_ROWS")) == 0;
 			B.rows = noRows ? 0 : 1;
 			static const bool noFast = getenv("PINC_B200_MG_FAST") && atoi(getenv("PINC_B200_MG_FAST")) == 0;

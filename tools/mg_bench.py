@@ -22,15 +22,17 @@ MODES = {0: "ops", 1: "fused-exact", 2: "auto", 3: "auto-exact", 4: "cluster-alw
 
 def main():
     L = plib.load()
-    sizes = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "16,32,64".split(","))]
+    # sizes: N (cube) or AxBxC
+    sizes = [x for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "16,32,64".split(","))]
     kind = sys.argv[2] if len(sys.argv) > 2 else "sin"
     modes = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1, 2, 3]
     out = []
-    for N in sizes:
-        true = (N, N, N)
-        levels = int(np.log2(N)) - 1
+    for spec in sizes:
+        true = tuple(int(v) for v in spec.split("x")) if "x" in spec else (int(spec),) * 3
+        N = true[0]
+        levels = int(np.log2(min(true))) - 1
         for mode in modes:
-            if mode == 0 and N > 64:
+            if mode == 0 and max(true) > 64:
                 continue
             L.pincMgSetMode(mode)
             rho, phi = GridH(L, true, 1), GridH(L, true, 1)
@@ -65,7 +67,7 @@ def main():
             if sol is not None:
                 p = phi.down()[1:-1, 1:-1, 1:-1, 0]
                 err = float(np.sqrt(np.mean((p - sol[1:-1, 1:-1, 1:-1]) ** 2)))
-            rec = {"N": N, "levels": levels, "mode": MODES[mode], "rho": kind, "vcycles": ncyc, "barRes_last": last,
+            rec = {"N": spec, "levels": levels, "mode": MODES[mode], "rho": kind, "vcycles": ncyc, "barRes_last": last,
                    "ms_per_solve": min(times), "us_per_vcycle": 1e3 * min(times) / max(ncyc, 1), "rms_error_vs_analytic": err}
             if os.environ.get("PINC_B200_MGPROF"):
                 buf = (C.c_longlong * 64)()
