@@ -228,8 +228,10 @@ int pincMgLastPath(void);
  *   3 cluster-exact  the cluster kernel with gBnd after every half-sweep;
  *   4 cluster-always as 2, but the cluster kernel is used whenever the levels fit its shared memory;
  *   5 allsm          as 2, but always the all-SM kernel.
- * Multi-rank solves: 2 = smoother and ghost fills over NVLink peer memory, V-cycle replayed as a CUDA graph;
- * 0/1/3 = one kernel and one exchange per reference call.
+ * Multi-rank solves: 2 = replicated (every rank gathers rho and phi of all ranks in one exchange, solves the global problem
+ * with the single-GPU kernel and keeps its sub-domain; global grids of <= 16 M nodes), else and with
+ * $PINC_B200_MG_REPLICA=0 distributed with smoother and ghost fills over NVLink peer memory and the V-cycle replayed as a
+ * CUDA graph; 0/1/3 = distributed, one kernel and one exchange per reference call.
  * $PINC_B200_MG = ops | fused | cluster | cluster-exact | cluster-always | allsm selects the start-up value. */
 void pincMgSetMode(int mode);
 

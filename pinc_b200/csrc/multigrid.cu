@@ -5,7 +5,9 @@
 // Two execution modes with the SAME per-point arithmetic (the device functions below):
 //
 //  ops    one kernel per reference call, ghost layers kept current by gHaloOp/gBnd exactly as the
-//         reference does.  Used for the individual entry points and whenever the solve spans several ranks.
+//         reference does.  Used for the individual entry points and for distributed multi-rank solves (the fallback:
+//         by default a multi-rank solve is REPLICATED - every rank gathers rho/phi and runs the fused kernel on the
+//         global problem, replicaSolve below).
 //  fused  single-rank periodic solves: ONE persistent cooperative kernel (k_mg_solve) runs the whole tolerance loop.
 //         Ghost layers are not touched inside (neighbours are read at the periodic image of the true node, which is
 //         bit-identical to reading a ghost that setSlice just filled) and are filled once at the end, so the arrays are

@@ -5,6 +5,10 @@ driven through the PINC entry points against the oracle on identical seeded inpu
   * rho, phi, E, particle phase space: <= 1e-10 relative (north_star), in practice ~1e-13;
   * residual norm per V-cycle: 1e-6 relative above the rounding floor;
   * run-to-run: rho, phi, E bit-identical (deterministic deposition)."""
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 
@@ -67,9 +71,21 @@ def test_cold_langmuir_four_subdomains():
             assert abs(kw - ko) <= 1e-10 * abs(ko) and abs(pw - po) <= 1e-10 * abs(po)
             pe.append(pw)
         assert max(pe) > 0
-        assert W.mg_path(0) >= 4          # the multi-rank solve ran replicated (global problem on every rank)
+        if os.environ.get("PINC_B200_MG_REPLICA") == "0":
+            assert W.mg_path(0) == 0      # distributed: one kernel and one exchange per reference call
+        else:
+            assert W.mg_path(0) >= 4      # the multi-rank solve ran replicated (global problem on every rank)
     finally:
         W.close()
+
+
+def test_cold_langmuir_four_subdomains_distributed_solve():
+    """The same scenario with the multigrid solve distributed over the ranks (the fallback of the replicated solve):
+    $PINC_B200_MG_REPLICA is read once per process, hence the subprocess."""
+    env = dict(os.environ, PINC_B200_MG_REPLICA="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", __file__ + "::test_cold_langmuir_four_subdomains"],
+                       capture_output=True, text=True, env=env, timeout=600, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "1 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def warm_small():
