@@ -672,6 +672,12 @@ __device__ __forceinline__ void llStore(uint4 *p, double v, unsigned tag){
 	unsigned lo = (unsigned)__double_as_longlong(v), hi = (unsigned)(__double_as_longlong(v) >> 32);
 	asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
 }
+__device__ __forceinline__ bool llTry(const uint4 *p, unsigned tag, double &v){
+	unsigned a, b, c, d;
+	asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+	v = __longlong_as_double(((long long)c << 32) | (long long)a);
+	return b == tag && d == tag;
+}
 __device__ __forceinline__ double llWait(const uint4 *p, unsigned tag){
 	unsigned a, b, c, d, spins = 0;
 	for(;;){
@@ -787,8 +793,6 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 				mgS[B.offRho + i] = ldg2(L.rho + ix(ox+jl+1, oy+kl+1, oz+ll+1, L.s0, L.s1));
 			}
 		const double coeff = 1./6.;
-		int hxShift = 0; while((1 << hxShift) < hx) hxShift++;
-		const bool rowLanes = B.rows && hx >= 1 && hx <= 32 && (1 << hxShift) == hx;
 		// halo node i (0 <= i < nHalo) of colour c: mailbox slot and index into the block array
 		auto haloNode = [&](int i, int c, int &slot, int &hidx){
 			int f, w, j, k, l;
@@ -857,70 +861,19 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 		} else
 		for(int h = 0; h < 2*nCycles; h++){
 			const int parity = (h & 1) ? 0 : 1;
-			long long *pfg = (S.K->prof && bid == 0 && threadIdx.x == 0) ? S.K->prof : nullptr;
-			long long tg0 = pfg ? clock64() : 0;
 			if(h > 0){
 				// receive the other colour's face nodes of half-sweep h-1
 				const unsigned tag = seq + (unsigned)h;
 				const int c = 1 - parity;
-				// a thread's (up to four) slots are read together, only the ones that have not arrived yet are polled again
-				int hs[4], hi[4]; unsigned ra[4], rb[4], rc[4], rd[4];
-				#pragma unroll
-				for(int w = 0; w < 4; w++){
-					int i = threadIdx.x + w*(int)blockDim.x;
-					hs[w] = -1;
-					if(i < nHalo){
-						haloNode(i, c, hs[w], hi[w]);
-						asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ra[w]), "=r"(rb[w]), "=r"(rc[w]), "=r"(rd[w]) : "l"(mine + hs[w]) : "memory");
-					}
-				}
-				#pragma unroll
-				for(int w = 0; w < 4; w++){
-					if(hs[w] < 0) continue;
-					if(rb[w] == tag && rd[w] == tag) Ph[hi[w]] = __longlong_as_double(((long long)rc[w] << 32) | (long long)ra[w]);
-					else Ph[hi[w]] = llWait(mine + hs[w], tag);
-				}
-				for(int i = threadIdx.x + 4*(int)blockDim.x; i < nHalo; i += blockDim.x){
+				for(int i = threadIdx.x; i < nHalo; i += blockDim.x){
 					int slot, hidx;
 					haloNode(i, c, slot, hidx);
 					Ph[hidx] = llWait(mine + slot, tag);
 				}
 			}
 			__syncthreads();
-			if(pfg){ long long t = clock64(); pfg[2*13] += t - tg0; pfg[2*13+1] += 1; tg0 = t; }
 			const bool send = h + 1 < 2*nCycles;
 			const unsigned stag = seq + (unsigned)h + 1u;
-			if(rowLanes){
-				// rows of the block across the lanes (hx <= 32 own-colour nodes per row, 32/hx rows per warp and trip): one
-				// divmod per trip instead of two per node, the face tests on k and l are uniform per row, rho is read coalesced.
-				// Four trips at a time: their rho and neighbour loads are in flight together, then the stores and sends.
-				const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
-				const int m = lane & (hx - 1), sub = lane >> hxShift, rpt = 32 >> hxShift;       // rows per trip
-				const int nTrips = (by*bz + rpt - 1) >> (5 - hxShift);
-				for(int t0 = warp; t0 < nTrips; t0 += 4*nWarps){
-					double vn[4]; int id[4], jj[4], kk[4], lq[4];
-					#pragma unroll
-					for(int u = 0; u < 4; u++){
-						const int row = (t0 + u*nWarps)*rpt + sub;
-						id[u] = 0;
-						if(t0 + u*nWarps >= nTrips || row >= by*bz) continue;
-						int k, l; dBy.divmod(row, l, k); k += 1; l += 1;
-						const int j = ((((1+k+l)&1) == parity) ? 1 : 2) + 2*m;
-						const int idx = j + ex*(k + ey*l);
-						const double rho = B.offRho >= 0 ? Rh[(j-1) + bx*((k-1) + by*(l-1))] : ldg2(L.rho + ix(ox+j, oy+k, oz+l, L.s0, L.s1));
-						const double *q = Ph + idx;
-						const double a = q[1], b2 = q[-1], c2 = q[ex], d = q[-ex], e = q[pl], f = q[-pl];
-						vn[u] = coeff*(a + b2 + c2 + d + e + f + rho);
-						id[u] = idx; jj[u] = j; kk[u] = k; lq[u] = l;
-					}
-					#pragma unroll
-					for(int u = 0; u < 4; u++){
-						if(!id[u]) continue;
-						Ph[id[u]] = vn[u];
-						if(send) sendNode(jj[u], kk[u], lq[u], vn[u], stag);
-					}
-				}
-			} else
 			// two nodes per trip: all loads before the stores (own-colour stores never alias other-colour loads)
 			for(int i = threadIdx.x; i < items; i += 2*blockDim.x){
 				double vn[2]; int id[2], jj[2], kk[2], lq[2]; bool ok[2];
@@ -943,7 +896,6 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 					if(send) sendNode(jj[w], kk[w], lq[w], vn[w], stag);
 				}
 			}
-			if(pfg){ pfg[2*14] += clock64() - tg0; pfg[2*14+1] += 1; }
 		}
 		__syncthreads();
 		for(int i = threadIdx.x; i < bx*by*bz; i += blockDim.x){
