@@ -1072,7 +1072,9 @@ __device__ __noinline__ void smallPyramid(const MgPlan &P, CK &K){
 	}
 }
 
-__global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
+// EXACT (gBnd after every half-sweep, modes 1 and 3) is a compile-time parameter only to keep the code of the default
+// kernel small: the persistent kernel is latency-bound and sensitive to its instruction footprint
+template<bool EXACT> __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
 	__shared__ double sh[18];
 	__shared__ double red[40];
 	CK K{ cg::this_cluster(), (int)blockIdx.x, 1, mgS, red, 0, P.prof, P.offZ };
@@ -1104,7 +1106,7 @@ __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
 				ProfScope pss(K, PS_LEVEL0);
 				if(P.pyramid) smallPyramid(P, K);
 				else if(P.smemSmall){
-					if(P.exact) smallSection<true>(P, K); else smallSection<false>(P, K);
+					smallSection<EXACT>(P, K);
 				} else {
 					for(int q = qs; q < b; q++) fDown(P, q, S1, seq);
 					fBottom(P, S1);
@@ -1303,9 +1305,11 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 		}
 	}
 	{	// one high-water mark for the kernel's dynamic shared memory
-		static size_t attrSet = 0;
+		static size_t attrSetBoth[2] = {0, 0};
+		size_t &attrSet = attrSetBoth[exact ? 1 : 0];
+		const void *kern = exact ? (const void*)k_mg_solve<true> : (const void*)k_mg_solve<false>;
 		if(smem > attrSet){
-			if(cudaFuncSetAttribute((const void*)k_mg_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) attrSet = smem;
+			if(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) attrSet = smem;
 			else { cudaGetLastError(); for(int q = 0; q < nL; q++) P.B[q].on = 0; P.smemSmall = 0; P.pyramid = 0; smem = 0; }
 		}
 	}
@@ -1319,7 +1323,7 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 	void *args[] = { &P };
 	{
 		LaunchScope ls(c, K_MGFUSED, work);
-		PINC_CUDA(cudaLaunchCooperativeKernel((void*)k_mg_solve, dim3(grid), dim3(MG_BLOCK), args, smem, c->stream));
+		PINC_CUDA(cudaLaunchCooperativeKernel(exact ? (void*)k_mg_solve<true> : (void*)k_mg_solve<false>, dim3(grid), dim3(MG_BLOCK), args, smem, c->stream));
 	}
 	PINC_CUDA(cudaMemcpyAsync(c->h_mgHist, c->d_mgHist, 256*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	c->mgHistPending = true;
