@@ -154,16 +154,34 @@ def run_ours(args, n_gpus, rank, world_size):
     torch.cuda.set_device(local_rank)
     dist = None
     nccl_id = None
+    parity = None
     if world_size > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         L = plib.load()
-        buf = C.create_string_buffer(128)
-        if rank == 0:
-            L.pincNcclUniqueId(buf)
-        t = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
-        dist.broadcast(t, 0)
-        nccl_id = bytes(t.cpu().tolist())
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import multi_check
+        if not args.no_parity:
+            # the NCCL path against the oracle BEFORE anything is timed (small seeded configs, every rank checks its own
+            # sub-domain against the oracle's run of the whole world): warm + cold, replicated + distributed solve
+            parity = {"tolerance": 1e-10, "cases": []}
+            for kind in ("warm", "cold"):
+                for replica in (1, 0):
+                    r = multi_check.check(rank, world_size, kind, steps=4, replica=replica)
+                    t = torch.tensor([r["worst_field_err"], r["worst_particle_err"], 0.0 if r["tables_exact"] else 1.0,
+                                      0.0 if r["cycles_equal"] else 1.0, 0.0 if r["sizes_exact"] else 1.0],
+                                     dtype=torch.float64, device="cuda")
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    v = t.tolist()
+                    parity["cases"].append({"config": f"{kind}, 16x8x8 cells per rank, {multi_check.SUB[world_size]}, 4 steps",
+                                            "solve": "replicated" if replica else "distributed (peer-memory smoother)",
+                                            "mg_path": r["mg_path"], "transport": r["transport"], "vcycles_last": r["vcycles_last"],
+                                            "worst_field_err": v[0], "worst_particle_err": v[1], "tables_exact": v[2] == 0.0,
+                                            "cycles_equal": v[3] == 0.0, "sizes_exact": v[4] == 0.0})
+            parity["ok"] = all(c["worst_field_err"] <= 1e-10 and c["worst_particle_err"] <= 1e-10 and c["tables_exact"]
+                               and c["cycles_equal"] and c["sizes_exact"] for c in parity["cases"])
+            parity["checker"] = "oracle/pinc_oracle.c (every rank runs the whole world on the CPU and compares its sub-domain)"
+        nccl_id = multi_check.fresh_nccl_id(L, rank)
     FUSED = True if args.particle_pass == "full" else "nodeposit"
     text, cfg = load_cfg(args.workload, n_gpus, args.particles_scale)
     assert cfg.nRanks == world_size, (cfg.nSubdomains, world_size)
@@ -292,7 +310,8 @@ def run_ours(args, n_gpus, rank, world_size):
         except Exception:
             pass
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic, "peak_source": peak_src,
+                    "traffic": traffic, "traffic_source": "static: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/traffic.json), not measured in this run",
+                    "peak_source": peak_src,
                     "alg_bytes_per_launch": by / cnt, "avg_launch_ms": kms / cnt, "hbm_bound_kernels": hbm_kernels}
         if dom == "mgfused":
             # the multigrid kernel is bound by the latency of its dependent half-sweeps, not by bytes: say so
@@ -317,6 +336,8 @@ def run_ours(args, n_gpus, rank, world_size):
                                    5: "replicated: global problem on every rank, all-SM persistent kernel",
                                    6: "replicated: global problem on every rank, cluster kernel"}.get(W.mg_path(), "?")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels}
+    if parity is not None:
+        line["parity"] = parity
     W.close()
     return line
 
@@ -332,6 +353,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer job (0: the same K as --steps)")
     ap.add_argument("--cpu-sample", type=float, default=1.0, help="fraction of the 70 particles/cell used by the CPU arms")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the NCCL path that N > 1 runs ahead of the timed region")
     ap.add_argument("--particle-pass", default="nodeposit", choices=["full", "nodeposit"],
                     help="nodeposit (default, measured faster): acc+move+classify in one pass, deposit as its own kernel; "
                          "full: the deposit of the staying particles joins the pass")
@@ -340,9 +362,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         if rank == 0:
-            a = argparse.Namespace(**vars(args))
-            a.steps = min(args.steps, 3); a.warmup = min(args.warmup, 1)
-            print(json.dumps(run_reference(a, args.gpus)), flush=True)
+            print(json.dumps(run_reference(args, args.gpus)), flush=True)
         return
     assert world == args.gpus, f"--gpus {args.gpus} needs {args.gpus} ranks (torchrun); WORLD_SIZE={world}"
     if args.warmup < 3:

@@ -214,6 +214,13 @@ void mgFreeSolver(MultigridSolver *solver);                                     
 /* residual history of the most recent mgSolve on this rank: returns the V-cycle count and
  * copies up to `cap` values of barRes (multigrid.c:1700-1704), one per V-cycle. */
 int pincMgLastHistory(double *barRes, int cap);
+/* barRes of the last V-cycle of the most recent mgSolve on this rank.  The reference's tolerance loop is unbounded
+ * (multigrid.c:1697, a stalled solve hangs); here it is bounded by $PINC_B200_MG_MAXCYCLES (default 10000) and a solve
+ * that ends above 1e-10 is a fatal "PINC-B200 ERROR" raised at the first synchronisation after the solve. */
+double pincMgLastBarRes(void);
+/* multi-rank solves replicated (1, default) or distributed over the ranks (0); overrides
+ * $PINC_B200_MG_REPLICA.  Process-wide: call it on every rank before the next mgSolve. */
+void pincMgSetReplica(int on);
 /* which implementation ran the most recent mgSolve on this rank: 0 one kernel per reference call (distributed), 1 the
  * all-SM persistent kernel, 2 the cluster kernel; +4: a multi-rank solve done by replication (every rank gathers rho and
  * phi, solves the global problem with the single-GPU kernel and keeps its own sub-domain) */

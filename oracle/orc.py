@@ -36,7 +36,7 @@ class OrcSim(C.Structure):
         ("nEmigrants", C.POINTER(c_long_p)), ("nImmigrants", C.POINTER(c_long_p)),
         ("mg", C.c_void_p),
         ("kinEnergy", C.c_double * 9), ("potEnergy", C.c_double),
-        ("lastCycles", C.c_int), ("lastBarRes", C.c_double * 64),
+        ("lastCycles", C.c_int), ("lastBarRes", C.c_double * 256),
     ]
 
 
@@ -227,7 +227,7 @@ class OrcWorld:
 
     def history(self):
         n = self.sim.lastCycles
-        return [self.sim.lastBarRes[i] for i in range(min(n, 64))]
+        return [self.sim.lastBarRes[i] for i in range(min(n, 256))]
 
 
 def neighbor_alloc(spec):

@@ -540,7 +540,7 @@ void orc_field_solve(OrcSim *s){
 	long nE = 3L*s->size[0]*s->size[1]*s->size[2];
 	for(int r=0;r<R;r++) orc_distr3d1(s->pos[r],s->nSpecies,s->iStart[r],s->iStop[r],s->charge,s->rho[r],s->size);
 	orc_halo(t,s->rho,s->size,1,1,1);
-	s->lastCycles = orc_mg_solve(s->mg,s->rho,s->phi,s->res,1e-10,1000,s->lastBarRes,64);
+	s->lastCycles = orc_mg_solve(s->mg,s->rho,s->phi,s->res,1e-10,1000,s->lastBarRes,256);
 	orc_halo(t,s->phi,s->size,1,0,0);
 	for(int r=0;r<R;r++) orc_findiff1st(s->phi[r],s->E[r],s->size);
 	orc_halo(t,s->E,s->size,3,0,0);

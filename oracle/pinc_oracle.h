@@ -94,7 +94,7 @@ typedef struct {
 	OrcMg *mg;
 	double kinEnergy[9], potEnergy;
 	int lastCycles;
-	double lastBarRes[64];
+	double lastBarRes[256];
 } OrcSim;
 void orc_step(OrcSim *s);
 /* everything of a step except the trailing accelerate (used for the t=0 set-up, main.c:155-180) */

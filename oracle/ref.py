@@ -9,6 +9,7 @@ Initial conditions are injected (GSL is absent).  Grids are zeroed after allocat
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 import queue
 import tempfile
@@ -196,10 +197,30 @@ class RefWorld:
         set_slice = C.cast(lib.setSlice, C.c_void_p)
         add_slice = C.cast(lib.addSlice, C.c_void_p)
 
+        def solve(r, st):
+            if history is None:
+                lib.mgSolve(st.solver, st.rho, st.phi, st.mpi)
+                return
+            # the tolerance loop of mgSolveRaw (src/multigrid.c:1696-1705) driven call by call, so that the
+            # reference's own barRes per V-cycle (which it does not keep) can be recorded
+            sol = st.solver.contents
+            rho0, phi0, res0 = (m.contents.grids[0] for m in (sol.mgRho, sol.mgPhi, sol.mgRes))
+            bar, hist = 2.0, []
+            while bar > 1e-10:
+                lib.mgVRecursive(0, sol.mgRho.contents.nLevels - 1, 0, sol.mgRho, sol.mgPhi, sol.mgRes, st.mpi)
+                lib.mgResidual(res0, rho0, phi0, st.mpi)
+                lib.gHaloOp(set_slice, res0, st.mpi, abi.TOHALO)
+                bar = lib.mgSumTrueSquared(res0, st.mpi)
+                bar /= lib.gTotTruesize(rho0, st.mpi)
+                bar = math.sqrt(bar)
+                hist.append(bar)
+            if r == 0:
+                history[:] = hist
+
         def phase(r, st):
             lib.puDistr3D1(st.pop, st.rho)
             lib.gHaloOp(add_slice, st.rho, st.mpi, abi.FROMHALO)
-            lib.mgSolve(st.solver, st.rho, st.phi, st.mpi)
+            solve(r, st)
             lib.gHaloOp(set_slice, st.phi, st.mpi, abi.TOHALO)
             lib.gFinDiff1st(st.phi, st.E)
             lib.gHaloOp(set_slice, st.E, st.mpi, abi.TOHALO)
@@ -223,7 +244,7 @@ class RefWorld:
             lib.puMigrate(st.pop, st.mpi, st.rho)
         self.run(phase)
 
-    def step(self):
+    def step(self, history=None):
         """src/main.c:212-261 minus object calls / HDF5 (canonical driver)."""
         lib = self.lib
 
@@ -231,7 +252,7 @@ class RefWorld:
             lib.puMove(st.pop, None)
         self.run(move)
         self.migrate()
-        self.field_solve()
+        self.field_solve(history)
 
         def acc(r, st):
             lib.puAcc3D1KE(st.pop, st.E)

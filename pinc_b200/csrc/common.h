@@ -23,7 +23,7 @@ enum KClass { K_PUSH = 0, K_MOVE, K_DEPOSIT, K_EXTRACT, K_IMPORT, K_SORT, K_GRID
 extern const char *kclassName[K_NCLASS];
 
 // device-side error bits (Ctx::d_flags[0])
-enum DevErr { ERR_POS_RANGE = 1, ERR_CAPACITY = 2, ERR_VEL_MAX = 4, ERR_P2P_TIMEOUT = 8 };
+enum DevErr { ERR_POS_RANGE = 1, ERR_CAPACITY = 2, ERR_VEL_MAX = 4, ERR_P2P_TIMEOUT = 8, ERR_FIX_OVERFLOW = 16 };
 
 // fixed-point scale of the deposition accumulators: weights in [0,1] are summed as
 // round(w * 2^46) in 64-bit integers, so a node can take 2^17 particles per species before the
@@ -111,6 +111,13 @@ struct Ctx {
 	long long *d_mgProf = nullptr;                          // optional cycle accounting ($PINC_B200_MGPROF)
 	bool mgHistPending = false;
 	std::vector<double> mgHistory;
+	// convergence report of the most recent solve (checked at the next stream synchronisation, see streamSync)
+	bool mgCheckPending = false;
+	double mgTol = 1e-10, mgLastBarRes = 0;
+	int mgMaxCycles = 0, mgLastCycles = 0;
+	// per-device launch attributes of the persistent kernels (cudaFuncSetAttribute applies to the current device only)
+	size_t mgAttrSmem[2] = {0, 0};
+	int clNc = -1; size_t clSmem = 0;
 	std::unordered_map<const void*, CycleGraph> cycleGraphs;     // keyed by the solver's mgRho
 	std::unordered_map<const void*, void*> mgGlobal;             // replicated global hierarchies of multi-rank solves (multigrid.cu)
 	bool mgGlobalBusy = false;
@@ -199,6 +206,8 @@ double readScalar(Ctx *c, int slot);           // D2H of d_scal[slot] + sync
 
 // ---- multigrid (multigrid.cu) ----
 void mgForgetPlans(Ctx *c);
+void mgConvergenceCheck(Ctx *c);                 // called by streamSync when a solve's history has landed
+int mgMaxCyclesDefault();
 void *mgProfBuffer(Ctx *c);
 bool clusterSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, double tol, int maxCycles, int exact);
 

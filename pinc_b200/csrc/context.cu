@@ -61,7 +61,10 @@ Ctx *cur(){
 	return t_ctx;
 }
 
-void streamSync(Ctx *c){ PINC_CUDA(cudaStreamSynchronize(c->stream)); }
+void streamSync(Ctx *c){
+	PINC_CUDA(cudaStreamSynchronize(c->stream));
+	if(c->mgCheckPending) mgConvergenceCheck(c);
+}
 
 void checkDeviceFlags(Ctx *c, const char *where){
 	PINC_CUDA(cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -72,6 +75,7 @@ void checkDeviceFlags(Ctx *c, const char *where){
 	if(f & ERR_POS_RANGE) fatal("%s: particle outside the local grid (not migrated, or |v| >= 1 cell per step)", where);
 	if(f & ERR_CAPACITY)  fatal("%s: particle buffer capacity exceeded", where);
 	if(f & ERR_P2P_TIMEOUT) fatal("%s: a neighbour rank did not arrive within 3 s (peer-memory smoother)", where);
+	if(f & ERR_FIX_OVERFLOW) fatal("%s: deposition accumulator overflow (more than 2^16 full-weight particles of one species on one grid node)", where);
 	fatal("%s: device error flags 0x%x", where, f);
 }
 

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(MC_BLOCK, 1) k_mg_cluster(CPlan P){
 		if(K.rank == 0 && threadIdx.x == 0 && cycles < 250) P.hist[1+cycles] = barRes;
 		cycles++;
 	}
-	if(K.rank == 0 && threadIdx.x == 0) P.hist[0] = (double)cycles;
+	if(K.rank == 0 && threadIdx.x == 0){ P.hist[0] = (double)cycles; P.hist[251] = barRes; }
 	// back to global (phi of every level, rho where it lived in shared memory), then the ghost layers of every
 	// array: the state the reference leaves behind
 	for(int q = 0; q <= b; q++){
@@ -115,8 +115,8 @@ void *mgProfBuffer(Ctx *c){
 }
 // host side: returns false if this solve does not fit the cluster kernel (the caller falls back)
 bool clusterSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, double tol, int maxCycles, int exact){
-	static int maxNc = -1;
-	static size_t maxSmem = 0;
+	int &maxNc = c->clNc;                        // per context: attributes and schedulability belong to the device
+	size_t &maxSmem = c->clSmem;
 	if(maxNc < 0){
 		int v = 0;
 		cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
@@ -192,6 +192,7 @@ bool clusterSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, 
 	}
 	PINC_CUDA(cudaMemcpyAsync(c->h_mgHist, c->d_mgHist, 256*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	c->mgHistPending = true;
+	c->mgCheckPending = true; c->mgTol = tol; c->mgMaxCycles = maxCycles;
 	return true;
 }
 

@@ -313,6 +313,7 @@ __global__ void k_gs_p2p_loop(double *__restrict__ phi, const double *__restrict
 					for(int i = 0; i < 6 && ok; i++) if(A.active[i>>1] && *((volatile const unsigned long long*)&A.myFlag[i]) < seq) ok = false;
 					if(!ok && clock64() - c0 > 6000000000LL){ atomicOr(flags, ERR_P2P_TIMEOUT); break; }
 				}
+				__threadfence_system();       // acquire: the mailbox loads below must not be satisfied before the counters were seen
 				if(pr){ tD = clock64(); prof[24] += tD - tC; }      // ticket + local generation + neighbours' counters
 			}
 		}
@@ -396,7 +397,7 @@ bool gridHaloP2P(Ctx *c, DevGrid *g, const MpiInfo *m){
 	return true;
 }
 
-extern int g_mgMode, g_mgForceCluster, g_mgNoCluster;
+extern int g_mgMode, g_mgForceCluster, g_mgNoCluster, g_mgReplica;
 // 0 ops, 1 fused-exact, 2 auto, 3 auto-exact (resolved from $PINC_B200_MG at first use; pincMgSetMode overrides)
 static int mgMode(){
 	if(g_mgMode < 0){
@@ -511,6 +512,7 @@ struct MgPlan {
 	Lvl L[MG_MAXLEV];
 	BLvl B[MG_MAXLEV];
 	unsigned *seqWord;       // running half-sweep number of the mailbox protocol (persists across launches)
+	uint4 *mailAll; unsigned long long mailSlots;       // all mailbox slots of this context (cleared when the 32-bit tags are about to wrap)
 	int nLevels, nPre, nPost, nCoarse, qSmall, maxCycles;
 	double tol, totTrue;
 	double *partial;         // 2*gridDim doubles
@@ -1099,6 +1101,14 @@ template<bool EXACT> __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(M
 	double barRes = 2.;
 	int cycles = 0;
 	unsigned seq = *((volatile unsigned*)P.seqWord);       // rewritten only after the last grid barrier of this launch
+	if(seq > 0xE0000000u){
+		// the 32-bit tags are about to wrap (after ~10^6 time steps): back to the initial state - every slot zero,
+		// sequence 0 - so that a stale tag can never match a fresh one
+		for(unsigned long long i = (unsigned long long)Sg.tid(); i < P.mailSlots; i += (unsigned long long)Sg.nthr()) P.mailAll[i] = make_uint4(0u, 0u, 0u, 0u);
+		__threadfence();
+		Sg.sync();
+		seq = 0;
+	}
 	while(barRes > P.tol && cycles < P.maxCycles){
 		for(int q = 0; q <= b && q < qs; q++){ if(q < b) fDown(P, q, Sg, seq); else fBottom(P, Sg); }
 		if(qs <= b){
@@ -1134,7 +1144,7 @@ template<bool EXACT> __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(M
 		if(blockIdx.x == 0 && threadIdx.x == 0 && cycles < 250) P.hist[1+cycles] = barRes;
 		cycles++;
 	}
-	if(blockIdx.x == 0 && threadIdx.x == 0) P.hist[0] = (double)cycles;
+	if(blockIdx.x == 0 && threadIdx.x == 0){ P.hist[0] = (double)cycles; P.hist[251] = barRes; }
 	const unsigned seqEnd = seq;
 	if(P.smemSmall){
 		if(blockIdx.x == 0)
@@ -1162,6 +1172,7 @@ int g_mgMode = -1;
 // 2 cluster (DSMEM-resident, gBnd batched per smoother call; default); 3 cluster with gBnd per half-sweep
 int g_mgForceCluster = 0;     // $PINC_B200_MG=cluster-always: use the cluster kernel whenever it fits
 int g_mgNoCluster = 0;        // $PINC_B200_MG=allsm: use the all-SM kernel whatever the size
+int g_mgReplica = -1;         // multi-rank solves replicated (1) or distributed (0); -1: from $PINC_B200_MG_REPLICA at first use
 static void ensureHist(Ctx *c){
 	if(c->d_mgHist) return;
 	PINC_CUDA(cudaMalloc(&c->d_mgHist, 256*sizeof(double)));
@@ -1301,12 +1312,12 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 				PINC_CUDA(cudaMemsetAsync(c->d_mgMail, 0, c->mgMailBytes, c->stream));
 			}
 			for(int q = 0; q < P.qSmall && q < nL; q++) if(P.B[q].on) P.B[q].mail = (uint4*)c->d_mgMail + mailOff[q];
+			P.mailAll = (uint4*)c->d_mgMail; P.mailSlots = c->mgMailBytes/sizeof(uint4);
 			if(blockSmem > smem) smem = blockSmem;
 		}
 	}
 	{	// one high-water mark for the kernel's dynamic shared memory
-		static size_t attrSetBoth[2] = {0, 0};
-		size_t &attrSet = attrSetBoth[exact ? 1 : 0];
+		size_t &attrSet = c->mgAttrSmem[exact ? 1 : 0];       // per context: the attribute belongs to the device
 		const void *kern = exact ? (const void*)k_mg_solve<true> : (const void*)k_mg_solve<false>;
 		if(smem > attrSet){
 			if(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) attrSet = smem;
@@ -1327,6 +1338,7 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 	}
 	PINC_CUDA(cudaMemcpyAsync(c->h_mgHist, c->d_mgHist, 256*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	c->mgHistPending = true;
+	c->mgCheckPending = true; c->mgTol = tol; c->mgMaxCycles = maxCycles;
 }
 
 // All-reduce of one double over peer memory (gNeutralizeGrid, residual norm): block-reduce the partial sums, store the
@@ -1450,6 +1462,9 @@ static void opsSolve(Ctx *c, funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, 
 			c->mgHistory.push_back(barRes);
 			cycles++;
 		}
+		c->mgLastBarRes = barRes; c->mgLastCycles = cycles;
+		if(p && m->mpiSize > 1) checkDeviceFlags(c, "mgSolve");        // a peer-memory timeout must not reach the pusher
+		if(!(barRes <= tol)) fatal("mgSolve: the multigrid solver did not reach barRes <= %g within %d V-cycles (barRes = %g); the reference would loop forever (src/multigrid.c:1697)", tol, cycles, barRes);
 	} else {
 		DevGrid *rho = devGrid(c, mgRho->grids[0]), *phi = devGrid(c, mgPhi->grids[0]);
 		for(int cyc = 0; cyc < mgRho->nMGCycles; cyc++){
@@ -1512,8 +1527,8 @@ static void freeGlobalMg(GlobalMg *G){
 	delete G;
 }
 static bool replicaEligible(Ctx *c, Multigrid *mgRho, const MpiInfo *m){
-	static const bool off = getenv("PINC_B200_MG_REPLICA") && atoi(getenv("PINC_B200_MG_REPLICA")) == 0;
-	if(off || mgMode() != 2 || m->mpiSize < 2 || !c->tp) return false;
+	if(g_mgReplica < 0) g_mgReplica = (getenv("PINC_B200_MG_REPLICA") && atoi(getenv("PINC_B200_MG_REPLICA")) == 0) ? 0 : 1;
+	if(!g_mgReplica || mgMode() != 2 || m->mpiSize < 2 || !c->tp) return false;
 	int nL = mgRho->nLevels;
 	if(nL < 2 || nL > MG_MAXLEV) return false;
 	long nGlobal = 1;
@@ -1621,6 +1636,25 @@ static void solveSingle(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *m
 	c->mgLastPath = 1;
 }
 
+// The reference's tolerance loop has no bound (src/multigrid.c:1697): a solve that stalls hangs the run.  Here the loop
+// is bounded ($PINC_B200_MG_MAXCYCLES, default 10000 V-cycles) and a solve that ends above the tolerance is a fatal
+// error on every path, raised at the first stream synchronisation after the solve (the persistent kernels report
+// through the history buffer, which lands with the solve) - an unconverged E never reaches the pusher unnoticed.
+int mgMaxCyclesDefault(){
+	static int v = 0;
+	if(!v){ const char *e = getenv("PINC_B200_MG_MAXCYCLES"); v = e && atoi(e) > 0 ? atoi(e) : 10000; }
+	return v;
+}
+void mgConvergenceCheck(Ctx *c){
+	c->mgCheckPending = false;
+	if(!c->h_mgHist) return;
+	c->mgLastCycles = (int)c->h_mgHist[0];
+	c->mgLastBarRes = c->h_mgHist[251];
+	if(!(c->mgLastBarRes <= c->mgTol))
+		fatal("mgSolve: the multigrid solver did not reach barRes <= %g within %d V-cycles (barRes = %g); the reference would loop forever (src/multigrid.c:1697)",
+			c->mgTol, c->mgLastCycles, c->mgLastBarRes);
+}
+
 void mgForgetPlans(Ctx *c){
 	for(auto &kv : c->cycleGraphs) if(kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
 	c->cycleGraphs.clear();
@@ -1671,7 +1705,7 @@ void mgSolveRaw(funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 	checkPlugins(mgRho);
 	Ctx *c = cur();
 	const double tol = 1.E-10;                       // src/multigrid.c:1695
-	const int maxCycles = 200;                       // the reference has no bound; this one reports instead of hanging
+	const int maxCycles = pinc::mgMaxCyclesDefault();    // the reference has no bound (it would hang); this one fails loudly, see mgConvergenceCheck
 	if(fusedEligible(c, mgRho, mgPhi, mgRes, mpiInfo)) pinc::solveSingle(c, mgRho, mgPhi, mgRes, tol, maxCycles);
 	else if(pinc::replicaEligible(c, mgRho, mpiInfo)) pinc::replicaSolve(c, mgRho, mgPhi, mgRes, mpiInfo, tol, maxCycles);
 	else { opsSolve(c, mgAlgo, mgRho, mgPhi, mgRes, mpiInfo, tol, maxCycles); c->mgLastPath = 0; }
@@ -1698,11 +1732,13 @@ int pincMgLastHistory(double *barRes, int cap){
 		int n = (int)c->h_mgHist[0];
 		c->mgHistory.assign(c->h_mgHist + 1, c->h_mgHist + 1 + (n < 250 ? n : 250));
 		c->mgHistPending = false;
-		if(n >= 200) fprintf(stderr, "PINC-B200 WARNING: multigrid did not reach the tolerance in %d V-cycles\n", n);
+		c->mgLastCycles = n;
 	}
 	int n = (int)c->mgHistory.size();
 	for(int i = 0; i < n && i < cap; i++) barRes[i] = c->mgHistory[i];
-	return n;
+	return c->mgLastCycles > n ? c->mgLastCycles : n;      // more than 250 V-cycles: the count is exact, the history holds the first 250
 }
+double pincMgLastBarRes(void){ Ctx *c = cur(); if(c->mgHistPending || c->mgCheckPending) streamSync(c); return c->mgLastBarRes; }
+void pincMgSetReplica(int on){ pinc::g_mgReplica = on ? 1 : 0; }
 
 } // extern "C"

@@ -373,13 +373,17 @@ __global__ void __launch_bounds__(256) k_distr_tail(const double *__restrict__ X
 	}
 }
 // rho = (rho*(1/q) + sum w)*q, and the integer grid is cleared for the next species
-__global__ void k_distr_finalize(double *__restrict__ rho, long long *__restrict__ fix, long n, double invq, double q){
+__global__ void k_distr_finalize(double *__restrict__ rho, long long *__restrict__ fix, long n, double invq, double q, int *flags){
 	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
 	const double inv = 1.0/(double)(1LL<<PINC_FIX_BITS);
 	for(; i < n; i += st){
 		double r = rho[i];
+		const long long f = fix[i];
+		// the accumulator wraps at 2^63 = 2^17 full-weight particles on one node: report at half of that instead of
+		// handing a wrapped sum to the solver
+		if(f > (1LL<<62) || f < -(1LL<<62)) atomicOr(flags, ERR_FIX_OVERFLOW);
 		r *= invq;
-		r += (double)fix[i]*inv;
+		r += (double)f*inv;
 		r *= q;
 		rho[i] = r;
 		fix[i] = 0;
@@ -739,7 +743,7 @@ void puDistr3D1(const Population *pop, Grid *rhoGrid){
 		}
 		if(n - ns > 0)
 			PINC_LAUNCH(c, K_DEPOSIT, 24.0*(n-ns), (k_distr_tail<<<pGrid(c,n-ns),256,0,c->stream>>>(X+ns, Y+ns, Z+ns, n-ns, rho->size[0], rho->size[1], rho->size[2], rho->d_fixS[s], c->d_flags)));
-		PINC_LAUNCH(c, K_DEPOSIT, 32.0*rho->n, (k_distr_finalize<<<gridFor(rho->n,256,c->numSMs*8),256,0,c->stream>>>(rho->d, rho->d_fixS[s], rho->n, 1.0/pop->charge[s], pop->charge[s])));
+		PINC_LAUNCH(c, K_DEPOSIT, 32.0*rho->n, (k_distr_finalize<<<gridFor(rho->n,256,c->numSMs*8),256,0,c->stream>>>(rho->d, rho->d_fixS[s], rho->n, 1.0/pop->charge[s], pop->charge[s], c->d_flags)));
 	}
 	dp->predep = nullptr;
 }

@@ -74,6 +74,8 @@ SIGNATURES = {
     "mgFreeSolver": (None, [P(abi.MultigridSolver)]),
     "pincMgLastHistory": (C.c_int, [abi.c_double_p, C.c_int]),
     "pincMgSetMode": (None, [C.c_int]),
+    "pincMgSetReplica": (None, [C.c_int]),
+    "pincMgLastBarRes": (C.c_double, []),
     "pincMgLastPath": (C.c_int, []),
     # entry points that take PINC's dictionary *ini (need the host's iniGet*; typed for the symbol check)
     "puAcc3D1_set": (C.c_void_p, [C.c_void_p]),

@@ -268,12 +268,6 @@ class World:
         self.run(phase)
         self._moved = bool(fused)
 
-    def unmove(self):
-        """Positions of a fused run are one puMove ahead of the reference's end-of-step state; step back
-        (pos -= vel is not bit-exact, so parity tests compare fused runs at the velocity/field level or run
-        the last step unfused)."""
-        raise NotImplementedError
-
     def energies(self):
         ns = self.cfg.nSpecies
         ke = sum(st.pop.contents.kinEnergy[ns] for st in self.ranks.values())

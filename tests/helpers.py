@@ -74,3 +74,21 @@ def sorted_particles(pos, vel):
     # (lattice starts have thousands of them) the same way
     idx = np.lexsort(np.round(rec, 7).T[::-1])
     return rec[idx]
+
+
+def multiset_close(pos_a, vel_a, pos_b, vel_b, tol):
+    """Two particle sets are equal as multisets up to `tol` per coordinate.  Sized for tens of millions of particles:
+    one argsort on x per side, then only the rows that disagree (near-ties in x that the two sides ordered
+    differently) are matched by a full lexicographic sort.  Returns the worst coordinate difference."""
+    if len(pos_a) != len(pos_b):
+        return np.inf
+    a = np.concatenate([pos_a, vel_a], axis=1)[np.argsort(pos_a[:, 0], kind="stable")]
+    b = np.concatenate([pos_b, vel_b], axis=1)[np.argsort(pos_b[:, 0], kind="stable")]
+    d = np.abs(a - b).max(axis=1) if len(a) else np.zeros(0)
+    bad = d > tol
+    worst = float(d[~bad].max()) if (~bad).any() else 0.0
+    if bad.any():
+        if bad.sum() > max(1000, len(a) // 1000):
+            return float(d.max())
+        worst = max(worst, float(np.abs(sorted_particles(a[bad, :3], a[bad, 3:]) - sorted_particles(b[bad, :3], b[bad, 3:])).max()))
+    return worst

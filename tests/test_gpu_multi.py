@@ -12,13 +12,14 @@ from helpers import ROOT
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("replica", [1, 0])
 @pytest.mark.parametrize("kind", ["warm", "cold"])
-def test_two_gpus_nccl(kind):
+def test_two_gpus_nccl(kind, replica):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(ROOT, "tools", "multi_check.py"), kind, "4"]
+           "--master-port", "29517", os.path.join(ROOT, "tools", "multi_check.py"), kind, "4", str(replica)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("] ok: ") == 2
