@@ -221,6 +221,9 @@ double pincMgLastBarRes(void);
 /* multi-rank solves replicated (1, default) or distributed over the ranks (0); overrides
  * $PINC_B200_MG_REPLICA.  Process-wide: call it on every rank before the next mgSolve. */
 void pincMgSetReplica(int on);
+/* A/B switch of the all-SM kernel's block-resident smoother: 0 never the row smoother (mgrows.cuh), 1 (default) for blocks
+ * too big for the register-descriptor path (levels of >= 1 M nodes), 2 whenever the block shape allows it. */
+void pincMgSetRowMode(int mode);
 /* which implementation ran the most recent mgSolve on this rank: 0 one kernel per reference call (distributed), 1 the
  * all-SM persistent kernel, 2 the cluster kernel; +4: a multi-rank solve done by replication (every rank gathers rho and
  * phi, solves the global problem with the single-GPU kernel and keeps its own sub-domain) */

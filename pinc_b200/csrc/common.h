@@ -107,6 +107,7 @@ struct Ctx {
 	cudaEvent_t tStart = nullptr, tStop = nullptr;
 	// multigrid residual history of the most recent solve (device + pinned host: [0] = cycles, [1..] = barRes)
 	double *d_mgHist = nullptr, *h_mgHist = nullptr;
+	void *d_mgRhoS = nullptr; size_t mgRhoSBytes = 0;       // colour-separated rho of the row smoother (mgrows.cuh)
 	void *d_mgMail = nullptr; size_t mgMailBytes = 0;       // halo mailboxes of the block-resident smoother (multigrid.cu)
 	long long *d_mgProf = nullptr;                          // optional cycle accounting ($PINC_B200_MGPROF)
 	bool mgHistPending = false;

@@ -260,6 +260,7 @@ void pincCtxDestroy(PincCtx *ctx){
 	if(c->d_partial) cudaFree(c->d_partial);
 	if(c->d_mgProf) cudaFree(c->d_mgProf);
 	if(c->d_mgMail) cudaFree(c->d_mgMail);
+	if(c->d_mgRhoS) cudaFree(c->d_mgRhoS);
 	if(c->d_mgHist){ cudaFree(c->d_mgHist); cudaFreeHost(c->h_mgHist); }
 	if(c->d_tmp) cudaFree(c->d_tmp);
 	for(auto e : c->evPool) cudaEventDestroy(e);

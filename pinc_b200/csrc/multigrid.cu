@@ -397,7 +397,7 @@ bool gridHaloP2P(Ctx *c, DevGrid *g, const MpiInfo *m){
 	return true;
 }
 
-extern int g_mgMode, g_mgForceCluster, g_mgNoCluster, g_mgReplica;
+extern int g_mgMode, g_mgForceCluster, g_mgNoCluster, g_mgReplica, g_mgRowMode;
 // 0 ops, 1 fused-exact, 2 auto, 3 auto-exact (resolved from $PINC_B200_MG at first use; pincMgSetMode overrides)
 static int mgMode(){
 	if(g_mgMode < 0){
@@ -507,6 +507,7 @@ struct BLvl {
 	int on, bx, by, bz, nbx, nby, nbz, nb, rows;
 	int offPhi, offRho;      // shared-memory offsets in doubles; offRho < 0: rho is read from global memory
 	uint4 *mail;             // nb x 2(by*bz + bx*bz + bx*by) slots
+	double *rhoS;            // row smoother: colour-separated copy of rho, nb x bx*by*bz doubles (mgrows.cuh)
 };
 struct MgPlan {
 	Lvl L[MG_MAXLEV];
@@ -950,11 +951,17 @@ __device__ __noinline__ void bNeutRho(const Lvl &L, const BLvl &B, Scope &S){
 	#pragma unroll
 	for(int u = 0; u < 4; u++) if(g[u] >= 0) L.rho[g[u]] = r[u] - avg;
 }
+} // namespace pinc
+#include "mgrows.cuh"
+namespace pinc {
+
 __device__ __noinline__ void fDown(const MgPlan &P, int q, Scope &S, unsigned &seq){
 	const Lvl &L = P.L[q], &C = P.L[q+1];
 	const bool blk = P.B[q].on && !S.single && P.nPre > 0;
-	if(blk && P.B[q].on == 1) bNeutRho(L, P.B[q], S); else fNeutralize(L.rho, L.s0, L.s1, L.s2, S);
-	if(blk) bGS(L, P.B[q], P.nPre, 0.0, S, seq); else fGS(L, P.nPre, 0.0, P.exact, S);
+	if(blk && P.B[q].on == 3){ if(P.B[q].bx == 32) rNeutRho<16>(L, P.B[q], S); else rNeutRho<8>(L, P.B[q], S); }
+	else if(blk && P.B[q].on == 1) bNeutRho(L, P.B[q], S); else fNeutralize(L.rho, L.s0, L.s1, L.s2, S);
+	if(blk && P.B[q].on == 3){ if(P.B[q].bx == 32) rGS<16>(L, P.B[q], P.nPre, 0.0, S, seq); else rGS<8>(L, P.B[q], P.nPre, 0.0, S, seq); }
+	else if(blk) bGS(L, P.B[q], P.nPre, 0.0, S, seq); else fGS(L, P.nPre, 0.0, P.exact, S);
 	{
 		ProfScope psr(*S.K, S.single ? 27 : 29);
 		int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2; long nt = (long)t0*t1*t2;
@@ -992,7 +999,8 @@ __device__ __noinline__ void fUp(const MgPlan &P, int q, Scope &S, unsigned &seq
 	}
 	double avg = S.allSum(acc)/(double)nt;
 	if(S.K->prof && blockIdx.x == 0 && threadIdx.x == 0 && !S.single){ S.K->prof[2*31] += clock64() - tUp; S.K->prof[2*31+1] += 1; }
-	if(P.B[q].on && !S.single && P.nPost > 0) bGS(L, P.B[q], P.nPost, avg, S, seq); else fGS(L, P.nPost, avg, P.exact, S);
+	if(P.B[q].on == 3 && !S.single && P.nPost > 0){ if(P.B[q].bx == 32) rGS<16>(L, P.B[q], P.nPost, avg, S, seq); else rGS<8>(L, P.B[q], P.nPost, avg, S, seq); }
+	else if(P.B[q].on && !S.single && P.nPost > 0) bGS(L, P.B[q], P.nPost, avg, S, seq); else fGS(L, P.nPost, avg, P.exact, S);
 	if(P.exact || P.nPost <= 0) fNeutralize(L.phi, L.s0, L.s1, L.s2, S);
 }
 __device__ __noinline__ void fGhosts(double *v, int s0, int s1, int s2, Scope &S){
@@ -1172,6 +1180,7 @@ int g_mgMode = -1;
 // 2 cluster (DSMEM-resident, gBnd batched per smoother call; default); 3 cluster with gBnd per half-sweep
 int g_mgForceCluster = 0;     // $PINC_B200_MG=cluster-always: use the cluster kernel whenever it fits
 int g_mgNoCluster = 0;        // $PINC_B200_MG=allsm: use the all-SM kernel whatever the size
+int g_mgRowMode = -1;         // row smoother (mgrows.cuh): 0 off, 1 for big blocks (default), 2 whenever the block shape allows; -1: from $PINC_B200_MG_ROWMODE
 int g_mgReplica = -1;         // multi-rank solves replicated (1) or distributed (0); -1: from $PINC_B200_MG_REPLICA at first use
 static void ensureHist(Ctx *c){
 	if(c->d_mgHist) return;
@@ -1293,6 +1302,19 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 			BLvl &B = P.B[q];
 			if(!planBlocks(r->tsize[0], r->tsize[1], r->tsize[2], grid-1, smemCap, B)) continue;
 			if(B.bx > 1000 || B.by > 1000 || B.bz > 1000){ B.on = 0; continue; }        // packed node coordinates in bGS
+			{	// big blocks: one x-row per thread, colour-separated rows (mgrows.cuh); $PINC_B200_MG_ROWMODE=0 off, 2 also for small blocks
+				if(g_mgRowMode < 0) g_mgRowMode = getenv("PINC_B200_MG_ROWMODE") ? atoi(getenv("PINC_B200_MG_ROWMODE")) : 1;
+				const int rowMode = g_mgRowMode;
+				const bool big = (B.bx/2)*B.by*B.bz > 2*MG_BLOCK || B.by*B.bz + B.bx*B.bz + B.bx*B.by > MG_BLOCK;
+				if(rowMode && (big || rowMode == 2) && (B.bx == 16 || B.bx == 32) && B.by*B.bz <= MG_BLOCK){
+					B.on = 3; B.offRho = -1;
+					mailOff[q] = mailSlots;
+					mailSlots += (size_t)B.nb*2*(B.by*B.bz + B.bx*B.bz + B.bx*B.by);
+					size_t need = (size_t)(B.bx+2)*(B.by+2)*(B.bz+2)*sizeof(double);
+					if(need > blockSmem) blockSmem = need;
+					continue;
+				}
+			}
 			{ static const int maxItems = getenv("PINC_B200_MG_MAXITEMS") ? atoi(getenv("PINC_B200_MG_MAXITEMS")) : 1024;     // bigger blocks are throughput-bound and the grid-wide sweep (fGS) is as fast or faster (us per V-cycle, fGS vs blocks: 64x64x128 532 vs 532, 64x128x128 736 vs 820, 128^3 1122 vs 1367)
 			  if((B.bx/2)*B.by*B.bz > maxItems){ B.on = 0; continue; } }
 			static const bool noRows = getenv("PINC_B200_MG_ROWS") && atoi(getenv("PINC_B200_MG_ROWS")) == 0;
@@ -1312,6 +1334,16 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 				PINC_CUDA(cudaMemsetAsync(c->d_mgMail, 0, c->mgMailBytes, c->stream));
 			}
 			for(int q = 0; q < P.qSmall && q < nL; q++) if(P.B[q].on) P.B[q].mail = (uint4*)c->d_mgMail + mailOff[q];
+			{	// colour-separated rho copies of the row-smoothed levels
+				size_t need = 0, off[MG_MAXLEV] = {0};
+				for(int q = 0; q < P.qSmall && q < nL; q++) if(P.B[q].on == 3){ off[q] = need; need += (size_t)P.B[q].nb*P.B[q].bx*P.B[q].by*P.B[q].bz; }
+				if(need*sizeof(double) > c->mgRhoSBytes){
+					if(c->d_mgRhoS){ streamSync(c); PINC_CUDA(cudaFree(c->d_mgRhoS)); }
+					c->mgRhoSBytes = need*sizeof(double);
+					PINC_CUDA(cudaMalloc(&c->d_mgRhoS, c->mgRhoSBytes));
+				}
+				for(int q = 0; q < P.qSmall && q < nL; q++) if(P.B[q].on == 3) P.B[q].rhoS = (double*)c->d_mgRhoS + off[q];
+			}
 			P.mailAll = (uint4*)c->d_mgMail; P.mailSlots = c->mgMailBytes/sizeof(uint4);
 			if(blockSmem > smem) smem = blockSmem;
 		}
@@ -1740,5 +1772,6 @@ int pincMgLastHistory(double *barRes, int cap){
 }
 double pincMgLastBarRes(void){ Ctx *c = cur(); if(c->mgHistPending || c->mgCheckPending) streamSync(c); return c->mgLastBarRes; }
 void pincMgSetReplica(int on){ pinc::g_mgReplica = on ? 1 : 0; }
+void pincMgSetRowMode(int mode){ pinc::g_mgRowMode = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 
 } // extern "C"

@@ -75,6 +75,7 @@ SIGNATURES = {
     "pincMgLastHistory": (C.c_int, [abi.c_double_p, C.c_int]),
     "pincMgSetMode": (None, [C.c_int]),
     "pincMgSetReplica": (None, [C.c_int]),
+    "pincMgSetRowMode": (None, [C.c_int]),
     "pincMgLastBarRes": (C.c_double, []),
     "pincMgLastPath": (C.c_int, []),
     # entry points that take PINC's dictionary *ini (need the host's iniGet*; typed for the symbol check)

@@ -202,7 +202,22 @@ def test_mg_solve_matches_oracle(gpu_lib, mode, true, levels):
         L.pincMgSetMode(2)
 
 
-def _run_mg_case(L, O, true, levels):
+@pytest.mark.parametrize("true,levels,rowmode,solves", [((64, 64, 64), 5, 2, 2), ((64, 64, 128), 5, 1, 2), ((64, 128, 128), 5, 1, 1),
+                                                        ((128, 128, 128), 6, 1, 1), ((128, 128, 128), 5, 1, 1)])
+def test_mg_row_smoother_matches_oracle(gpu_lib, true, levels, rowmode, solves):
+    """The row smoother of the all-SM kernel (mgrows.cuh: big blocks, one x-row per thread) at the global grids of the
+    replicated 2/4/8-rank solves, and forced onto the 64^3 blocks: V-cycle count, residual history and phi against the oracle."""
+    L, O = gpu_lib, orc.load()
+    L.pincMgSetMode(5)
+    L.pincMgSetRowMode(rowmode)
+    try:
+        _run_mg_case(L, O, true, levels, solves)
+    finally:
+        L.pincMgSetMode(2)
+        L.pincMgSetRowMode(1)
+
+
+def _run_mg_case(L, O, true, levels, solves=2):
     rho, phi, solver = _mg_problem(L, true, levels, seed=20)
     m = single_mpi(L, true)
     t = topo1(true)
@@ -210,9 +225,9 @@ def _run_mg_case(L, O, true, levels):
     rr, pr, er = rho.flat().copy(), phi.flat().copy(), np.zeros(rho.flat().size)
     rho.up(); phi.up()
     rng = np.random.default_rng(21)
-    for solve in range(2):
-        hist = np.zeros(64)
-        n_ref = O.orc_mg_solve(mg, orc.ptr_array([rr]), orc.ptr_array([pr]), orc.ptr_array([er]), 1e-10, 100, orc.dp(hist), 64)
+    for solve in range(solves):
+        hist = np.zeros(256)
+        n_ref = O.orc_mg_solve(mg, orc.ptr_array([rr]), orc.ptr_array([pr]), orc.ptr_array([er]), 1e-10, 250, orc.dp(hist), 256)
         L.mgSolve(solver, rho.ptr, phi.ptr, m)
         buf = (C.c_double * 256)()
         n = L.pincMgLastHistory(buf, 256)

@@ -73,7 +73,7 @@ def main():
                 buf = (C.c_longlong * 64)()
                 L.pincMgProfRead.argtypes = [C.POINTER(C.c_longlong)]
                 if L.pincMgProfRead(buf):
-                    names = ["neut_rho", "gs_big", "gs_small", "restrict", "prolong", "neut_phi", "norm", "gs_big_sync", "small_section", "b_load", "b_wait", "b_compute", "b_tail", "g_wait", "g_compute", "-",
+                    names = ["neut_rho", "gs_big", "gs_small", "restrict", "prolong", "neut_phi", "norm", "gs_big_sync", "small_section", "b_load", "b_wait", "r_sync", "b_tail", "r_recv", "r_comp", "r_send",
                              "gs16", "res16", "pro16", "-", "gs8", "res8", "pro8", "-", "gs4", "res4", "pro4", "-", "f_neut", "f_resid", "f_restr", "f_prol"]
                     solves = 3
                     rec["prof_us_per_vcycle"] = {n: round(buf[2 * i] / 1965.0 / (solves * max(ncyc, 1)), 2) for i, n in enumerate(names) if n != "-"}
