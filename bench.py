@@ -165,16 +165,17 @@ def run_ours(args, n_gpus, rank, world_size):
             # the NCCL path against the oracle BEFORE anything is timed (small seeded configs, every rank checks its own
             # sub-domain against the oracle's run of the whole world): warm + cold, replicated + distributed solve
             parity = {"tolerance": 1e-10, "cases": []}
-            for kind in ("warm", "cold"):
-                for replica in (1, 0):
-                    r = multi_check.check(rank, world_size, kind, steps=4, replica=replica)
+            # (kind, replicated?, hybrid?, cells per rank): the hybrid solve needs a finest level of > 4096 nodes per rank
+            for kind, replica, hybrid, true in (("warm", 1, 1, "32,16,16"), ("cold", 1, 1, "32,16,16"), ("warm", 1, 0, "16,8,8"), ("warm", 0, 0, "16,8,8")):
+                if True:
+                    r = multi_check.check(rank, world_size, kind, steps=4, replica=replica, hybrid=hybrid, true=true)
                     t = torch.tensor([r["worst_field_err"], r["worst_particle_err"], 0.0 if r["tables_exact"] else 1.0,
                                       0.0 if r["cycles_equal"] else 1.0, 0.0 if r["sizes_exact"] else 1.0],
                                      dtype=torch.float64, device="cuda")
                     dist.all_reduce(t, op=dist.ReduceOp.MAX)
                     v = t.tolist()
-                    parity["cases"].append({"config": f"{kind}, 16x8x8 cells per rank, {multi_check.SUB[world_size]}, 4 steps",
-                                            "solve": "replicated" if replica else "distributed (peer-memory smoother)",
+                    parity["cases"].append({"config": f"{kind}, {true.replace(',', 'x')} cells per rank, {multi_check.SUB[world_size]}, 4 steps",
+                                            "solve": ("hybrid (finest level distributed over peer-memory mailboxes, coarser levels replicated)" if hybrid else "replicated") if replica else "distributed (one kernel per reference call, peer-memory smoother)",
                                             "mg_path": r["mg_path"], "transport": r["transport"], "vcycles_last": r["vcycles_last"],
                                             "worst_field_err": v[0], "worst_particle_err": v[1], "tables_exact": v[2] == 0.0,
                                             "cycles_equal": v[3] == 0.0, "sizes_exact": v[4] == 0.0})
@@ -334,7 +335,8 @@ def run_ours(args, n_gpus, rank, world_size):
                        "vcycles_last_solve": len(hist), "ic_seconds": t_ic,
                        "mg_path": {0: "distributed, one kernel per reference call", 1: "all-SM persistent kernel", 2: "cluster kernel",
                                    5: "replicated: global problem on every rank, all-SM persistent kernel",
-                                   6: "replicated: global problem on every rank, cluster kernel"}.get(W.mg_path(), "?")},
+                                   6: "replicated: global problem on every rank, cluster kernel",
+                                   9: "hybrid: finest level distributed (block faces across sub-domains through peer-memory mailboxes), coarser levels replicated, one persistent kernel per rank"}.get(W.mg_path(), "?")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels}
     if parity is not None:
         line["parity"] = parity

@@ -221,6 +221,10 @@ double pincMgLastBarRes(void);
 /* multi-rank solves replicated (1, default) or distributed over the ranks (0); overrides
  * $PINC_B200_MG_REPLICA.  Process-wide: call it on every rank before the next mgSolve. */
 void pincMgSetReplica(int on);
+/* replicated multi-rank solves keep the finest level distributed (1, default: hybrid - every rank smooths its own sub-domain,
+ * block faces across sub-domain boundaries travel through peer memory; the coarser levels are replicated) or replicate the
+ * whole hierarchy (0); overrides $PINC_B200_MG_HYBRID.  Process-wide. */
+void pincMgSetHybrid(int on);
 /* A/B switch of the all-SM kernel's block-resident smoother: 0 never the row smoother (mgrows.cuh), 1 (default) for blocks
  * too big for the register-descriptor path (levels of >= 1 M nodes), 2 whenever the block shape allows it. */
 void pincMgSetRowMode(int mode);

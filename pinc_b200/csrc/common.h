@@ -117,11 +117,13 @@ struct Ctx {
 	double mgTol = 1e-10, mgLastBarRes = 0;
 	int mgMaxCycles = 0, mgLastCycles = 0;
 	// per-device launch attributes of the persistent kernels (cudaFuncSetAttribute applies to the current device only)
-	size_t mgAttrSmem[2] = {0, 0};
+	size_t mgAttrSmem[3] = {0, 0, 0};
 	int clNc = -1; size_t clSmem = 0;
 	std::unordered_map<const void*, CycleGraph> cycleGraphs;     // keyed by the solver's mgRho
 	std::unordered_map<const void*, void*> mgGlobal;             // replicated global hierarchies of multi-rank solves (multigrid.cu)
 	bool mgGlobalBusy = false;
+	void *mgXArena = nullptr;                                    // peer-mapped arena of the hybrid multi-rank solve (multigrid.cu)
+	double mgXTagHigh = 0; bool mgXPending = false;              // its running mailbox tag after the most recent solve (reset before the 32-bit tags wrap)
 	int mgLastPath = 0;                                          // pincMgLastPath: 0 ops, 1 all-SM kernel, 2 cluster kernel, +4 replicated
 	Transport *tp = nullptr;
 	std::string lastError;
@@ -180,6 +182,10 @@ struct Transport {
 	virtual void barrier(Ctx *c) = 0;
 	virtual const char *name() const = 0;
 	virtual P2P *p2p() { return nullptr; }     // peer-memory arena, if this transport has one
+	// collective: a zeroed device allocation per rank that every rank can address (peers[r] = rank r's, peers[own] = *mine);
+	// false (on every rank) if this transport cannot do that
+	virtual bool peerAlloc(Ctx *, size_t, char **, std::vector<char*> &) { return false; }
+	virtual void peerFree(Ctx *, char *, std::vector<char*> &) {}
 };
 Transport *makeSelfTransport();
 void localCopies(Ctx *c, std::vector<Msg> &sends, std::vector<Msg> &recvs);   // matches and removes self messages
@@ -207,6 +213,7 @@ double readScalar(Ctx *c, int slot);           // D2H of d_scal[slot] + sync
 
 // ---- multigrid (multigrid.cu) ----
 void mgForgetPlans(Ctx *c);
+void mgFreeArena(Ctx *c);                        // before the transport goes away
 void mgConvergenceCheck(Ctx *c);                 // called by streamSync when a solve's history has landed
 int mgMaxCyclesDefault();
 void *mgProfBuffer(Ctx *c);

@@ -266,6 +266,7 @@ void pincCtxDestroy(PincCtx *ctx){
 	for(auto e : c->evPool) cudaEventDestroy(e);
 	cudaEventDestroy(c->tStart); cudaEventDestroy(c->tStop);
 	cudaStreamDestroy(c->stream);
+	mgFreeArena(c);
 	delete c->tp;
 	if(t_ctx == c) t_ctx = nullptr;
 	delete c;

@@ -397,7 +397,7 @@ bool gridHaloP2P(Ctx *c, DevGrid *g, const MpiInfo *m){
 	return true;
 }
 
-extern int g_mgMode, g_mgForceCluster, g_mgNoCluster, g_mgReplica, g_mgRowMode;
+extern int g_mgMode, g_mgForceCluster, g_mgNoCluster, g_mgReplica, g_mgRowMode, g_mgHybrid;
 // 0 ops, 1 fused-exact, 2 auto, 3 auto-exact (resolved from $PINC_B200_MG at first use; pincMgSetMode overrides)
 static int mgMode(){
 	if(g_mgMode < 0){
@@ -509,9 +509,23 @@ struct BLvl {
 	uint4 *mail;             // nb x 2(by*bz + bx*bz + bx*by) slots
 	double *rhoS;            // row smoother: colour-separated copy of rho, nb x bx*by*bz doubles (mgrows.cuh)
 };
+// Hybrid multi-rank solve (hybridSolve below): levels q < qDist are DISTRIBUTED (every rank smooths its own sub-domain
+// block-resident, faces across a sub-domain boundary travel through tagged 16-byte slots in the NEIGHBOUR'S arena over
+// NVLink), levels q >= qDist are REPLICATED (every rank holds and solves the global level).  All cross-GPU traffic is
+// "data is its own flag" (st.relaxed.sys / ld.relaxed.sys of {lo, tag, hi, tag}): no fence, no flag word.
+#define XD_MAXR 32
+struct XDist {
+	int on, qDist, R, me;
+	int ns[3], sub[3];             // sub-domains per dimension, this rank's sub-domain
+	int nbr[6];                    // rank across face f = 2*dim + side (side 0: lower)
+	uint4 *peer[XD_MAXR];          // every rank's arena (peer[me] is this rank's own)
+	unsigned *ctr;                 // persisted counters in my arena: [0] mailbox tags, [1] sums, [2] halo fills, [3] gathers
+	unsigned offSum, offPlane, planeCap, offGath, gathCap;      // slot (16-byte) offsets into an arena
+};
 struct MgPlan {
 	Lvl L[MG_MAXLEV];
 	BLvl B[MG_MAXLEV];
+	XDist X;
 	unsigned *seqWord;       // running half-sweep number of the mailbox protocol (persists across launches)
 	uint4 *mailAll; unsigned long long mailSlots;       // all mailbox slots of this context (cleared when the 32-bit tags are about to wrap)
 	int nLevels, nPre, nPost, nCoarse, qSmall, maxCycles;
@@ -528,7 +542,32 @@ struct MgPlan {
 	CPlan C;
 };
 
+// ---- cross-GPU slots: one 16-byte store {value.lo, tag, value.hi, tag} at system scope; the reader polls until both tags match
+__device__ __forceinline__ void llStoreSys(uint4 *p, double v, unsigned tag){
+	unsigned lo = (unsigned)__double_as_longlong(v), hi = (unsigned)(__double_as_longlong(v) >> 32);
+	asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
+}
+__device__ __noinline__ void llTimeout(const uint4 *p, unsigned tag, unsigned a, unsigned b){
+	printf("PINC-B200 ERROR: rank-to-rank slot %p never reached tag %u (holds %u/%u) - a neighbour rank did not arrive\n", (const void*)p, tag, a, b);
+	__trap();
+}
+__device__ __forceinline__ double llWaitSys(const uint4 *p, unsigned tag){
+	unsigned a, b, c, d, spins = 0;
+	unsigned long long t0 = 0;
+	for(;;){
+		asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+		if(b == tag && d == tag) break;
+		if((++spins & 0xfffu) == 0){                  // bounded: ~20 s of wall clock, then fail loudly instead of hanging the device
+			unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+			if(!t0) t0 = t; else if(t - t0 > 20000000000ULL) llTimeout(p, tag, b, d);
+		}
+	}
+	return __longlong_as_double(((long long)c << 32) | (long long)a);
+}
+
 struct Scope {
+	const XDist *X;          // hybrid multi-rank solve: cross-GPU description (MgPlan::X), else unused
+	unsigned xMail, xSum, xHalo, xGath;     // running tags of the cross-GPU operations (identical on all ranks)
 	bool single;             // only this CTA takes part (block-level barriers)
 	unsigned *bar; unsigned gen;
 	double *partial; int flip;
@@ -582,15 +621,35 @@ struct Scope {
 		flip ^= 1;
 		return tot;
 	}
+	// the same over all ranks: rank r's CTA 0 stores its total into slot r of every rank, every CTA polls the R slots of
+	// its own arena and adds them in rank order (identical bits everywhere); two slot sets alternate, a set is rewritten
+	// only after every rank has sent its next value, i.e. after it has read this one
+	__device__ __noinline__ double allSumX(double v){
+		double tot = allSum(v);
+		const XDist &x = *X;
+		const unsigned tag = ++xSum, set = tag & 1u;
+		if(blockIdx.x == 0 && (int)threadIdx.x < x.R) llStoreSys(x.peer[threadIdx.x] + x.offSum + set*XD_MAXR + x.me, tot, tag);
+		if(threadIdx.x < 32){
+			const int lane = threadIdx.x;
+			double t = lane < x.R ? llWaitSys(x.peer[x.me] + x.offSum + set*XD_MAXR + lane, tag) : 0.0;
+			double a = 0;
+			for(int r = 0; r < x.R; r++) a += __shfl_sync(0xffffffffu, t, r);
+			if(lane == 0) sh[17] = a;
+		}
+		__syncthreads();
+		tot = sh[17];
+		__syncthreads();
+		return tot;
+	}
 };
 
 // gNeutralizeGrid on the true nodes: returns after the subtraction is visible to everyone
-__device__ __noinline__ void fNeutralize(double *v, int s0, int s1, int s2, Scope &S){
+template<bool X = false> __device__ __noinline__ void fNeutralize(double *v, int s0, int s1, int s2, Scope &S){
 	ProfScope psn(*S.K, S.single ? 27 : 28);
 	int t0 = s0-2, t1 = s1-2, t2 = s2-2; long nt = (long)t0*t1*t2;
 	double acc = 0;
 	for(long i = S.tid(); i < nt; i += S.nthr()){ int j,k,l; truePoint(i,t0,t1,j,k,l); acc += ldg2(v + ix(j,k,l,s0,s1)); }
-	double avg = S.allSum(acc)/(double)nt;
+	double avg = X ? S.allSumX(acc)/((double)nt*(double)S.X->R) : S.allSum(acc)/(double)nt;
 	for(long i = S.tid(); i < nt; i += S.nthr()){ int j,k,l; truePoint(i,t0,t1,j,k,l); long g = ix(j,k,l,s0,s1); v[g] = ldg2(v + g) - avg; }
 	S.sync();
 }
@@ -698,31 +757,48 @@ __device__ __forceinline__ double fastVal(const double *Ph, int idx, int ex, int
 	double a = Ph[idx+1], b = Ph[idx-1], c = Ph[idx+ex], d = Ph[idx-ex], e = Ph[idx+pl], f = Ph[idx-pl];
 	return coeff*(a + b + c + d + e + f + rho);
 }
-__device__ __forceinline__ void fastSend(uint4 *mail, const FastNode &n, double v, unsigned stag){
-	if(n.t0 != LL_NONE) llStore(mail + n.t0, v, stag);
-	if(n.t1 != LL_NONE) llStore(mail + n.t1, v, stag);
-	if(n.t2 != LL_NONE) llStore(mail + n.t2, v, stag);
+// X (hybrid multi-rank solve, distributed level): a slot offset carries the face it crosses in its top three bits, the face's
+// base is this rank's mailbox array or the neighbour rank's (xBase, shared memory), and stores/polls are system-scope
+#define LL_FACE_SHIFT 29
+#define LL_OFF_MASK 0x1fffffffu
+template<bool X> __device__ __forceinline__ void fastSend(uint4 *mail, uint4 *const *xBase, const FastNode &n, double v, unsigned stag){
+	if constexpr(X){
+		if(n.t0 != LL_NONE) llStoreSys(xBase[n.t0 >> LL_FACE_SHIFT] + (n.t0 & LL_OFF_MASK), v, stag);
+		if(n.t1 != LL_NONE) llStoreSys(xBase[n.t1 >> LL_FACE_SHIFT] + (n.t1 & LL_OFF_MASK), v, stag);
+		if(n.t2 != LL_NONE) llStoreSys(xBase[n.t2 >> LL_FACE_SHIFT] + (n.t2 & LL_OFF_MASK), v, stag);
+	} else {
+		if(n.t0 != LL_NONE) llStore(mail + n.t0, v, stag);
+		if(n.t1 != LL_NONE) llStore(mail + n.t1, v, stag);
+		if(n.t2 != LL_NONE) llStore(mail + n.t2, v, stag);
+	}
 }
-__device__ __forceinline__ void fastHalf(double *Ph, int ex, int pl, uint4 *mail, const uint4 *pAddr, int pIdx, bool recv, unsigned tagIn,
+template<bool X> __device__ __forceinline__ void fastHalf(double *Ph, int ex, int pl, uint4 *mail, uint4 *const *xBase, const uint4 *pAddr, int pIdx, bool recv, unsigned tagIn,
 		const FastNode &a, const FastNode &b, unsigned stag, bool send){
-	if(recv && pAddr) Ph[pIdx] = llWait(pAddr, tagIn);
+	if(recv && pAddr) Ph[pIdx] = X ? llWaitSys(pAddr, tagIn) : llWait(pAddr, tagIn);
 	__syncthreads();
 	double va = 0, vb = 0;
 	if(a.idx) va = fastVal(Ph, a.idx, ex, pl, a.rho);
 	if(b.idx) vb = fastVal(Ph, b.idx, ex, pl, b.rho);
-	if(a.idx){ Ph[a.idx] = va; if(send) fastSend(mail, a, va, stag); }
-	if(b.idx){ Ph[b.idx] = vb; if(send) fastSend(mail, b, vb, stag); }
+	if(a.idx){ Ph[a.idx] = va; if(send) fastSend<X>(mail, xBase, a, va, stag); }
+	if(b.idx){ Ph[b.idx] = vb; if(send) fastSend<X>(mail, xBase, b, vb, stag); }
 }
 // c0*: nodes of colour 0 and the halo node of colour 0 this thread receives; same for colour 1.  Half-sweep h updates
 // colour 1 (h even) or 0 (h odd) and first receives the other colour's face nodes of half-sweep h-1.
-__device__ __noinline__ void bSmoothFast(double *Ph, int ex, int pl, uint4 *mail, const uint4 *p0Addr, int p0Idx, const uint4 *p1Addr, int p1Idx,
+// X: the halo loaded from this rank's memory is not the neighbour rank's data, so the call starts with an exchange of the
+// colour-0 boundary nodes (tag seq+1) and the half-sweeps use tags seq+2 .. (the caller advances seq by 2*nCycles + 2).
+template<bool X> __device__ __noinline__ void bSmoothFast(double *Ph, int ex, int pl, uint4 *mail, uint4 *const *xBase, const uint4 *p0Addr, int p0Idx, const uint4 *p1Addr, int p1Idx,
 		FastNode a0, FastNode b0, FastNode a1, FastNode b1, int nCycles, unsigned seq, long long *pf, long long tEnter){
 	long long tW = 0;
 	if(pf){ pf[2*9] += clock64() - tEnter; pf[2*9+1] += 1; tW = clock64(); }
+	if constexpr(X){
+		seq += 1u;
+		if(a0.idx) fastSend<X>(mail, xBase, a0, Ph[a0.idx], seq);
+		if(b0.idx) fastSend<X>(mail, xBase, b0, Ph[b0.idx], seq);
+	}
 	for(int h2 = 0; h2 < nCycles; h2++){
 		const unsigned t = seq + 2u*(unsigned)h2;
-		fastHalf(Ph, ex, pl, mail, p0Addr, p0Idx, h2 > 0, t, a1, b1, t + 1u, true);
-		fastHalf(Ph, ex, pl, mail, p1Addr, p1Idx, true, t + 1u, a0, b0, t + 2u, h2 + 1 < nCycles);
+		fastHalf<X>(Ph, ex, pl, mail, xBase, p0Addr, p0Idx, X || h2 > 0, t, a1, b1, t + 1u, true);
+		fastHalf<X>(Ph, ex, pl, mail, xBase, p1Addr, p1Idx, true, t + 1u, a0, b0, t + 2u, h2 + 1 < nCycles);
 	}
 	if(pf){ pf[2*10] += clock64() - tW; pf[2*10+1] += 2*nCycles; }
 }
@@ -733,8 +809,9 @@ __device__ __noinline__ void bSmoothFast(double *Ph, int ex, int pl, uint4 *mail
 // next half-sweep copies the tagged values it was sent into its halo layer.  A slot is rewritten two half-sweeps later,
 // which needs the value its reader produces in between: the protocol is its own back-pressure.  Same arithmetic per
 // node as fGS, hence the same bits.
-__device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, double sIn, Scope &S, unsigned &seq){
+template<bool X> __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, double sIn, Scope &S, unsigned &seq){
 	ProfScope ps(*S.K, PS_GS_BIG);
+	__shared__ uint4 *xBase[6];
 	const int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2;
 	const int bid = (int)blockIdx.x - 1;
 	const bool act = bid >= 0 && bid < B.nb;
@@ -763,7 +840,19 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 			out[3] = (unsigned)(cx + B.nbx*(yp + B.nby*cz))*slots + fb[2];
 			out[4] = (unsigned)(cx + B.nbx*(cy + B.nby*zm))*slots + fb[5];
 			out[5] = (unsigned)(cx + B.nbx*(cy + B.nby*zp))*slots + fb[4];
+			if constexpr(X){
+				// a face on the sub-domain boundary of a decomposed dimension goes to the same slot of the neighbour RANK's array
+				if(threadIdx.x < 6){
+					const int f = threadIdx.x, d = f >> 1, side = f & 1;
+					const int cc = d == 0 ? cx : (d == 1 ? cy : cz), nn = d == 0 ? B.nbx : (d == 1 ? B.nby : B.nbz);
+					const bool edge = side ? cc == nn-1 : cc == 0;
+					const XDist &x = *S.X;
+					const size_t rel = (size_t)(B.mail - x.peer[x.me]);
+					xBase[f] = (edge && x.ns[d] > 1) ? x.peer[x.nbr[f]] + rel : B.mail;
+				}
+			}
 		}
+		if constexpr(X) __syncthreads();
 		// block + halo layer from global memory (periodic image), with the pending mean shift applied
 		const int ne = pl*(bz+2);
 		auto srcOf = [&](int i) -> const double* {
@@ -818,12 +907,21 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 			hidx = j + ex*(k + ey*l);
 		};
 		auto sendNode = [&](int j, int k, int l, double v, unsigned stag){
-			if(j == 1)  llStore(B.mail + out[0] + (k-1) + by*(l-1), v, stag);
-			if(j == bx) llStore(B.mail + out[1] + (k-1) + by*(l-1), v, stag);
-			if(k == 1)  llStore(B.mail + out[2] + (j-1) + bx*(l-1), v, stag);
-			if(k == by) llStore(B.mail + out[3] + (j-1) + bx*(l-1), v, stag);
-			if(l == 1)  llStore(B.mail + out[4] + (j-1) + bx*(k-1), v, stag);
-			if(l == bz) llStore(B.mail + out[5] + (j-1) + bx*(k-1), v, stag);
+			if constexpr(X){
+				if(j == 1)  llStoreSys(xBase[0] + out[0] + (k-1) + by*(l-1), v, stag);
+				if(j == bx) llStoreSys(xBase[1] + out[1] + (k-1) + by*(l-1), v, stag);
+				if(k == 1)  llStoreSys(xBase[2] + out[2] + (j-1) + bx*(l-1), v, stag);
+				if(k == by) llStoreSys(xBase[3] + out[3] + (j-1) + bx*(l-1), v, stag);
+				if(l == 1)  llStoreSys(xBase[4] + out[4] + (j-1) + bx*(k-1), v, stag);
+				if(l == bz) llStoreSys(xBase[5] + out[5] + (j-1) + bx*(k-1), v, stag);
+			} else {
+				if(j == 1)  llStore(B.mail + out[0] + (k-1) + by*(l-1), v, stag);
+				if(j == bx) llStore(B.mail + out[1] + (k-1) + by*(l-1), v, stag);
+				if(k == 1)  llStore(B.mail + out[2] + (j-1) + bx*(l-1), v, stag);
+				if(k == by) llStore(B.mail + out[3] + (j-1) + bx*(l-1), v, stag);
+				if(l == 1)  llStore(B.mail + out[4] + (j-1) + bx*(k-1), v, stag);
+				if(l == bz) llStore(B.mail + out[5] + (j-1) + bx*(k-1), v, stag);
+			}
 		};
 		if(fast){
 			// fast path (at most two nodes per thread and colour, one halo node per thread and colour): node addresses,
@@ -847,36 +945,47 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 						// a node lies on at most one face per dimension unless the block is two nodes wide, where the second
 						// face of that dimension takes a slot of its own
 						unsigned t[6]; int nt = 0;
+						constexpr unsigned FS = X ? (1u << LL_FACE_SHIFT) : 0u;       // X: the face rides in the top bits
 						if(j == 1)  t[nt++] = out[0] + (k-1) + by*(l-1);
-						if(j == bx) t[nt++] = out[1] + (k-1) + by*(l-1);
-						if(k == 1)  t[nt++] = out[2] + (j-1) + bx*(l-1);
-						if(k == by) t[nt++] = out[3] + (j-1) + bx*(l-1);
-						if(l == 1)  t[nt++] = out[4] + (j-1) + bx*(k-1);
-						if(l == bz) t[nt++] = out[5] + (j-1) + bx*(k-1);
+						if(j == bx) t[nt++] = out[1] + (k-1) + by*(l-1) + 1u*FS;
+						if(k == 1)  t[nt++] = out[2] + (j-1) + bx*(l-1) + 2u*FS;
+						if(k == by) t[nt++] = out[3] + (j-1) + bx*(l-1) + 3u*FS;
+						if(l == 1)  t[nt++] = out[4] + (j-1) + bx*(k-1) + 4u*FS;
+						if(l == bz) t[nt++] = out[5] + (j-1) + bx*(k-1) + 5u*FS;
 						if(nt > 0) n.t0 = t[0];
 						if(nt > 1) n.t1 = t[1];
 						if(nt > 2) n.t2 = t[2];
 					}
 				}
 			}
-			bSmoothFast(Ph, ex, pl, B.mail, pAddr[0], pIdx[0], pAddr[1], pIdx[1], nd[0][0], nd[0][1], nd[1][0], nd[1][1], nCycles, seq,
+			bSmoothFast<X>(Ph, ex, pl, B.mail, xBase, pAddr[0], pIdx[0], pAddr[1], pIdx[1], nd[0][0], nd[0][1], nd[1][0], nd[1][1], nCycles, seq,
 				(S.K->prof && bid == 0 && threadIdx.x == 0) ? S.K->prof : nullptr, tEnter);
-		} else
+		} else {
+		const unsigned seqG = X ? seq + 1u : seq;
+		if constexpr(X){
+			// the call starts with an exchange of the colour-0 boundary nodes (see bSmoothFast)
+			__syncthreads();
+			for(int i = threadIdx.x; i < items; i += blockDim.x){
+				int m, r, k, l; dHx.divmod(i, r, m); dBy.divmod(r, l, k); k += 1; l += 1;
+				int j = ((((1+k+l)&1) == 0) ? 1 : 2) + 2*m;
+				sendNode(j, k, l, Ph[j + ex*(k + ey*l)], seqG);
+			}
+		}
 		for(int h = 0; h < 2*nCycles; h++){
 			const int parity = (h & 1) ? 0 : 1;
-			if(h > 0){
+			if(X || h > 0){
 				// receive the other colour's face nodes of half-sweep h-1
-				const unsigned tag = seq + (unsigned)h;
+				const unsigned tag = seqG + (unsigned)h;
 				const int c = 1 - parity;
 				for(int i = threadIdx.x; i < nHalo; i += blockDim.x){
 					int slot, hidx;
 					haloNode(i, c, slot, hidx);
-					Ph[hidx] = llWait(mine + slot, tag);
+					Ph[hidx] = X ? llWaitSys(mine + slot, tag) : llWait(mine + slot, tag);
 				}
 			}
 			__syncthreads();
 			const bool send = h + 1 < 2*nCycles;
-			const unsigned stag = seq + (unsigned)h + 1u;
+			const unsigned stag = seqG + (unsigned)h + 1u;
 			// two nodes per trip: all loads before the stores (own-colour stores never alias other-colour loads)
 			for(int i = threadIdx.x; i < items; i += 2*blockDim.x){
 				double vn[2]; int id[2], jj[2], kk[2], lq[2]; bool ok[2];
@@ -900,16 +1009,17 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 				}
 			}
 		}
+		}
 		__syncthreads();
 		for(int i = threadIdx.x; i < bx*by*bz; i += blockDim.x){
 			int jl, r, kl, ll; dBx.divmod(i, r, jl); dBy.divmod(r, ll, kl);
 			bsum += Ph[(jl+1) + ex*((kl+1) + ey*(ll+1))];
 		}
 	}
-	seq += 2u*(unsigned)nCycles;
+	seq += 2u*(unsigned)nCycles + (X ? 2u : 0u);
 	const long long tTail = clock64();
 	// the 2*nCycles gBnd calls, applied once (as fGS does in batched mode), on the way back to global memory
-	double avg = S.allSum(bsum)/((double)t0*t1*t2);
+	double avg = X ? S.allSumX(bsum)/((double)t0*t1*t2*(double)S.X->R) : S.allSum(bsum)/((double)t0*t1*t2);
 	if(act)
 		for(int i = threadIdx.x; i < bx*by*bz; i += blockDim.x){
 			int jl, r, kl, ll; dBx.divmod(i, r, jl); dBy.divmod(r, ll, kl);
@@ -922,7 +1032,7 @@ __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, doubl
 // gBnd(rho) = gNeutralizeGrid (src/grid.c:730-779) ahead of a block-resident smoother call: every block CTA handles the
 // rho of its own nodes with the thread <-> node mapping of bGS's fast path, so the smoother reads what the same thread
 // wrote and no grid barrier is needed after the subtraction (readers in other CTAs come after the smoother's barriers)
-__device__ __noinline__ void bNeutRho(const Lvl &L, const BLvl &B, Scope &S){
+template<bool X> __device__ __noinline__ void bNeutRho(const Lvl &L, const BLvl &B, Scope &S){
 	ProfScope psn(*S.K, 28);
 	const int bid = (int)blockIdx.x - 1;
 	const bool act = bid >= 0 && bid < B.nb;
@@ -947,7 +1057,8 @@ __device__ __noinline__ void bNeutRho(const Lvl &L, const BLvl &B, Scope &S){
 		#pragma unroll
 		for(int u = 0; u < 4; u++) acc += r[u];
 	}
-	const double avg = S.allSum(acc)/((double)(L.s0-2)*(L.s1-2)*(L.s2-2));
+	const double nt = (double)(L.s0-2)*(L.s1-2)*(L.s2-2);
+	const double avg = X ? S.allSumX(acc)/(nt*(double)S.X->R) : S.allSum(acc)/nt;
 	#pragma unroll
 	for(int u = 0; u < 4; u++) if(g[u] >= 0) L.rho[g[u]] = r[u] - avg;
 }
@@ -955,21 +1066,84 @@ __device__ __noinline__ void bNeutRho(const Lvl &L, const BLvl &B, Scope &S){
 #include "mgrows.cuh"
 namespace pinc {
 
-__device__ __noinline__ void fDown(const MgPlan &P, int q, Scope &S, unsigned &seq){
+// ---- hybrid multi-rank solve: the distributed levels --------------------------------------------------------------------
+// Ghost FACES of a rank-local array (all a 7-point stencil reads): a non-decomposed dimension wraps locally, a decomposed
+// one travels through the plane slots of the neighbours' arenas.  Two plane sets alternate; a set is rewritten two calls
+// later, after the neighbour has sent its next planes, i.e. after the grid barrier that ended its reading of this set.
+__device__ __noinline__ void xHalo(double *v, int s0, int s1, int s2, Scope &S){
+	const XDist &x = *S.X;
+	const unsigned tag = ++S.xHalo, set = tag & 1u;
+	const int t[3] = {s0-2, s1-2, s2-2};
+	uint4 *mine = x.peer[x.me] + x.offPlane + (size_t)set*6*x.planeCap;
+	for(int pass = 0; pass < 2; pass++)
+		for(int d = 0; d < 3; d++){
+			const bool dec = x.ns[d] > 1;
+			if(pass == 1 && !dec) continue;
+			const int ta = d == 0 ? t[1] : t[0], tb = d == 2 ? t[1] : t[2], n = ta*tb;
+			uint4 *toLo = x.peer[x.nbr[2*d]] + x.offPlane + (size_t)(set*6 + 2*d+1)*x.planeCap;      // my lower layer is the lower neighbour's upper ghost
+			uint4 *toHi = x.peer[x.nbr[2*d+1]] + x.offPlane + (size_t)(set*6 + 2*d)*x.planeCap;
+			for(long i = S.tid(); i < n; i += S.nthr()){
+				const int a = (int)(i % ta) + 1, b = (int)(i / ta) + 1;
+				long gLo, gHi, hLo, hHi;          // boundary layers, ghost layers
+				if(d == 0){ gLo = ix(1,a,b,s0,s1); gHi = ix(t[0],a,b,s0,s1); hLo = ix(0,a,b,s0,s1); hHi = ix(t[0]+1,a,b,s0,s1); }
+				else if(d == 1){ gLo = ix(a,1,b,s0,s1); gHi = ix(a,t[1],b,s0,s1); hLo = ix(a,0,b,s0,s1); hHi = ix(a,t[1]+1,b,s0,s1); }
+				else { gLo = ix(a,b,1,s0,s1); gHi = ix(a,b,t[2],s0,s1); hLo = ix(a,b,0,s0,s1); hHi = ix(a,b,t[2]+1,s0,s1); }
+				if(pass == 0){
+					const double vLo = ldg2(v + gLo), vHi = ldg2(v + gHi);
+					if(dec){ llStoreSys(toLo + i, vLo, tag); llStoreSys(toHi + i, vHi, tag); }
+					else { v[hHi] = vLo; v[hLo] = vHi; }
+				} else {
+					v[hLo] = llWaitSys(mine + (size_t)(2*d)*x.planeCap + i, tag);
+					v[hHi] = llWaitSys(mine + (size_t)(2*d+1)*x.planeCap + i, tag);
+				}
+			}
+		}
+	S.sync();
+}
+
+// X: level q is distributed (hybrid multi-rank solve); its coarse level q+1 is the first replicated one (qDist = q+1)
+template<bool X = false> __device__ __noinline__ void fDown(const MgPlan &P, int q, Scope &S, unsigned &seq){
 	const Lvl &L = P.L[q], &C = P.L[q+1];
 	const bool blk = P.B[q].on && !S.single && P.nPre > 0;
+	if constexpr(X){
+		if(P.B[q].on == 1) bNeutRho<true>(L, P.B[q], S); else fNeutralize<true>(L.rho, L.s0, L.s1, L.s2, S);
+		bGS<true>(L, P.B[q], P.nPre, 0.0, S, S.xMail);
+		xHalo(L.phi, L.s0, L.s1, L.s2, S);
+	} else {
 	if(blk && P.B[q].on == 3){ if(P.B[q].bx == 32) rNeutRho<16>(L, P.B[q], S); else rNeutRho<8>(L, P.B[q], S); }
-	else if(blk && P.B[q].on == 1) bNeutRho(L, P.B[q], S); else fNeutralize(L.rho, L.s0, L.s1, L.s2, S);
+	else if(blk && P.B[q].on == 1) bNeutRho<false>(L, P.B[q], S); else fNeutralize(L.rho, L.s0, L.s1, L.s2, S);
 	if(blk && P.B[q].on == 3){ if(P.B[q].bx == 32) rGS<16>(L, P.B[q], P.nPre, 0.0, S, seq); else rGS<8>(L, P.B[q], P.nPre, 0.0, S, seq); }
-	else if(blk) bGS(L, P.B[q], P.nPre, 0.0, S, seq); else fGS(L, P.nPre, 0.0, P.exact, S);
+	else if(blk) bGS<false>(L, P.B[q], P.nPre, 0.0, S, seq); else fGS(L, P.nPre, 0.0, P.exact, S);
+	}
 	{
 		ProfScope psr(*S.K, S.single ? 27 : 29);
 		int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2; long nt = (long)t0*t1*t2;
 		for(long i = S.tid(); i < nt; i += S.nthr()){ int j,k,l; truePoint(i,t0,t1,j,k,l);
-			L.res[ix(j,k,l,L.s0,L.s1)] = resPoint<true>(L.phi, L.rho, j, k, l, L.s0, L.s1, L.s2); }
+			L.res[ix(j,k,l,L.s0,L.s1)] = resPoint<!X>(L.phi, L.rho, j, k, l, L.s0, L.s1, L.s2); }
 		S.sync();
 	}
-	{
+	if constexpr(X){
+		// restriction of my sub-domain, gathered into every rank's replicated rho(q+1): each coarse value goes into slot
+		// (my rank, node) of every rank's gather buffer; then every rank unpacks all R segments into the global array
+		xHalo(L.res, L.s0, L.s1, L.s2, S);
+		ProfScope psr(*S.K, 30);
+		const XDist &x = *S.X;
+		const unsigned tag = ++S.xGath, set = tag & 1u;
+		const int c0 = (L.s0-2)/2, c1 = (L.s1-2)/2, c2 = (L.s2-2)/2; const long nc = (long)c0*c1*c2;
+		for(long i = S.tid(); i < nc; i += S.nthr()){
+			int J,K,Lz; truePoint(i,c0,c1,J,K,Lz);
+			const double v = restrictPoint<false>(L.res, J, K, Lz, L.s0, L.s1, L.s2);
+			for(int r = 0; r < x.R; r++) llStoreSys(x.peer[r] + x.offGath + (size_t)set*x.gathCap + (size_t)x.me*nc + i, v, tag);
+		}
+		const uint4 *in = x.peer[x.me] + x.offGath + (size_t)set*x.gathCap;
+		for(long ii = S.tid(); ii < nc*x.R; ii += S.nthr()){
+			const int r = (int)(ii / nc); const long i = ii - (long)r*nc;
+			int J,K,Lz; truePoint(i,c0,c1,J,K,Lz);
+			const int rx = r % x.ns[0], rr = r / x.ns[0], ry = rr % x.ns[1], rz = rr / x.ns[1];
+			C.rho[ix(rx*c0 + J, ry*c1 + K, rz*c2 + Lz, C.s0, C.s1)] = llWaitSys(in + ii, tag);
+		}
+		S.sync();
+	} else {
 		ProfScope psr(*S.K, S.single ? 27 : 30);
 		int t0 = C.s0-2, t1 = C.s1-2, t2 = C.s2-2; long nt = (long)t0*t1*t2;
 		for(long i = S.tid(); i < nt; i += S.nthr()){ int J,K,Lz; truePoint(i,t0,t1,J,K,Lz);
@@ -984,23 +1158,30 @@ __device__ __noinline__ void fBottom(const MgPlan &P, Scope &S){
 	if(P.exact || P.nCoarse <= 0) fNeutralize(L.phi, L.s0, L.s1, L.s2, S);      // batched mode: fGS just ended with this gBnd
 }
 // res(q) := P(phi(q+1)); phi(q) += res(q); gBnd; post-smooth; gBnd
-__device__ __noinline__ void fUp(const MgPlan &P, int q, Scope &S, unsigned &seq){
+template<bool X = false> __device__ __noinline__ void fUp(const MgPlan &P, int q, Scope &S, unsigned &seq){
 	const Lvl &L = P.L[q], &C = P.L[q+1];
 	int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2; long nt = (long)t0*t1*t2;
 	const long long tUp = clock64();
 	double acc = 0;
+	// X: the coarse level is the replicated global one; my fine node (j,k,l) is global node (ox+j, oy+k, oz+l)
+	const int ox = X ? S.X->sub[0]*t0 : 0, oy = X ? S.X->sub[1]*t1 : 0, oz = X ? S.X->sub[2]*t2 : 0;
 	for(long i = S.tid(); i < nt; i += S.nthr()){
 		int j,k,l; truePoint(i,t0,t1,j,k,l); long g = ix(j,k,l,L.s0,L.s1);
-		double p = prolPoint(C.phi, j, k, l, C.s0, C.s1, C.s2);
+		double p = prolPoint(C.phi, ox+j, oy+k, oz+l, C.s0, C.s1, C.s2);
 		L.res[g] = p;
 		double v = ldg2(L.phi + g); v += p;
 		L.phi[g] = v;
 		acc += v;
 	}
+	if constexpr(X){
+		double avg = S.allSumX(acc)/((double)nt*(double)S.X->R);
+		bGS<true>(L, P.B[q], P.nPost, avg, S, S.xMail);
+		return;
+	}
 	double avg = S.allSum(acc)/(double)nt;
 	if(S.K->prof && blockIdx.x == 0 && threadIdx.x == 0 && !S.single){ S.K->prof[2*31] += clock64() - tUp; S.K->prof[2*31+1] += 1; }
 	if(P.B[q].on == 3 && !S.single && P.nPost > 0){ if(P.B[q].bx == 32) rGS<16>(L, P.B[q], P.nPost, avg, S, seq); else rGS<8>(L, P.B[q], P.nPost, avg, S, seq); }
-	else if(P.B[q].on && !S.single && P.nPost > 0) bGS(L, P.B[q], P.nPost, avg, S, seq); else fGS(L, P.nPost, avg, P.exact, S);
+	else if(P.B[q].on && !S.single && P.nPost > 0) bGS<false>(L, P.B[q], P.nPost, avg, S, seq); else fGS(L, P.nPost, avg, P.exact, S);
 	if(P.exact || P.nPost <= 0) fNeutralize(L.phi, L.s0, L.s1, L.s2, S);
 }
 __device__ __noinline__ void fGhosts(double *v, int s0, int s1, int s2, Scope &S){
@@ -1084,7 +1265,7 @@ __device__ __noinline__ void smallPyramid(const MgPlan &P, CK &K){
 
 // EXACT (gBnd after every half-sweep, modes 1 and 3) is a compile-time parameter only to keep the code of the default
 // kernel small: the persistent kernel is latency-bound and sensitive to its instruction footprint
-template<bool EXACT> __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(MgPlan P){
+template<bool EXACT, bool DIST> __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(const __grid_constant__ MgPlan P){
 	__shared__ double sh[18];
 	__shared__ double red[40];
 	CK K{ cg::this_cluster(), (int)blockIdx.x, 1, mgS, red, 0, P.prof, P.offZ };
@@ -1101,6 +1282,8 @@ template<bool EXACT> __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(M
 		__syncthreads();
 	}
 	Scope Sg; Sg.single = false; Sg.bar = P.bar; Sg.partial = P.partial; Sg.flip = 0; Sg.sh = sh; Sg.gen = 0;
+	Sg.X = &P.X; Sg.xMail = Sg.xSum = Sg.xHalo = Sg.xGath = 0;
+	if constexpr(DIST){ Sg.xMail = P.X.ctr[0]; Sg.xSum = P.X.ctr[1]; Sg.xHalo = P.X.ctr[2]; Sg.xGath = P.X.ctr[3]; }      // rewritten after the last grid barrier of this launch
 	if(threadIdx.x == 0) Sg.gen = P.barBase;            // arrival count at kernel start (host-tracked)
 	Sg.K = &K;
 	Scope S1 = Sg; S1.single = true;
@@ -1118,7 +1301,10 @@ template<bool EXACT> __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(M
 		seq = 0;
 	}
 	while(barRes > P.tol && cycles < P.maxCycles){
-		for(int q = 0; q <= b && q < qs; q++){ if(q < b) fDown(P, q, Sg, seq); else fBottom(P, Sg); }
+		for(int q = 0; q <= b && q < qs; q++){
+			if(DIST && q < P.X.qDist) fDown<DIST>(P, q, Sg, seq);
+			else if(q < b) fDown(P, q, Sg, seq); else fBottom(P, Sg);
+		}
 		if(qs <= b){
 			if(blockIdx.x == 0){
 				ProfScope pss(K, PS_LEVEL0);
@@ -1133,20 +1319,21 @@ template<bool EXACT> __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(M
 			}
 			Sg.sync();
 		}
-		for(int q = (qs <= b ? qs : b) - 1; q >= 0; q--) fUp(P, q, Sg, seq);
+		for(int q = (qs <= b ? qs : b) - 1; q >= 0; q--){ if(DIST && q < P.X.qDist) fUp<DIST>(P, q, Sg, seq); else fUp(P, q, Sg, seq); }
 		// mgSolveRaw :1700-1704: residual, square in place, true-grid sum, RMS
 		const Lvl &L = P.L[0];
 		ProfScope psn(K, PS_NORM);
 		int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2; long nt = (long)t0*t1*t2;
 		double acc = 0;
+		if constexpr(DIST) xHalo(L.phi, L.s0, L.s1, L.s2, Sg);
 		for(long i = Sg.tid(); i < nt; i += Sg.nthr()){
 			int j,k,l; truePoint(i,t0,t1,j,k,l);
-			double r = resPoint<true>(L.phi, L.rho, j, k, l, L.s0, L.s1, L.s2);
+			double r = resPoint<!DIST>(L.phi, L.rho, j, k, l, L.s0, L.s1, L.s2);
 			r = r*r;
 			L.res[ix(j,k,l,L.s0,L.s1)] = r;
 			acc += r;
 		}
-		barRes = Sg.allSum(acc);
+		barRes = DIST ? Sg.allSumX(acc) : Sg.allSum(acc);
 		barRes /= P.totTrue;
 		barRes = sqrt(barRes);
 		if(blockIdx.x == 0 && threadIdx.x == 0 && cycles < 250) P.hist[1+cycles] = barRes;
@@ -1168,11 +1355,15 @@ template<bool EXACT> __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(M
 		Sg.sync();
 	}
 	for(int q = 0; q <= b; q++){
+		if(DIST && q < P.X.qDist) continue;          // rank-local levels: the host fills their ghost layers from the neighbours (hybridSolve)
 		fGhosts(P.L[q].phi, P.L[q].s0, P.L[q].s1, P.L[q].s2, Sg);
 		fGhosts(P.L[q].rho, P.L[q].s0, P.L[q].s1, P.L[q].s2, Sg);
 		fGhosts(P.L[q].res, P.L[q].s0, P.L[q].s1, P.L[q].s2, Sg);
 	}
-	if(blockIdx.x == 0 && threadIdx.x == 0) *P.seqWord = seqEnd;
+	if(blockIdx.x == 0 && threadIdx.x == 0){
+		*P.seqWord = seqEnd;
+		if constexpr(DIST){ P.X.ctr[0] = Sg.xMail; P.X.ctr[1] = Sg.xSum; P.X.ctr[2] = Sg.xHalo; P.X.ctr[3] = Sg.xGath; P.hist[252] = (double)Sg.xMail; }
+	}
 }
 
 int g_mgMode = -1;
@@ -1234,9 +1425,52 @@ static bool planBlocks(int t0, int t1, int t2, int maxBlocks, long smemCap, BLvl
 	return B.on != 0;
 }
 
-static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, double tol, int maxCycles, int exact){
+// arena of the hybrid multi-rank solve: one allocation per rank, mapped into every other rank (Transport::peerAlloc)
+struct XArena { char *mine = nullptr; std::vector<char*> peers; size_t bytes = 0; int share = 1; };
+static void freeXArena(Ctx *c){
+	XArena *A = (XArena*)c->mgXArena;
+	if(!A) return;
+	if(A->mine && c->tp) c->tp->peerFree(c, A->mine, A->peers);
+	delete A;
+	c->mgXArena = nullptr;
+}
+// collective: every rank asks for the same size (same plan)
+static XArena *ensureXArena(Ctx *c, size_t bytes){
+	XArena *A = (XArena*)c->mgXArena;
+	if(A && A->bytes >= bytes) return A;
+	int share = A ? A->share : 0;
+	if(A){ streamSync(c); c->tp->barrier(c); freeXArena(c); }
+	A = new XArena();
+	bytes += bytes/4;
+	if(!c->tp->peerAlloc(c, bytes, &A->mine, A->peers)){ delete A; return nullptr; }
+	A->bytes = bytes;
+	if(!share){
+		// ranks sharing this rank's device (thread ranks of the tests): their persistent kernels must be co-resident
+		std::vector<long> dev(c->size);
+		long mine = c->device;
+		c->tp->allgatherLong(c, &mine, 1, dev.data());
+		for(int r = 0; r < c->size; r++) if(dev[r] == mine && !strcmp(c->tp->name(), "threads")) share++;
+		if(share < 1) share = 1;
+	}
+	A->share = share;
+	c->mgXArena = A;
+	c->mgXTagHigh = 0;
+	return A;
+}
+
+// XH: hybrid multi-rank solve (levels < XH->qDist are this rank's sub-domain, the others the replicated global levels);
+// returns false if the distributed levels cannot be smoothed block-resident (nothing launched, nothing changed)
+static bool fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, double tol, int maxCycles, int exact, const XDist *XH = nullptr){
 	MgPlan P{};
 	int nL = mgRho->nLevels;
+	const int qDist = XH ? XH->qDist : 0;
+	int share = 1;
+	if(XH){
+		if(exact || nL < 2 || qDist != 1) return false;
+		XArena *A0 = ensureXArena(c, 4096);
+		if(!A0) return false;
+		share = A0->share;
+	}
 	P.nLevels = nL; P.nPre = mgRho->nPreSmooth; P.nPost = mgRho->nPostSmooth; P.nCoarse = mgRho->nCoarseSolve;
 	P.qSmall = nL; P.offZ = -1;
 	double work = 0;
@@ -1287,11 +1521,14 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 		if(!ok) smem = 0;
 	}
 	DevGrid *r0 = devGrid(c, mgRho->grids[0]);
-	P.totTrue = (double)trueCount(r0);
-	int grid = P.qSmall == 0 ? 1 : c->numSMs;
+	P.totTrue = (double)trueCount(r0)*(XH ? XH->R : 1);
+	int grid = P.qSmall == 0 ? 1 : c->numSMs/share;
+	if(XH && (P.qSmall < qDist || grid < 10)) return false;          // a distributed level must be a grid-wide one
 	// block-resident smoothing of the grid-wide levels (batched gBnd only; CTA 0 is left to the small levels)
 	P.seqWord = c->d_bar + 16;
 	static const bool blocksOff = getenv("PINC_B200_MG_BLOCKS") && atoi(getenv("PINC_B200_MG_BLOCKS")) == 0;
+	size_t xMailOff[MG_MAXLEV] = {0}, xSlots = 0;
+	if(XH && (blocksOff || P.nPre <= 0 || P.nPost <= 0)) return false;
 	if(!exact && grid > 8 && !blocksOff){
 		int smemOptin = 0;
 		PINC_CUDA(cudaDeviceGetAttribute(&smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
@@ -1300,8 +1537,18 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 		for(int q = 0; q < P.qSmall && q < nL; q++){
 			DevGrid *r = devGrid(c, mgRho->grids[q]);
 			BLvl &B = P.B[q];
-			if(!planBlocks(r->tsize[0], r->tsize[1], r->tsize[2], grid-1, smemCap, B)) continue;
-			if(B.bx > 1000 || B.by > 1000 || B.bz > 1000){ B.on = 0; continue; }        // packed node coordinates in bGS
+			if(!planBlocks(r->tsize[0], r->tsize[1], r->tsize[2], grid-1, smemCap, B)){ if(q < qDist) return false; continue; }
+			if(B.bx > 1000 || B.by > 1000 || B.bz > 1000){ B.on = 0; if(q < qDist) return false; continue; }        // packed node coordinates in bGS
+			if(q < qDist){
+				// distributed level of a hybrid solve: always block-resident (bGS<true>), mailboxes in the peer-mapped arena
+				if((B.bx/2)*B.by*B.bz > 2*MG_BLOCK || B.by*B.bz + B.bx*B.bz + B.bx*B.by > MG_BLOCK) B.on = 2;
+				B.rows = 1;
+				xMailOff[q] = xSlots;
+				xSlots += (size_t)B.nb*2*(B.by*B.bz + B.bx*B.bz + B.bx*B.by);
+				size_t need = (size_t)(B.offRho >= 0 ? B.offRho + B.bx*B.by*B.bz : (B.bx+2)*(B.by+2)*(B.bz+2))*sizeof(double);
+				if(need > blockSmem) blockSmem = need;
+				continue;
+			}
 			{	// big blocks: one x-row per thread, colour-separated rows (mgrows.cuh); $PINC_B200_MG_ROWMODE=0 off, 2 also for small blocks
 				if(g_mgRowMode < 0) g_mgRowMode = getenv("PINC_B200_MG_ROWMODE") ? atoi(getenv("PINC_B200_MG_ROWMODE")) : 1;
 				const int rowMode = g_mgRowMode;
@@ -1333,7 +1580,7 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 				PINC_CUDA(cudaMalloc(&c->d_mgMail, c->mgMailBytes));
 				PINC_CUDA(cudaMemsetAsync(c->d_mgMail, 0, c->mgMailBytes, c->stream));
 			}
-			for(int q = 0; q < P.qSmall && q < nL; q++) if(P.B[q].on) P.B[q].mail = (uint4*)c->d_mgMail + mailOff[q];
+			for(int q = qDist; q < P.qSmall && q < nL; q++) if(P.B[q].on) P.B[q].mail = (uint4*)c->d_mgMail + mailOff[q];
 			{	// colour-separated rho copies of the row-smoothed levels
 				size_t need = 0, off[MG_MAXLEV] = {0};
 				for(int q = 0; q < P.qSmall && q < nL; q++) if(P.B[q].on == 3){ off[q] = need; need += (size_t)P.B[q].nb*P.B[q].bx*P.B[q].by*P.B[q].bz; }
@@ -1345,15 +1592,39 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 				for(int q = 0; q < P.qSmall && q < nL; q++) if(P.B[q].on == 3) P.B[q].rhoS = (double*)c->d_mgRhoS + off[q];
 			}
 			P.mailAll = (uint4*)c->d_mgMail; P.mailSlots = c->mgMailBytes/sizeof(uint4);
-			if(blockSmem > smem) smem = blockSmem;
 		}
+		if(blockSmem > smem) smem = blockSmem;
 	}
+	if(XH){
+		// arena layout in 16-byte slots: [16 counters][2 x XD_MAXR sums][2 x 6 planes][2 x R gather segments][mailboxes of the distributed levels]
+		for(int q = 0; q < qDist; q++) if(!P.B[q].on) return false;
+		P.X = *XH;
+		P.X.on = 1;
+		size_t planeCap = 0;
+		for(int q = 0; q < qDist; q++){
+			DevGrid *r = devGrid(c, mgRho->grids[q]);
+			const size_t t0 = r->tsize[0], t1 = r->tsize[1], t2 = r->tsize[2];
+			planeCap = std::max(planeCap, std::max(t0*t1, std::max(t0*t2, t1*t2)));
+		}
+		DevGrid *rl = devGrid(c, mgRho->grids[qDist-1]);
+		const size_t nc = (size_t)(rl->tsize[0]/2)*(rl->tsize[1]/2)*(rl->tsize[2]/2);
+		P.X.offSum = 16; P.X.offPlane = P.X.offSum + 2*XD_MAXR; P.X.planeCap = (unsigned)planeCap;
+		P.X.offGath = P.X.offPlane + 12*(unsigned)planeCap; P.X.gathCap = (unsigned)(nc*XH->R);
+		const size_t offMail = (size_t)P.X.offGath + 2*(size_t)P.X.gathCap;
+		const size_t slots = offMail + xSlots;
+		if(slots >= (1u << LL_FACE_SHIFT)) return false;
+		XArena *A = ensureXArena(c, slots*sizeof(uint4));
+		if(!A) return false;
+		for(int r = 0; r < XH->R; r++) P.X.peer[r] = (uint4*)A->peers[r];
+		P.X.ctr = (unsigned*)A->mine;
+		for(int q = 0; q < qDist; q++) P.B[q].mail = (uint4*)A->mine + offMail + xMailOff[q];
+	}
+	const void *kern = XH ? (const void*)k_mg_solve<false,true> : exact ? (const void*)k_mg_solve<true,false> : (const void*)k_mg_solve<false,false>;
 	{	// one high-water mark for the kernel's dynamic shared memory
-		size_t &attrSet = c->mgAttrSmem[exact ? 1 : 0];       // per context: the attribute belongs to the device
-		const void *kern = exact ? (const void*)k_mg_solve<true> : (const void*)k_mg_solve<false>;
+		size_t &attrSet = c->mgAttrSmem[XH ? 2 : exact ? 1 : 0];       // per context: the attribute belongs to the device
 		if(smem > attrSet){
 			if(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) attrSet = smem;
-			else { cudaGetLastError(); for(int q = 0; q < nL; q++) P.B[q].on = 0; P.smemSmall = 0; P.pyramid = 0; smem = 0; }
+			else { cudaGetLastError(); if(XH) return false; for(int q = 0; q < nL; q++) P.B[q].on = 0; P.smemSmall = 0; P.pyramid = 0; smem = 0; }
 		}
 	}
 	P.partial = partialBuffer(c, 2L*grid);
@@ -1364,13 +1635,23 @@ static void fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 	P.hist = c->d_mgHist;
 	P.prof = (long long*)mgProfBuffer(c);
 	void *args[] = { &P };
+	// rank threads sharing a device: every allocation above may synchronise the device, so all of them launch together
+	if(XH && share > 1){ streamSync(c); c->tp->barrier(c); }
 	{
 		LaunchScope ls(c, K_MGFUSED, work);
-		PINC_CUDA(cudaLaunchCooperativeKernel(exact ? (void*)k_mg_solve<true> : (void*)k_mg_solve<false>, dim3(grid), dim3(MG_BLOCK), args, smem, c->stream));
+		if(XH && share > 1){
+			// (a cooperative launch only adds the co-residency check, which does not know about the other ranks' kernels)
+			k_mg_solve<false,true><<<dim3(grid), dim3(MG_BLOCK), smem, c->stream>>>(P);
+			PINC_CUDA(cudaGetLastError());
+		} else
+			PINC_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(MG_BLOCK), args, smem, c->stream));
 	}
 	PINC_CUDA(cudaMemcpyAsync(c->h_mgHist, c->d_mgHist, 256*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	c->mgHistPending = true;
 	c->mgCheckPending = true; c->mgTol = tol; c->mgMaxCycles = maxCycles;
+	c->mgXPending = XH != nullptr;
+	if(XH && share > 1){ streamSync(c); c->tp->barrier(c); }
+	return true;
 }
 
 // All-reduce of one double over peer memory (gNeutralizeGrid, residual norm): block-reduce the partial sums, store the
@@ -1577,8 +1858,9 @@ static bool replicaEligible(Ctx *c, Multigrid *mgRho, const MpiInfo *m){
 	return nGlobal <= (1L << 24);          // 16 M nodes = 128 MB per array: far below what one GPU holds, and still L2-friendly
 }
 static void solveSingle(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, double tol, int maxCycles);
-static void replicaSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *m, double tol, int maxCycles){
-	const int nL = mgRho->nLevels, R = m->mpiSize, me = m->mpiRank;
+// the replicated global hierarchy of a solver (created on first use, rebuilt when the shapes change)
+static GlobalMg *globalMgFor(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, const MpiInfo *m){
+	const int nL = mgRho->nLevels, R = m->mpiSize;
 	const Grid *g0 = mgRho->grids[0];
 	GlobalMg *G = nullptr;
 	auto it = c->mgGlobal.find(mgRho);
@@ -1602,39 +1884,45 @@ static void replicaSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *
 		PINC_CUDA(cudaMalloc(&G->d_pack, (size_t)seg*R*sizeof(double)));
 		c->mgGlobal[mgRho] = G;
 	}
-	Multigrid *gRho = G->solver->mgRho, *gPhi = G->solver->mgPhi, *gRes = G->solver->mgRes;
-	// 1. pack my true nodes: rho(0), phi(0..L-1)
+	return G;
+}
+// every rank's true nodes of rho(0) (if withRho) and of phi(qFirst .. L-1) into the global hierarchy of every rank: pack,
+// ONE grouped exchange, unpack
+static void gatherGlobal(Ctx *c, GlobalMg *G, Multigrid *mgRho, Multigrid *mgPhi, const MpiInfo *m, bool withRho, int qFirst){
+	const int nL = mgRho->nLevels, R = m->mpiSize, me = m->mpiRank;
+	Multigrid *gRho = G->solver->mgRho, *gPhi = G->solver->mgPhi;
 	double *mine = G->d_pack + (long)me*G->seg;
 	long off = 0;
-	std::vector<long> segOff(nL + 1);
+	std::vector<long> segOff(nL + 1, -1);
 	for(int q = -1; q < nL; q++){
+		if(q < 0 ? !withRho : q < qFirst) continue;
 		DevGrid *g = devGrid(c, q < 0 ? mgRho->grids[0] : mgPhi->grids[q]);
 		long nt = trueCount(g);
 		segOff[q+1] = off;
 		PINC_LAUNCH(c, K_GRIDOP, 16.0*nt, (k_rep_pack<<<tGrid(c,nt),256,0,c->stream>>>(g->d, g->size[0], g->size[1], g->tsize[0], g->tsize[1], g->tsize[2], mine + off)));
 		off += nt;
 	}
-	// 2. everybody's segment to everybody
+	if(!off) return;
 	std::vector<Msg> sends, recvs;
 	for(int r = 0; r < R; r++){
 		if(r == me) continue;
-		sends.push_back(Msg{ r, 7100, (void*)mine, (size_t)G->seg*sizeof(double) });
-		recvs.push_back(Msg{ r, 7100, (void*)(G->d_pack + (long)r*G->seg), (size_t)G->seg*sizeof(double) });
+		sends.push_back(Msg{ r, 7100, (void*)mine, (size_t)off*sizeof(double) });
+		recvs.push_back(Msg{ r, 7100, (void*)(G->d_pack + (long)r*G->seg), (size_t)off*sizeof(double) });
 	}
 	c->tp->exchange(c, sends, recvs);
-	// 3. assemble the global rho(0) and phi(q)
 	for(int q = -1; q < nL; q++){
+		if(segOff[q+1] < 0) continue;
 		DevGrid *loc = devGrid(c, q < 0 ? mgRho->grids[0] : mgPhi->grids[q]);
 		DevGrid *glo = devGrid(c, q < 0 ? gRho->grids[0] : gPhi->grids[q]);
 		long nT = trueCount(glo);
 		PINC_LAUNCH(c, K_GRIDOP, 16.0*nT, (k_rep_unpack<<<tGrid(c,nT),256,0,c->stream>>>(glo->d, glo->size[0], glo->size[1], G->d_pack, G->seg, segOff[q+1],
 			loc->tsize[0], loc->tsize[1], loc->tsize[2], G->ns[0], G->ns[1], G->ns[2])));
 	}
-	// 4. the global problem, redundantly on every rank
-	solveSingle(c, gRho, gPhi, gRes, tol, maxCycles);
-	const int path = c->mgLastPath + 4;
-	// 5. my sub-domain of every level of phi, rho and res, ghost layers included
-	for(int q = 0; q < nL; q++){
+}
+// my sub-domain of levels qFirst .. L-1 of the global phi, rho and res, ghost layers included
+static void extractLocal(Ctx *c, GlobalMg *G, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *m, int qFirst){
+	Multigrid *gRho = G->solver->mgRho, *gPhi = G->solver->mgPhi, *gRes = G->solver->mgRes;
+	for(int q = qFirst; q < mgRho->nLevels; q++){
 		Multigrid *locs[3] = {mgPhi, mgRho, mgRes}, *glos[3] = {gPhi, gRho, gRes};
 		for(int a = 0; a < 3; a++){
 			DevGrid *loc = devGrid(c, locs[a]->grids[q]), *glo = devGrid(c, glos[a]->grids[q]);
@@ -1643,8 +1931,71 @@ static void replicaSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *
 				m->subdomain[0]*loc->tsize[0], m->subdomain[1]*loc->tsize[1], m->subdomain[2]*loc->tsize[2])));
 		}
 	}
+}
+static void replicaSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *m, double tol, int maxCycles){
+	GlobalMg *G = globalMgFor(c, mgRho, mgPhi, m);
+	gatherGlobal(c, G, mgRho, mgPhi, m, true, 0);
+	// the global problem, redundantly on every rank
+	solveSingle(c, G->solver->mgRho, G->solver->mgPhi, G->solver->mgRes, tol, maxCycles);
+	const int path = c->mgLastPath + 4;
+	extractLocal(c, G, mgRho, mgPhi, mgRes, m, 0);
 	c->mgLastPath = path;
 }
+
+// =================================================================================================
+// multi-rank solves, hybrid: the finest level distributed, the coarser ones replicated
+// =================================================================================================
+// Replicating the whole solve makes every GPU sweep the whole global finest level, which no longer fits the SMs' shared
+// memory (8 ranks: 128^3, 944 us per V-cycle).  Here every rank keeps what it owns anyway - its sub-domain of the finest
+// level - and smooths it with the block-resident smoother of the single-GPU kernel; the faces of blocks on a sub-domain
+// boundary go into the NEIGHBOUR RANK'S mailboxes over NVLink with the same tagged 16-byte stores as inside one GPU
+// (st.relaxed.sys, the data is its own flag: no fence, no flag word, no NCCL call).  The restricted residual is gathered
+// into every rank's copy of the next level (same slots), and from there down the hierarchy is the replicated global one:
+// those levels are latency-bound, so solving them redundantly costs nothing, and the prolongation back reads the local
+// copy.  gBnd's means and the residual norm are sums over all ranks, added in rank order (identical bits everywhere).
+// One persistent kernel per rank and solve (k_mg_solve<false,true>); the ranks only meet in those slots.
+int g_mgHybrid = -1;          // 1 (default): hybrid whenever it applies; 0: replicate the whole solve; from $PINC_B200_MG_HYBRID
+static bool hybridSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *m, double tol, int maxCycles){
+	if(g_mgHybrid < 0) g_mgHybrid = (getenv("PINC_B200_MG_HYBRID") && atoi(getenv("PINC_B200_MG_HYBRID")) == 0) ? 0 : 1;
+	if(!g_mgHybrid || m->mpiSize > XD_MAXR) return false;
+	const int nL = mgRho->nLevels;
+	const Grid *g0 = mgRho->grids[0];
+	for(int d = 1; d < 4; d++) if(g0->trueSize[d] < 4 || (g0->trueSize[d] & 3)) return false;      // blocks with even edges on level 0, even level 1
+	if(c->mgXPending){ streamSync(c); c->mgXPending = false; }
+	if(c->mgXTagHigh > 3.0e9){
+		// the 32-bit tags are about to wrap (identical on every rank): back to the initial state, collectively
+		XArena *A = (XArena*)c->mgXArena;
+		c->tp->barrier(c);
+		if(A){ PINC_CUDA(cudaMemsetAsync(A->mine, 0, A->bytes, c->stream)); streamSync(c); }
+		c->tp->barrier(c);
+		c->mgXTagHigh = 0;
+	}
+	XDist X{};
+	X.qDist = 1; X.R = m->mpiSize; X.me = m->mpiRank;
+	for(int d = 0; d < 3; d++){ X.ns[d] = m->nSubdomains[d]; X.sub[d] = m->subdomain[d]; }
+	for(int d = 0; d < 3; d++){ X.nbr[2*d] = dimNb(m, d, -1); X.nbr[2*d+1] = dimNb(m, d, +1); }
+	GlobalMg *G = globalMgFor(c, mgRho, mgPhi, m);
+	// level 0: this rank's own grids; levels >= 1: the global hierarchy
+	std::vector<Grid*> gr(nL), gp(nL), ge(nL);
+	for(int q = 0; q < nL; q++){
+		gr[q] = q < X.qDist ? mgRho->grids[q] : G->solver->mgRho->grids[q];
+		gp[q] = q < X.qDist ? mgPhi->grids[q] : G->solver->mgPhi->grids[q];
+		ge[q] = q < X.qDist ? mgRes->grids[q] : G->solver->mgRes->grids[q];
+	}
+	Multigrid xr = *mgRho, xp = *mgPhi, xe = *mgRes;
+	xr.grids = gr.data(); xp.grids = gp.data(); xe.grids = ge.data();
+	gatherGlobal(c, G, mgRho, mgPhi, m, false, X.qDist);        // the coarse levels keep their phi from solve to solve (src/multigrid.c:1496-1548)
+	if(!fusedSolve(c, &xr, &xp, &xe, tol, maxCycles, 0, &X)) return false;
+	extractLocal(c, G, mgRho, mgPhi, mgRes, m, X.qDist);
+	for(int q = 0; q < X.qDist; q++){
+		gridHalo(c, devGrid(c, mgPhi->grids[q]), m, 0, 0);
+		gridHalo(c, devGrid(c, mgRho->grids[q]), m, 0, 0);
+		gridHalo(c, devGrid(c, mgRes->grids[q]), m, 0, 0);
+	}
+	c->mgLastPath = 1 + 8;
+	return true;
+}
+void mgFreeArena(Ctx *c){ freeXArena(c); }
 
 // which single-GPU kernel runs a periodic solve (the caller has checked fusedEligible's shape conditions)
 static void solveSingle(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, double tol, int maxCycles){
@@ -1682,6 +2033,7 @@ void mgConvergenceCheck(Ctx *c){
 	if(!c->h_mgHist) return;
 	c->mgLastCycles = (int)c->h_mgHist[0];
 	c->mgLastBarRes = c->h_mgHist[251];
+	if(c->mgXPending){ c->mgXTagHigh = c->h_mgHist[252]; c->mgXPending = false; }
 	if(!(c->mgLastBarRes <= c->mgTol))
 		fatal("mgSolve: the multigrid solver did not reach barRes <= %g within %d V-cycles (barRes = %g); the reference would loop forever (src/multigrid.c:1697)",
 			c->mgTol, c->mgLastCycles, c->mgLastBarRes);
@@ -1739,7 +2091,9 @@ void mgSolveRaw(funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 	const double tol = 1.E-10;                       // src/multigrid.c:1695
 	const int maxCycles = pinc::mgMaxCyclesDefault();    // the reference has no bound (it would hang); this one fails loudly, see mgConvergenceCheck
 	if(fusedEligible(c, mgRho, mgPhi, mgRes, mpiInfo)) pinc::solveSingle(c, mgRho, mgPhi, mgRes, tol, maxCycles);
-	else if(pinc::replicaEligible(c, mgRho, mpiInfo)) pinc::replicaSolve(c, mgRho, mgPhi, mgRes, mpiInfo, tol, maxCycles);
+	else if(pinc::replicaEligible(c, mgRho, mpiInfo)){
+		if(!pinc::hybridSolve(c, mgRho, mgPhi, mgRes, mpiInfo, tol, maxCycles)) pinc::replicaSolve(c, mgRho, mgPhi, mgRes, mpiInfo, tol, maxCycles);
+	}
 	else { opsSolve(c, mgAlgo, mgRho, mgPhi, mgRes, mpiInfo, tol, maxCycles); c->mgLastPath = 0; }
 }
 
@@ -1772,6 +2126,7 @@ int pincMgLastHistory(double *barRes, int cap){
 }
 double pincMgLastBarRes(void){ Ctx *c = cur(); if(c->mgHistPending || c->mgCheckPending) streamSync(c); return c->mgLastBarRes; }
 void pincMgSetReplica(int on){ pinc::g_mgReplica = on ? 1 : 0; }
+void pincMgSetHybrid(int on){ pinc::g_mgHybrid = on ? 1 : 0; }
 void pincMgSetRowMode(int mode){ pinc::g_mgRowMode = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 
 } // extern "C"

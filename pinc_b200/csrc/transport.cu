@@ -116,6 +116,34 @@ struct ThreadTransport : Transport {
 	}
 	void barrier(Ctx *c) override { streamSync(c); pthread_barrier_wait(&w->bar); }
 	const char *name() const override { return "threads"; }
+	// one process: the pointers are valid everywhere on the same device; other devices need peer access
+	bool peerAlloc(Ctx *c, size_t bytes, char **mine, std::vector<char*> &peers) override {
+		char *p = nullptr;
+		long ok = cudaMalloc(&p, bytes) == cudaSuccess && cudaMemset(p, 0, bytes) == cudaSuccess;
+		if(!ok) cudaGetLastError();
+		std::vector<long> all(3*(size_t)w->n);
+		long v[3] = { (long)(uintptr_t)p, (long)c->device, ok };
+		allgatherLong(c, v, 3, all.data());
+		for(int r = 0; r < w->n && ok; r++){
+			if(!all[3*r+2]) ok = 0;
+			else if(all[3*r+1] != c->device){
+				int can = 0;
+				cudaDeviceCanAccessPeer(&can, c->device, (int)all[3*r+1]);
+				if(!can) ok = 0;
+				else { cudaError_t e = cudaDeviceEnablePeerAccess((int)all[3*r+1], 0); if(e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0; cudaGetLastError(); }
+			}
+		}
+		long okAll[1] = { ok };
+		std::vector<long> oks(w->n);
+		allgatherLong(c, okAll, 1, oks.data());
+		for(int r = 0; r < w->n; r++) if(!oks[r]) ok = 0;
+		if(!ok){ if(p) cudaFree(p); return false; }
+		peers.assign(w->n, nullptr);
+		for(int r = 0; r < w->n; r++) peers[r] = (char*)(uintptr_t)all[3*r];
+		*mine = p;
+		return true;
+	}
+	void peerFree(Ctx *, char *mine, std::vector<char*> &peers) override { if(mine) cudaFree(mine); peers.clear(); }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -187,6 +215,47 @@ struct NcclTransport : Transport {
 		peerOk = (v == 0.0);
 		if(!peerOk && c->rank == 0) fprintf(stderr, "PINC-B200 WARNING: peer-to-peer arena unavailable, halo exchange stays on NCCL send/recv\n");
 	}
+	// one process per GPU on one NVLink/NVSwitch node: CUDA IPC handles, all-gathered through NCCL
+	bool peerAlloc(Ctx *c, size_t bytes, char **mine, std::vector<char*> &peers) override {
+		if(getenv("PINC_B200_NO_P2P")) return false;
+		NcclApi *n = ncclApi();
+		char *p = nullptr;
+		int ok = cudaMalloc(&p, bytes) == cudaSuccess;
+		cudaIpcMemHandle_t h; memset(&h, 0, sizeof h);
+		if(ok) ok = cudaMemset(p, 0, bytes) == cudaSuccess && cudaIpcGetMemHandle(&h, p) == cudaSuccess;
+		if(!ok) cudaGetLastError();
+		char *d = (char*)tmpBuffer(c, sizeof(h)*(c->size + 1));
+		PINC_CUDA(cudaMemcpyAsync(d, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+		PINC_NCCL(n->AllGather(d, d + sizeof h, sizeof h, ncclChar, comm, c->stream));
+		std::vector<cudaIpcMemHandle_t> all(c->size);
+		PINC_CUDA(cudaMemcpyAsync(all.data(), d + sizeof h, sizeof(h)*c->size, cudaMemcpyDeviceToHost, c->stream));
+		streamSync(c);
+		peers.assign(c->size, nullptr);
+		for(int r = 0; r < c->size && ok; r++){
+			if(r == c->rank){ peers[r] = p; continue; }
+			void *q = nullptr;
+			if(cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess){ ok = 0; cudaGetLastError(); }
+			peers[r] = (char*)q;
+		}
+		double v = ok ? 0.0 : 1.0;                       // everybody or nobody
+		PINC_CUDA(cudaMemcpyAsync(c->d_scal + 254, &v, sizeof v, cudaMemcpyHostToDevice, c->stream));
+		PINC_NCCL(n->AllReduce(c->d_scal + 254, c->d_scal + 254, 1, ncclDouble, ncclSum, comm, c->stream));
+		PINC_CUDA(cudaMemcpyAsync(&v, c->d_scal + 254, sizeof v, cudaMemcpyDeviceToHost, c->stream));
+		streamSync(c);
+		if(v != 0.0){
+			for(int r = 0; r < c->size; r++) if(peers[r] && peers[r] != p) cudaIpcCloseMemHandle(peers[r]);
+			if(p) cudaFree(p);
+			peers.clear();
+			return false;
+		}
+		*mine = p;
+		return true;
+	}
+	void peerFree(Ctx *, char *mine, std::vector<char*> &peers) override {
+		for(char *q : peers) if(q && q != mine) cudaIpcCloseMemHandle(q);
+		if(mine) cudaFree(mine);
+		peers.clear();
+	}
 	void exchange(Ctx *c, std::vector<Msg> sends, std::vector<Msg> recvs) override {
 		localCopies(c, sends, recvs);
 		// NCCL pairs the sends and receives of two ranks in posting order: order both sides by tag
@@ -234,6 +303,7 @@ void pincCommInitThreads(PincCtx **ctxs, int n){
 	for(int r = 0; r < n; r++){
 		Ctx *c = (Ctx*)ctxs[r];
 		if(c->rank != r || c->size != n) fatal("pincCommInitThreads: context %d has rank %d of %d", r, c->rank, c->size);
+		mgFreeArena(c);
 		delete c->tp;
 		c->tp = new ThreadTransport(w);
 	}
@@ -254,6 +324,7 @@ void pincCommInitNccl(PincCtx *ctx, const char *uniqueId128){
 	memcpy(&id, uniqueId128, 128);
 	NcclTransport *t = new NcclTransport();
 	PINC_NCCL(ncclApi()->CommInitRank(&t->comm, c->size, id, c->rank));
+	mgFreeArena(c);
 	delete c->tp;
 	c->tp = t;
 	t->setupPeer(c);

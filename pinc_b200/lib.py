@@ -13,7 +13,7 @@ import os
 from . import abi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libpinc_b200.so")
+SO_PATH = os.environ.get("PINC_B200_LIB") or os.path.join(HERE, "libpinc_b200.so")      # the override is for A/B builds of the same ABI
 
 P = C.POINTER
 _lib = None
@@ -76,6 +76,7 @@ SIGNATURES = {
     "pincMgSetMode": (None, [C.c_int]),
     "pincMgSetReplica": (None, [C.c_int]),
     "pincMgSetRowMode": (None, [C.c_int]),
+    "pincMgSetHybrid": (None, [C.c_int]),
     "pincMgLastBarRes": (C.c_double, []),
     "pincMgLastPath": (C.c_int, []),
     # entry points that take PINC's dictionary *ini (need the host's iniGet*; typed for the symbol check)

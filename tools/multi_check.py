@@ -2,7 +2,7 @@
 """Multi-GPU parity check: one process per GPU (torchrun), NCCL transport, against the oracle.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
-        tools/multi_check.py [cold|warm] [steps] [replica 1|0]
+        tools/multi_check.py [cold|warm] [steps] [replica 1|0] [hybrid 0|1]
 
 Every rank steps its own sub-domain on its GPU; every rank also steps the WHOLE world in the oracle on the CPU
 (small config) and compares its own sub-domain: population sizes and migrant tables exact, V-cycle counts equal,
@@ -33,7 +33,7 @@ def fresh_nccl_id(L, rank):
     return bytes(t.cpu().tolist())
 
 
-def check(rank, world, kind="warm", steps=4, replica=1, tol=1e-10):
+def check(rank, world, kind="warm", steps=4, replica=1, tol=1e-10, hybrid=0, true="16,8,8"):
     """Returns {'worst_field_err', 'worst_particle_err', 'tables_exact', 'cycles_equal', 'sizes_exact', 'mg_path', ...}
     for THIS rank; raises nothing (the caller decides).  Collective: every rank must call it."""
     from helpers import small_cfg, sorted_particles
@@ -41,7 +41,8 @@ def check(rank, world, kind="warm", steps=4, replica=1, tol=1e-10):
     from pinc_b200 import initial, lib as plib, sim
     L = plib.load()
     L.pincMgSetReplica(int(replica))
-    over = dict(grid__nsubdomains=SUB[world], grid__truesize="16,8,8", multigrid__mglevels=3, population__nparticles="8 pc",
+    L.pincMgSetHybrid(int(hybrid))
+    over = dict(grid__nsubdomains=SUB[world], grid__truesize=true, multigrid__mglevels=3, population__nparticles="8 pc",
                 population__nalloc="24 pc", grid__nemigrantsalloc="4 pc")
     if kind == "cold":
         over["population__perturbamplitude"] = "2e-3,0,0,0,0,0"
@@ -86,6 +87,7 @@ def check(rank, world, kind="warm", steps=4, replica=1, tol=1e-10):
                      and out["cycles_equal"] and out["sizes_exact"])
     W.close()
     L.pincMgSetReplica(1)
+    L.pincMgSetHybrid(1)
     return out
 
 
@@ -95,11 +97,12 @@ def main():
     kind = sys.argv[1] if len(sys.argv) > 1 else "warm"
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
     replica = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    hybrid = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    r = check(rank, world, kind, steps, replica)
+    r = check(rank, world, kind, steps, replica, hybrid=hybrid, true="32,16,16" if hybrid else "16,8,8")
     assert r["ok"], r
     print(f"rank {rank}/{world} [{kind}] ok: {steps} steps, transport={r['transport']}, mg_path={r['mg_path']}, "
           f"worst field error {r['worst_field_err']:.2e}, emigrants last step {r['emigrants_last_step']}", flush=True)
