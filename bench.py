@@ -146,6 +146,48 @@ def run_reference(args, n_gpus):
 
 
 # ------------------------------------------------------------------------------------------------------------
+def run_mg_error_scaling(args, n_gpus):
+    """BASELINE configs[2] (input/mgErrorScaling.ini, src/multigrid.c:1734-1851): the stand-alone multigrid solve of the sine
+    problem on a ladder of grids; V-cycles, time per V-cycle and the error against the analytic solution.  One GPU (for
+    N > 1 every rank would run a replica: the path does not shard, so only rank 0 reports)."""
+    import torch
+    from pinc_b200 import lib as plib
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import mg_bench
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    L = plib.load()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    for _ in range(max(1, args.warmup // 2)):
+        mg_bench.run_case(L, 64, "sin", 2, reps=1)
+    sampler.start()
+    launches0 = L.pincLaunchCount()
+    recs, orders = mg_bench.error_scaling(L, (16, 32, 64, 128))
+    launches = L.pincLaunchCount() - launches0
+    clocks = sampler.stop()
+    big = recs[-2]                       # 64^3: the grid of BASELINE configs[1]
+    n_fine = 64 ** 3
+    value = n_fine * big["vcycles"] / (big["ms_per_solve"] * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = (606 + 32) * value / 1e9
+    return {"metric": "fine-grid nodes x V-cycles per second (mgSolve, sine problem, 64^3)", "value": value, "unit": "node-V-cycles/s",
+            "n_gpus": n_gpus, "steps": 3, "warmup": args.warmup, "ms_per_step": big["ms_per_solve"], "higher_is_better": True,
+            "scaling": "replicas only", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "mgErrorScaling (BASELINE configs[2]): rho = k^2 sin(kx) with the reference's PI (src/grid.h:584), N^3 cells for N = 16..128, "
+                                   "mgLevels = log2(N) - 1, V(10,10), 10 coarse sweeps, tolerance 1e-10; a step = one cold-started mgSolve (best of 3)",
+                       "l2": "all levels are L2/shared-memory resident by design (2.3 MB per array at 64^3); no flush"},
+            "cases": [{k: r[k] for k in ("N", "levels", "vcycles", "ms_per_solve", "us_per_vcycle", "rms_error_vs_analytic", "max_error_vs_analytic", "barRes_last", "path")} for r in recs],
+            "error_order_observed": orders, "error_order_expected": 2.0,
+            "clocks": clocks, "gpu_launches": int(launches),
+            "roofline": {"kernel": "k_mg_solve", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "note": "latency-bound (DESIGN.md section 4): 638 algorithmic B per fine node and V-cycle; us_per_vcycle is the figure of merit"},
+            "e2e": None}
+
+
 def run_ours(args, n_gpus, rank, world_size):
     import torch
     from pinc_b200 import abi, initial, lib as plib, sim
@@ -337,7 +379,9 @@ def run_ours(args, n_gpus, rank, world_size):
                                    5: "replicated: global problem on every rank, all-SM persistent kernel",
                                    6: "replicated: global problem on every rank, cluster kernel",
                                    9: "hybrid: finest level distributed (block faces across sub-domains through peer-memory mailboxes), coarser levels replicated, one persistent kernel per rank"}.get(W.mg_path(), "?")},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
+            "kernels_source": f"{prof_steps} extra steps AFTER the timed region with CUDA events around every launch (the timed steps carry no per-launch events); "
+                              "avg_launch_ms and ms_per_step therefore come from different steps of the same run"}
     if parity is not None:
         line["parity"] = parity
     W.close()
@@ -367,6 +411,10 @@ def main():
             print(json.dumps(run_reference(args, args.gpus)), flush=True)
         return
     assert world == args.gpus, f"--gpus {args.gpus} needs {args.gpus} ranks (torchrun); WORLD_SIZE={world}"
+    if args.workload == "mgErrorScaling":
+        if rank == 0:
+            print(json.dumps(run_mg_error_scaling(args, args.gpus)), flush=True)
+        return
     if args.warmup < 3:
         print(f"bench.py: --warmup {args.warmup} raised to 3 (timing rules)", file=sys.stderr)
         args.warmup = 3

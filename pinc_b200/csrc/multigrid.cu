@@ -1070,35 +1070,47 @@ namespace pinc {
 // Ghost FACES of a rank-local array (all a 7-point stencil reads): a non-decomposed dimension wraps locally, a decomposed
 // one travels through the plane slots of the neighbours' arenas.  Two plane sets alternate; a set is rewritten two calls
 // later, after the neighbour has sent its next planes, i.e. after the grid barrier that ended its reading of this set.
-__device__ __noinline__ void xHalo(double *v, int s0, int s1, int s2, Scope &S){
+// sides: bit 0 = fill the lower ghost layers, bit 1 = the upper ones (the restriction only reads lower ghosts).
+__device__ __noinline__ void xHalo(double *v, int s0, int s1, int s2, Scope &S, int sides = 3){
+	ProfScope psx(*S.K, PS_GS_BIG_SYNC);
 	const XDist &x = *S.X;
 	const unsigned tag = ++S.xHalo, set = tag & 1u;
 	const int t[3] = {s0-2, s1-2, s2-2};
+	const bool pr = S.K->prof && blockIdx.x == 0 && threadIdx.x == 0;
+	long long tq = pr ? clock64() : 0;
 	uint4 *mine = x.peer[x.me] + x.offPlane + (size_t)set*6*x.planeCap;
-	for(int pass = 0; pass < 2; pass++)
-		for(int d = 0; d < 3; d++){
+	const int n0 = t[1]*t[2], n1 = t[0]*t[2], n2 = t[0]*t[1];
+	for(int pass = 0; pass < 2; pass++){
+		// one flat index over the three face pairs: a thread has at most one node per pass on the benchmark grids, so a pass
+		// is one L2 round trip, not three
+		for(int ii = (int)S.tid(); ii < n0 + n1 + n2; ii += (int)S.nthr()){
+			const int d = ii < n0 ? 0 : (ii < n0 + n1 ? 1 : 2), i = ii - (d == 0 ? 0 : (d == 1 ? n0 : n0 + n1));
 			const bool dec = x.ns[d] > 1;
 			if(pass == 1 && !dec) continue;
-			const int ta = d == 0 ? t[1] : t[0], tb = d == 2 ? t[1] : t[2], n = ta*tb;
-			uint4 *toLo = x.peer[x.nbr[2*d]] + x.offPlane + (size_t)(set*6 + 2*d+1)*x.planeCap;      // my lower layer is the lower neighbour's upper ghost
-			uint4 *toHi = x.peer[x.nbr[2*d+1]] + x.offPlane + (size_t)(set*6 + 2*d)*x.planeCap;
-			for(long i = S.tid(); i < n; i += S.nthr()){
-				const int a = (int)(i % ta) + 1, b = (int)(i / ta) + 1;
-				long gLo, gHi, hLo, hHi;          // boundary layers, ghost layers
-				if(d == 0){ gLo = ix(1,a,b,s0,s1); gHi = ix(t[0],a,b,s0,s1); hLo = ix(0,a,b,s0,s1); hHi = ix(t[0]+1,a,b,s0,s1); }
-				else if(d == 1){ gLo = ix(a,1,b,s0,s1); gHi = ix(a,t[1],b,s0,s1); hLo = ix(a,0,b,s0,s1); hHi = ix(a,t[1]+1,b,s0,s1); }
-				else { gLo = ix(a,b,1,s0,s1); gHi = ix(a,b,t[2],s0,s1); hLo = ix(a,b,0,s0,s1); hHi = ix(a,b,t[2]+1,s0,s1); }
-				if(pass == 0){
-					const double vLo = ldg2(v + gLo), vHi = ldg2(v + gHi);
-					if(dec){ llStoreSys(toLo + i, vLo, tag); llStoreSys(toHi + i, vHi, tag); }
-					else { v[hHi] = vLo; v[hLo] = vHi; }
-				} else {
-					v[hLo] = llWaitSys(mine + (size_t)(2*d)*x.planeCap + i, tag);
-					v[hHi] = llWaitSys(mine + (size_t)(2*d+1)*x.planeCap + i, tag);
-				}
+			const int ta = d == 0 ? t[1] : t[0];
+			const int b0 = i / ta, a = i - b0*ta + 1, b = b0 + 1;
+			long gLo, gHi, hLo, hHi;          // boundary layers, ghost layers
+			if(d == 0){ gLo = ix(1,a,b,s0,s1); gHi = ix(t[0],a,b,s0,s1); hLo = ix(0,a,b,s0,s1); hHi = ix(t[0]+1,a,b,s0,s1); }
+			else if(d == 1){ gLo = ix(a,1,b,s0,s1); gHi = ix(a,t[1],b,s0,s1); hLo = ix(a,0,b,s0,s1); hHi = ix(a,t[1]+1,b,s0,s1); }
+			else { gLo = ix(a,b,1,s0,s1); gHi = ix(a,b,t[2],s0,s1); hLo = ix(a,b,0,s0,s1); hHi = ix(a,b,t[2]+1,s0,s1); }
+			if(pass == 0){
+				// my lower layer fills somebody's UPPER ghost, my upper layer somebody's LOWER ghost
+				double vLo = 0, vHi = 0;
+				if(sides & 2) vLo = ldg2(v + gLo);
+				if(sides & 1) vHi = ldg2(v + gHi);
+				if(dec){
+					if(sides & 2) llStoreSys(x.peer[x.nbr[2*d]] + x.offPlane + (size_t)(set*6 + 2*d+1)*x.planeCap + i, vLo, tag);
+					if(sides & 1) llStoreSys(x.peer[x.nbr[2*d+1]] + x.offPlane + (size_t)(set*6 + 2*d)*x.planeCap + i, vHi, tag);
+				} else { if(sides & 2) v[hHi] = vLo; if(sides & 1) v[hLo] = vHi; }
+			} else {
+				if(sides & 1) v[hLo] = llWaitSys(mine + (size_t)(2*d)*x.planeCap + i, tag);
+				if(sides & 2) v[hHi] = llWaitSys(mine + (size_t)(2*d+1)*x.planeCap + i, tag);
 			}
 		}
+		if(pr){ long long tn = clock64(); S.K->prof[2*(13+pass)] += tn - tq; S.K->prof[2*(13+pass)+1] += 1; tq = tn; }
+	}
 	S.sync();
+	if(pr){ S.K->prof[2*15] += clock64() - tq; S.K->prof[2*15+1] += 1; }
 }
 
 // X: level q is distributed (hybrid multi-rank solve); its coarse level q+1 is the first replicated one (qDist = q+1)
@@ -1125,7 +1137,7 @@ template<bool X = false> __device__ __noinline__ void fDown(const MgPlan &P, int
 	if constexpr(X){
 		// restriction of my sub-domain, gathered into every rank's replicated rho(q+1): each coarse value goes into slot
 		// (my rank, node) of every rank's gather buffer; then every rank unpacks all R segments into the global array
-		xHalo(L.res, L.s0, L.s1, L.s2, S);
+		xHalo(L.res, L.s0, L.s1, L.s2, S, 1);
 		ProfScope psr(*S.K, 30);
 		const XDist &x = *S.X;
 		const unsigned tag = ++S.xGath, set = tag & 1u;
