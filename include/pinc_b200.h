@@ -188,7 +188,10 @@ void gSubFrom(Grid *result, const Grid *subtraction);                           
 double gSumTruegrid(const Grid *grid);                                          /* grid.h:388 (grid.c:833) */
 long int gTotTruesize(const Grid *grid, const MpiInfo *mpiInfo);                /* grid.h:308 (grid.c:849) */
 void gNeutralizeGrid(Grid *grid, const MpiInfo *mpiInfo);                       /* grid.h:357 (grid.c:730) */
-void gBnd(Grid *grid, const MpiInfo *mpiInfo);                                  /* grid.h:402 (grid.c:992); PERIODIC only */
+void gBnd(Grid *grid, const MpiInfo *mpiInfo);                                  /* grid.h:402 (grid.c:992): PERIODIC, DIRICHLET, NEUMANN */
+void gDirichlet(Grid *grid, const int boundary, const MpiInfo *mpiInfo);        /* grid.c:929 (no prototype in grid.h) */
+void gNeumann(Grid *grid, const int boundary, const MpiInfo *mpiInfo);          /* grid.c:958 (no prototype in grid.h) */
+void gSetBndSlices(Grid *grid, MpiInfo *mpiInfo);                               /* grid.h:66 (grid.c:608); host arrays */
 void gPotEnergy(const Grid *rho, const Grid *phi, Population *pop);             /* grid.h:527 (grid.c:1276) */
 
 /* ---------------------------------------------------------------------------------
@@ -196,6 +199,7 @@ void gPotEnergy(const Grid *rho, const Grid *phi, Population *pop);             
  * ------------------------------------------------------------------------------- */
 void mgSolve(const MultigridSolver *solver, const Grid *rho, const Grid *phi, const MpiInfo *mpiInfo); /* multigrid.h:95 (multigrid.c:403) */
 void mgSolveRaw(funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *mpiInfo); /* multigrid.c:1688 */
+void mgRestrictBnd(Multigrid *mgGrid);                                          /* multigrid.h:366 (multigrid.c:1314); host arrays */
 void mgVRecursive(int level, int bottom, int top, Multigrid *mgRho, Multigrid *mgPhi,
                   Multigrid *mgRes, const MpiInfo *mpiInfo);                    /* multigrid.c:1550 */
 void mgGS3D(Grid *phi, const Grid *rho, int nCycles, const MpiInfo *mpiInfo);  /* multigrid.c:683 */

@@ -91,6 +91,15 @@ def load():
     lib.orc_mg_vcycle.argtypes = [C.c_void_p, PP, PP, PP]
     lib.orc_mg_level.restype = c_double_p
     lib.orc_mg_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p]
+    lib.orc_slice_max.restype = C.c_long
+    lib.orc_slice_max.argtypes = [c_int_p]
+    lib.orc_set_bnd_slices.argtypes = [P(OrcTopo), C.c_int, c_int_p, c_int_p, c_double_p]
+    lib.orc_bnd.argtypes = [P(OrcTopo), PP, c_int_p, c_int_p, PP]
+    lib.orc_gs3d_bnd.argtypes = [P(OrcTopo), PP, PP, c_int_p, C.c_int, c_int_p, PP]
+    lib.orc_mg_set_bnd.argtypes = [C.c_void_p, c_int_p]
+    lib.orc_mg_bnd_slice.restype = c_double_p
+    lib.orc_mg_bnd_slice.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.orc_mg_restrict_bnd.argtypes = [C.c_void_p]
     lib.orc_step.argtypes = [P(OrcSim)]
     lib.orc_field_solve.argtypes = [P(OrcSim)]
     lib.orc_accelerate.argtypes = [P(OrcSim), C.c_double]
@@ -183,6 +192,23 @@ class OrcWorld:
         s.rho, s.phi, s.res, s.E = k["rho"], k["phi"], k["res"], k["E"]
         s.emigrants, s.nEmigrants, s.nImmigrants = k["emig"], k["nEmig"], k["nImm"]
         s.mg = self.mg
+
+    def set_boundaries(self, names):
+        """grid:boundaries (lower x,y,z then upper x,y,z) for the multigrid levels: gSetBndSlices on level 0, then mgRestrictBnd.
+        Returns the per-rank numpy views of the level-0 boundary slices (8 x orc_slice_max doubles)."""
+        kinds = {"PERIODIC": 1, "DIRICHLET": 2, "NEUMANN": 3}
+        b = [kinds[x] for x in names]
+        self.bnd = np.array([0x10] + b[:3] + [0x10] + b[3:], dtype=np.int32)
+        self.lib.orc_mg_set_bnd(self.mg, ip(self.bnd))
+        nmax = self.lib.orc_slice_max(ip(self.size))
+        self.bnd_slices = []
+        for r in range(self.n):
+            p = self.lib.orc_mg_bnd_slice(self.mg, 0, r)
+            self.lib.orc_set_bnd_slices(C.byref(self.topo), r, ip(self.size), ip(self.bnd), p)
+            self.bnd_slices.append(np.ctypeslib.as_array(p, shape=(8 * nmax,)))
+        self.lib.orc_mg_restrict_bnd(self.mg)
+        self._keep["bnd0"] = (c_double_p * self.n)(*[self.lib.orc_mg_bnd_slice(self.mg, 0, r) for r in range(self.n)])
+        return self.bnd_slices
 
     def set_particles(self, per_rank):
         for r in range(self.n):

@@ -376,6 +376,60 @@ void orc_gs3d(const OrcTopo *t, double **phi, double **rho, const int *size, int
 	}
 }
 
+/* ---- boundary conditions (src/grid.c:921-1023) -------------------------------------------------------------------
+ * bnd[8]: bndType per boundary index as in Grid::bnd of a rank-4 grid (1..3 lower x,y,z; 5..7 upper; 0 and 4 unused):
+ * 1 PERIODIC, 2 DIRICHLET, 3 NEUMANN.  bndSlice[r]: 8 slices of orc_slice_max() doubles, slice `boundary` in the element
+ * order of getSlice/setSlice (src/grid.c:467, 940-952). */
+long orc_slice_max(const int *size){
+	/* nSliceMax of src/grid.c:455-465 runs over all rank dimensions INCLUDING the component axis, whose "slice" is the
+	 * whole scalar grid: that term always wins */
+	return (long)size[0]*size[1]*size[2];
+}
+/* src/grid.c:608-662 */
+void orc_set_bnd_slices(const OrcTopo *t, int rank, const int *size, const int *bnd, double *bndSlice){
+	long nMax = orc_slice_max(size);
+	int sub[3]; rank_to_sub(t,rank,sub);
+	for(int d=1;d<4;d++){
+		if(sub[d-1]==0 && (bnd[d]==2 || bnd[d]==3)) for(long s=0;s<nMax;s++) bndSlice[s+nMax*d] = bnd[d]==2 ? 1. : 2.;
+		if(sub[d-1]==t->nSub[d-1]-1 && (bnd[d+4]==2 || bnd[d+4]==3)) for(long s=0;s<nMax;s++) bndSlice[s+nMax*(d+4)] = bnd[d+4]==2 ? 1. : 2.;
+	}
+}
+/* gDirichlet :929-956 (slice 1 on a lower edge, size-1 on an upper edge - the reference's own asymmetry) and
+ * gNeumann :958-990 (ghost slice := slice two further in, minus twice the boundary value) */
+static void edge(double *val, const int *size, int boundary, int kind, const double *bndSlice){
+	int d = boundary%4 - 1, upper = boundary>4;
+	long nMax = orc_slice_max(size), ns = (long)size[0]*size[1]*size[2]/size[d];
+	const double *b = bndSlice + boundary*nMax;
+	if(kind==2){ slice_put(b,val,size,1,d,1+upper*(size[d]-2),0); return; }
+	int offset = upper*(size[d]-1);
+	double *buf = malloc(sizeof(double)*ns);
+	slice_get(buf,val,size,1,d,offset+2-4*upper);
+	for(long s=0;s<ns;s++) buf[s] -= 2*b[s];
+	slice_put(buf,val,size,1,d,offset,0);
+	free(buf);
+}
+/* gBnd :992-1023 */
+void orc_bnd(const OrcTopo *t, double **val, const int *size, const int *bnd, double **bndSlice){
+	int periodic = 0;
+	for(int d=1;d<4;d++) if(bnd[d]==1) periodic = 1;
+	if(periodic) orc_neutralize(t,val,size);
+	for(int r=0;r<t->nRanks;r++){
+		int sub[3]; rank_to_sub(t,r,sub);
+		for(int d=1;d<4;d++) if(sub[d-1]==0 && (bnd[d]==2 || bnd[d]==3)) edge(val[r],size,d,bnd[d],bndSlice[r]);
+		for(int d=5;d<8;d++) if(sub[d-5]==t->nSub[d-5]-1 && (bnd[d]==2 || bnd[d]==3)) edge(val[r],size,d,bnd[d],bndSlice[r]);
+	}
+}
+/* mgGS3D with gBnd after every colour (src/multigrid.c:683-767) */
+void orc_gs3d_bnd(const OrcTopo *t, double **phi, double **rho, const int *size, int nCycles, const int *bnd, double **bndSlice){
+	for(int c=0;c<nCycles;c++){
+		for(int par=1;par>=0;par--){
+			for(int r=0;r<t->nRanks;r++) gs_colour(phi[r],rho[r],size,par);
+			orc_halo(t,phi,size,1,0,0);
+			orc_bnd(t,phi,size,bnd,bndSlice);
+		}
+	}
+}
+
 /* src/multigrid.c:1385-1403 + src/grid.c:296-334, on true nodes (ghosts are set by the halo
  * exchange that always follows). */
 void orc_residual(double *res, const double *rho, const double *phi, const int *size){
@@ -432,6 +486,8 @@ struct OrcMg {
 	int nLevels, nPre, nPost, nCoarse;
 	int size[16][3];
 	double **rho[16], **phi[16], **res[16];   /* [level][rank]; level 0 borrowed per call */
+	int nonPeriodic, bnd[8];                  /* orc_mg_set_bnd: boundary types of every level */
+	double **bndSlice[16];                    /* [level][rank], 8 slices each */
 };
 
 /* src/multigrid.c:128-206, 297-349: level q has trueSize/2^q, one ghost layer per side. */
@@ -452,7 +508,35 @@ OrcMg *orc_mg_alloc(const OrcTopo *t, int nLevels, int nPre, int nPost, int nCoa
 	}
 	return mg;
 }
+/* non-periodic edges: allocates (zeroed) boundary slices for every level of phi */
+void orc_mg_set_bnd(OrcMg *mg, const int *bnd){
+	mg->nonPeriodic = 0;
+	for(int b=0;b<8;b++){ mg->bnd[b] = bnd[b]; if(b%4 && bnd[b]!=1) mg->nonPeriodic = 1; }
+	for(int q=0;q<mg->nLevels;q++){
+		if(mg->bndSlice[q]) continue;
+		mg->bndSlice[q] = calloc(mg->topo.nRanks,sizeof(double*));
+		for(int r=0;r<mg->topo.nRanks;r++) mg->bndSlice[q][r] = calloc(8*orc_slice_max(mg->size[q]),sizeof(double));
+	}
+}
+double *orc_mg_bnd_slice(OrcMg *mg, int level, int rank){ return mg->bndSlice[level] ? mg->bndSlice[level][rank] : 0; }
+/* src/multigrid.c:1314-1379 */
+void orc_mg_restrict_bnd(OrcMg *mg){
+	for(int q=0;q<mg->nLevels-1;q++){
+		long nF = orc_slice_max(mg->size[q]), nC = orc_slice_max(mg->size[q+1]);
+		for(int r=0;r<mg->topo.nRanks;r++)
+			for(int d=1;d<8;d++){ if(d==4) continue; for(long s=0;s<nC;s++) mg->bndSlice[q+1][r][s+nC*d] = mg->bndSlice[q][r][2*s+nF*d]; }
+	}
+}
+static void mg_bnd(OrcMg *mg, int level){
+	if(mg->nonPeriodic) orc_bnd(&mg->topo,mg->phi[level],mg->size[level],mg->bnd,mg->bndSlice[level]);
+	else orc_neutralize(&mg->topo,mg->phi[level],mg->size[level]);
+}
+static void mg_gs(OrcMg *mg, int level, int nCycles){
+	if(mg->nonPeriodic) orc_gs3d_bnd(&mg->topo,mg->phi[level],mg->rho[level],mg->size[level],nCycles,mg->bnd,mg->bndSlice[level]);
+	else orc_gs3d(&mg->topo,mg->phi[level],mg->rho[level],mg->size[level],nCycles);
+}
 void orc_mg_free(OrcMg *mg){
+	for(int q=0;q<mg->nLevels;q++) if(mg->bndSlice[q]){ for(int r=0;r<mg->topo.nRanks;r++) free(mg->bndSlice[q][r]); free(mg->bndSlice[q]); }
 	for(int q=0;q<mg->nLevels;q++){
 		if(q>0) for(int r=0;r<mg->topo.nRanks;r++){ free(mg->rho[q][r]); free(mg->phi[q][r]); free(mg->res[q][r]); }
 		free(mg->rho[q]); free(mg->phi[q]); free(mg->res[q]);
@@ -475,23 +559,23 @@ static void vcycle(OrcMg *mg, int level){
 		orc_halo(t,phi,sz,1,0,0);
 		orc_halo(t,rho,sz,1,0,0);
 		orc_neutralize(t,rho,sz);
-		orc_gs3d(t,phi,rho,sz,mg->nCoarse);
-		orc_neutralize(t,phi,sz);
+		mg_gs(mg,level,mg->nCoarse);
+		mg_bnd(mg,level);
 		orc_bilin_prol3d(t,mg->res[level-1],mg->size[level-1],phi,sz);
 		return;
 	}
 	orc_halo(t,rho,sz,1,0,0);
 	orc_neutralize(t,rho,sz);
-	orc_gs3d(t,phi,rho,sz,mg->nPre);
+	mg_gs(mg,level,mg->nPre);
 	for(int r=0;r<R;r++) orc_residual(res[r],rho[r],phi[r],sz);
 	orc_halo(t,res,sz,1,0,0);
 	for(int r=0;r<R;r++) orc_half_restrict3d(res[r],sz,mg->rho[level+1][r],mg->size[level+1]);
 	vcycle(mg,level+1);
 	for(int r=0;r<R;r++) for(long g=0;g<n;g++) phi[r][g] += res[r][g];
 	orc_halo(t,phi,sz,1,0,0);
-	orc_neutralize(t,phi,sz);
-	orc_gs3d(t,phi,rho,sz,mg->nPost);
-	orc_neutralize(t,phi,sz);
+	mg_bnd(mg,level);
+	mg_gs(mg,level,mg->nPost);
+	mg_bnd(mg,level);
 	if(level>0) orc_bilin_prol3d(t,mg->res[level-1],mg->size[level-1],phi,sz);
 }
 

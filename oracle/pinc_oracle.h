@@ -61,6 +61,12 @@ void orc_neutralize(const OrcTopo *t, double **val, const int *size);
 void orc_findiff1st(const double *phi, double *E, const int *size);
 void orc_gmul(double *val, long n, double num);
 void orc_gs3d(const OrcTopo *t, double **phi, double **rho, const int *size, int nCycles);
+/* boundary conditions (src/grid.c:608-662, 921-1023): bnd[8] = bndType per boundary index of a rank-4 grid (1..3 lower, 5..7
+ * upper; 1 PERIODIC, 2 DIRICHLET, 3 NEUMANN); bndSlice[rank] = 8 slices of orc_slice_max(size) doubles */
+long orc_slice_max(const int *size);
+void orc_set_bnd_slices(const OrcTopo *t, int rank, const int *size, const int *bnd, double *bndSlice);
+void orc_bnd(const OrcTopo *t, double **val, const int *size, const int *bnd, double **bndSlice);
+void orc_gs3d_bnd(const OrcTopo *t, double **phi, double **rho, const int *size, int nCycles, const int *bnd, double **bndSlice);
 void orc_residual(double *res, const double *rho, const double *phi, const int *size);
 void orc_half_restrict3d(const double *fine, const int *fsize, double *coarse, const int *csize);
 void orc_bilin_prol3d(const OrcTopo *t, double **fine, const int *fsize, double **coarse, const int *csize);
@@ -71,6 +77,10 @@ double orc_pot_energy(const double *rho, const double *phi, const int *size);
 typedef struct OrcMg OrcMg;
 OrcMg *orc_mg_alloc(const OrcTopo *t, int nLevels, int nPre, int nPost, int nCoarse);
 void   orc_mg_free(OrcMg *mg);
+/* non-periodic edges: boundary types for every level; the (zeroed) slices of level q, rank r; mgRestrictBnd (multigrid.c:1314) */
+void   orc_mg_set_bnd(OrcMg *mg, const int *bnd);
+double *orc_mg_bnd_slice(OrcMg *mg, int level, int rank);
+void   orc_mg_restrict_bnd(OrcMg *mg);
 /* rho0/phi0/res0: per-rank finest-level arrays owned by the caller.  Returns the number of
  * V-cycles; barRes[c] receives the residual norm after V-cycle c (up to cap). */
 int    orc_mg_solve(OrcMg *mg, double **rho0, double **phi0, double **res0, double tol,

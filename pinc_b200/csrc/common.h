@@ -42,6 +42,11 @@ struct DevGrid {
 	long maxSlice = 0;
 	long long *d_fixS[8] = {nullptr};   // per-species fixed-point accumulators of the deposition (scalar grids, lazily)
 	bool fixDirty = false;              // accumulators hold deposits nobody consumed (cleared before the next use)
+	// Dirichlet/Neumann boundary values (Grid::bndSlice, src/grid.c:467: 2*rank slices of nSliceMax doubles, slice index =
+	// boundary = d for a lower and rank+d for an upper edge); mirrored when the grid has a non-periodic edge
+	double *d_bnd = nullptr;
+	long bndStride = 0;                 // nSliceMax
+	bool nonPeriodic = false;
 };
 
 struct DevPop {
@@ -204,6 +209,9 @@ bool gridHaloP2P(Ctx *c, DevGrid *g, const MpiInfo *m);
 bool allSumP2P(Ctx *c, const double *partial, int n, double *out, const MpiInfo *m);   // multigrid.cu: one-double all-reduce over peer memory       // multigrid.cu: ghost fill over peer memory, false if unavailable
 void gridHaloFaces(Ctx *c, DevGrid *g, const MpiInfo *m);      // faces of the decomposed dimensions only, one exchange
 void gridNeutralize(Ctx *c, DevGrid *g, const MpiInfo *m);
+void gridBnd(Ctx *c, DevGrid *g, const MpiInfo *m);             // gBnd (src/grid.c:992-1023): periodic, Dirichlet and Neumann edges
+void gridEdge(Ctx *c, DevGrid *g, int boundary, int kind);     // gDirichlet / gNeumann of one edge
+void gridUploadBnd(Ctx *c, DevGrid *g);                          // host bndSlice -> device (after the host changed it)
 void gridAddTo(Ctx *c, DevGrid *r, const DevGrid *a);
 // sum over the true grid of val (mode 0), val^2 after squaring in place (mode 1) or val*other (mode 2);
 // the result lands in c->d_scal[slot] (this rank only, no all-reduce)

@@ -199,6 +199,15 @@ DevGrid *devGrid(Ctx *c, const Grid *g, bool upload){
 	PINC_CUDA(cudaMalloc(&dg->d_recv, (size_t)6*ms*sizeof(double)));
 	if(upload) PINC_CUDA(cudaMemcpyAsync(dg->d, g->val, (size_t)dg->n*sizeof(double), cudaMemcpyHostToDevice, c->stream));
 	else PINC_CUDA(cudaMemsetAsync(dg->d, 0, (size_t)dg->n*sizeof(double), c->stream));
+	for(int r = 1; r < g->rank; r++) if(g->bnd && (g->bnd[r] != PERIODIC || g->bnd[r + g->rank] != PERIODIC)) dg->nonPeriodic = true;
+	if(dg->nonPeriodic){
+		// nSliceMax as src/grid.c:455-465 (the component axis counts as a dimension)
+		long nMax = 0;
+		for(int d = 0; d < g->rank; d++){ long n = 1; for(int dd = 0; dd < g->rank; dd++) if(dd != d) n *= g->size[dd]; if(n > nMax) nMax = n; }
+		dg->bndStride = nMax;
+		PINC_CUDA(cudaMalloc(&dg->d_bnd, (size_t)2*g->rank*nMax*sizeof(double)));
+		gridUploadBnd(c, dg);
+	}
 	c->grids[g] = dg;
 	return dg;
 }
@@ -223,6 +232,7 @@ DevPop *devPop(Ctx *c, const Population *p, bool upload){
 
 static void freeDevGrid(DevGrid *g){
 	cudaFree(g->d); cudaFree(g->d_send); cudaFree(g->d_recv); for(int s = 0; s < 8; s++) if(g->d_fixS[s]) cudaFree(g->d_fixS[s]);
+	if(g->d_bnd) cudaFree(g->d_bnd);
 	delete g;
 }
 static void freeDevPop(DevPop *p){
@@ -276,6 +286,7 @@ void pincSyncGridToDevice(Grid *grid){
 	Ctx *c = cur();
 	DevGrid *g = devGrid(c, grid, false);
 	PINC_CUDA(cudaMemcpyAsync(g->d, grid->val, (size_t)g->n*sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	if(g->nonPeriodic) gridUploadBnd(c, g);
 	streamSync(c);
 }
 void pincSyncGridToHost(Grid *grid){

@@ -261,6 +261,58 @@ __global__ void k_findiff2nd(double *__restrict__ res, const double *__restrict_
 	}
 }
 
+// ---- boundary conditions (src/grid.c:921-1023) ---------------------------------------------------------------------
+void gridUploadBnd(Ctx *c, DevGrid *g){
+	if(!g->d_bnd) return;
+	if(!g->host->bndSlice) fatal("a grid with a DIRICHLET/NEUMANN edge needs Grid::bndSlice (src/grid.c:467)");
+	PINC_CUDA(cudaMemcpyAsync(g->d_bnd, g->host->bndSlice, (size_t)2*g->host->rank*g->bndStride*sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	streamSync(c);              // the host array is pageable and may change right after
+}
+// ghost := value two layers further in - 2*A (src/grid.c:958-990)
+__global__ void k_neumann(double *__restrict__ v, const double *__restrict__ bnd, Dims D, int dd, int take, int place, long ns){
+	long e = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; e < ns; e += st){
+		double a = v[sliceElem(D, dd, take, e)];
+		a -= 2*bnd[e];
+		v[sliceElem(D, dd, place, e)] = a;
+	}
+}
+// one edge: gDirichlet (slice 1 on a lower, size-1 on an upper edge := bndSlice; the asymmetry is the reference's,
+// src/grid.c:940) or gNeumann (ghost slice 0 / size-1 := slice 2 / size-3 minus twice bndSlice)
+void gridEdge(Ctx *c, DevGrid *g, int boundary, int kind){
+	const int rank = g->host->rank, d = boundary % rank, upper = boundary > rank;
+	if(d < 1 || !g->d_bnd) fatal("gDirichlet/gNeumann: boundary %d of a grid without non-periodic edges", boundary);
+	const int dd = d - 1, sz = g->size[dd];
+	const long ns = g->n / sz;
+	const double *b = g->d_bnd + (long)boundary*g->bndStride;
+	const int blocks = gridFor(ns, 256, c->numSMs*4);
+	if(kind == DIRICHLET){
+		const int offset = 1 + upper*(sz - 2);
+		PINC_LAUNCH(c, K_HALO, 16.0*ns, (k_slice_unpack<<<blocks,256,0,c->stream>>>(g->d, b, dimsOf(g), dd, offset, ns, 0)));
+	} else {
+		const int offset = upper*(sz - 1);
+		PINC_LAUNCH(c, K_HALO, 24.0*ns, (k_neumann<<<blocks,256,0,c->stream>>>(g->d, b, dimsOf(g), dd, offset + 2 - 4*upper, offset, ns)));
+	}
+}
+void gridBnd(Ctx *c, DevGrid *g, const MpiInfo *m){
+	const Grid *h = g->host;
+	const int rank = h->rank;
+	bool periodic = false;
+	for(int d = 1; d < rank; d++) if(h->bnd[d] == PERIODIC) periodic = true;         // (the reference looks at the lower edges only)
+	if(periodic) gridNeutralize(c, g, m);
+	if(!g->nonPeriodic) return;
+	for(int d = 1; d < rank; d++)
+		if(m->subdomain[d-1] == 0){
+			if(h->bnd[d] == DIRICHLET) gridEdge(c, g, d, DIRICHLET);
+			else if(h->bnd[d] == NEUMANN) gridEdge(c, g, d, NEUMANN);
+		}
+	for(int d = rank+1; d < 2*rank; d++)
+		if(m->subdomain[d-rank-1] == m->nSubdomains[d-rank-1]-1){
+			if(h->bnd[d] == DIRICHLET) gridEdge(c, g, d, DIRICHLET);
+			if(h->bnd[d] == NEUMANN) gridEdge(c, g, d, NEUMANN);
+		}
+}
+
 } // namespace pinc
 
 using namespace pinc;
@@ -307,13 +359,26 @@ long int gTotTruesize(const Grid *grid, const MpiInfo *mpiInfo){
 }
 void gNeutralizeGrid(Grid *grid, const MpiInfo *mpiInfo){ Ctx *c = cur(); gridNeutralize(c, devGrid(c, grid), mpiInfo); }
 
-// src/grid.c:992-1023.  Only the periodic branch is implemented (every BASELINE config is periodic;
-// Dirichlet/Neumann are SURVEY 8f-3).
-void gBnd(Grid *grid, const MpiInfo *mpiInfo){
-	for(int d = 1; d < grid->rank; d++)
-		if(grid->bnd[d] != PERIODIC || grid->bnd[d + grid->rank] != PERIODIC)
-			fatal("gBnd: only PERIODIC boundaries are implemented");
-	gNeutralizeGrid(grid, mpiInfo);
+// src/grid.c:992-1023
+void gBnd(Grid *grid, const MpiInfo *mpiInfo){ Ctx *c = cur(); gridBnd(c, devGrid(c, grid), mpiInfo); }
+// src/grid.c:929-956 / :958-990; boundary = d (lower edge) or rank + d (upper edge), d in 1..3
+void gDirichlet(Grid *grid, const int boundary, const MpiInfo *mpiInfo){ (void)mpiInfo; Ctx *c = cur(); gridEdge(c, devGrid(c, grid), boundary, DIRICHLET); }
+void gNeumann(Grid *grid, const int boundary, const MpiInfo *mpiInfo){ (void)mpiInfo; Ctx *c = cur(); gridEdge(c, devGrid(c, grid), boundary, NEUMANN); }
+// src/grid.c:608-662: constant boundary values (1 on Dirichlet, 2 on Neumann edges of the global domain) into grid->bndSlice
+void gSetBndSlices(Grid *grid, MpiInfo *mpiInfo){
+	const int rank = grid->rank;
+	if(!grid->bndSlice) fatal("gSetBndSlices: the grid has no bndSlice");
+	long nMax = 0;
+	for(int d = 0; d < rank; d++){ long n = 1; for(int dd = 0; dd < rank; dd++) if(dd != d) n *= grid->size[dd]; if(n > nMax) nMax = n; }
+	for(int d = 1; d < rank; d++){
+		if(mpiInfo->subdomain[d-1] == 0 && (grid->bnd[d] == DIRICHLET || grid->bnd[d] == NEUMANN))
+			for(long s = 0; s < nMax; s++) grid->bndSlice[s + nMax*d] = grid->bnd[d] == DIRICHLET ? 1. : 2.;
+		if(mpiInfo->subdomain[d-1] == mpiInfo->nSubdomains[d-1]-1 && (grid->bnd[d+rank] == DIRICHLET || grid->bnd[d+rank] == NEUMANN))
+			for(long s = 0; s < nMax; s++) grid->bndSlice[s + nMax*(d+rank)] = grid->bnd[d+rank] == DIRICHLET ? 1. : 2.;
+	}
+	Ctx *c = cur();
+	auto it = c->grids.find(grid);
+	if(it != c->grids.end() && it->second->nonPeriodic) gridUploadBnd(c, it->second);
 }
 
 void gHaloOpDim(funPtr sliceOp, Grid *grid, const MpiInfo *mpiInfo, int d, opDirection dir){

@@ -88,7 +88,7 @@ Grid *pincGridAlloc(int nDims, const int *trueSizeIn, const int *nGhostLayersIn,
 	g->val = zalloc<double>(g->sizeProd[rank]);
 	g->sendSlice = zalloc<double>(nSliceMax);
 	g->recvSlice = zalloc<double>(nSliceMax);
-	g->bndSlice = nullptr;                                    // only Dirichlet/Neumann use it (not implemented)
+	g->bndSlice = zalloc<double>(2*rank*nSliceMax);           // src/grid.c:467 (there uninitialised; zero here)
 	g->bnd = (bndType*)zalloc<int>(2*rank);
 	int b = 0;
 	for(int r = 0; r < 2*rank; r++){
@@ -101,7 +101,7 @@ void pincGridFree(Grid *g){
 	if(!g) return;
 	pincForget(g);
 	free(g->size); free(g->trueSize); free(g->nGhostLayers); free(g->sizeProd);
-	free(g->val); free(g->sendSlice); free(g->recvSlice); free(g->bnd);
+	free(g->val); free(g->sendSlice); free(g->recvSlice); free(g->bnd); free(g->bndSlice);
 	free(g);
 }
 

@@ -411,7 +411,7 @@ static int mgMode(){
 static int mgModeResolved(){ return mgMode(); }
 static void opGS(Ctx *c, DevGrid *phi, DevGrid *rho, int nCycles, const MpiInfo *m){
 	long nt = trueCount(phi);
-	if(m->mpiSize > 1 && mgMode() == 2 && nCycles > 0){
+	if(m->mpiSize > 1 && mgMode() == 2 && nCycles > 0 && !phi->nonPeriodic){
 		// multi-rank lean path: between half-sweeps only the faces of the decomposed dimensions are exchanged (one
 		// grouped exchange), gBnd's mean subtraction is applied once at the end (see mgcluster.cu for why that is
 		// the same function), then the full dimension-by-dimension halo restores edge and corner ghosts
@@ -447,7 +447,7 @@ static void opGS(Ctx *c, DevGrid *phi, DevGrid *rho, int nCycles, const MpiInfo 
 		for(int parity = 1; parity >= 0; parity--){
 			PINC_LAUNCH(c, K_GS, 12.0*nt, (k_gs_colour<<<tGrid(c,nt),256,0,c->stream>>>(phi->d, rho->d, phi->size[0], phi->size[1], phi->size[2], parity)));
 			gridHalo(c, phi, m, 0, 0);
-			gridNeutralize(c, phi, m);
+			gridBnd(c, phi, m);
 		}
 }
 static void opResidual(Ctx *c, DevGrid *res, DevGrid *rho, DevGrid *phi){
@@ -476,7 +476,7 @@ static void opVCycle(Ctx *c, int level, int bottom, int top, Multigrid *mgRho, M
 		gridHalo(c, rho, m, 0, 0);
 		gridNeutralize(c, rho, m);
 		opGS(c, phi, rho, mgRho->nCoarseSolve, m);
-		gridNeutralize(c, phi, m);
+		gridBnd(c, phi, m);
 		if(level > 0) opProlong(c, devGrid(c, mgRes->grids[level-1]), phi, m);
 		return;
 	}
@@ -489,9 +489,9 @@ static void opVCycle(Ctx *c, int level, int bottom, int top, Multigrid *mgRho, M
 	opVCycle(c, level+1, bottom, top, mgRho, mgPhi, mgRes, m);
 	gridAddTo(c, phi, res);
 	gridHalo(c, phi, m, 0, 0);
-	gridNeutralize(c, phi, m);
+	gridBnd(c, phi, m);
 	opGS(c, phi, rho, mgRho->nPostSmooth, m);
-	gridNeutralize(c, phi, m);
+	gridBnd(c, phi, m);
 	if(level > top) opProlong(c, devGrid(c, mgRes->grids[level-1]), phi, m);
 }
 
@@ -2089,6 +2089,31 @@ static void checkPlugins(const Multigrid *mg){
 		fatal("multigrid: only the gaussSeidelRB smoother (mgGS3D) is implemented");
 	if((mg->restrictor && mg->restrictor != mgHalfRestrict3D) || (mg->prolongator && mg->prolongator != mgBilinProl3D))
 		fatal("multigrid: only halfWeight restriction and bilinear prolongation are implemented");
+}
+
+// src/multigrid.c:1314-1379: boundary values of every coarser level := every second value of the finer level's slices
+// (host arrays; the reference defines this function and never calls it - its coarse bndSlice arrays stay uninitialised,
+// so a host that wants non-periodic multigrid calls it after gSetBndSlices on the finest level)
+void mgRestrictBnd(Multigrid *mg){
+	Ctx *c = cur();
+	for(int lvl = 0; lvl < mg->nLevels-1; lvl++){
+		Grid *f = mg->grids[lvl], *g = mg->grids[lvl+1];
+		const int rank = f->rank;
+		if(!f->bndSlice || !g->bndSlice) fatal("mgRestrictBnd: level %d has no bndSlice", lvl);
+		long nF = 0, nC = 0;
+		for(int d = 0; d < rank; d++){
+			long a = 1, b = 1;
+			for(int dd = 0; dd < rank; dd++) if(dd != d){ a *= f->size[dd]; b *= g->size[dd]; }
+			if(a > nF) nF = a;
+			if(b > nC) nC = b;
+		}
+		for(int d = 1; d < 2*rank; d++){
+			if(d == rank) continue;
+			for(long s = 0; s < nC; s++) g->bndSlice[s + nC*d] = f->bndSlice[2*s + nF*d];
+		}
+		auto it = c->grids.find(g);
+		if(it != c->grids.end() && it->second->nonPeriodic) gridUploadBnd(c, it->second);
+	}
 }
 
 void mgVRecursive(int level, int bottom, int top, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *mpiInfo){

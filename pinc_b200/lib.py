@@ -59,6 +59,10 @@ SIGNATURES = {
     "gTotTruesize": (C.c_long, [P(abi.Grid), P(abi.MpiInfo)]),
     "gNeutralizeGrid": (None, [P(abi.Grid), P(abi.MpiInfo)]),
     "gBnd": (None, [P(abi.Grid), P(abi.MpiInfo)]),
+    "gDirichlet": (None, [P(abi.Grid), C.c_int, P(abi.MpiInfo)]),
+    "gNeumann": (None, [P(abi.Grid), C.c_int, P(abi.MpiInfo)]),
+    "gSetBndSlices": (None, [P(abi.Grid), P(abi.MpiInfo)]),
+    "mgRestrictBnd": (None, [P(abi.Multigrid)]),
     "gPotEnergy": (None, [P(abi.Grid), P(abi.Grid), P(abi.Population)]),
     # multigrid
     "mgSolve": (None, [P(abi.MultigridSolver), P(abi.Grid), P(abi.Grid), P(abi.MpiInfo)]),

@@ -120,10 +120,11 @@ class World:
     def _alloc(self, r, st):
         L, cfg = self.lib, self.cfg
         nD, nS = cfg.nDims, cfg.nSpecies
-        bnd = _ia([abi.PERIODIC] * (2 * nD))
+        kinds = {"PERIODIC": abi.PERIODIC, "DIRICHLET": abi.DIRICHLET, "NEUMANN": abi.NEUMANN}
         for b in cfg.boundaries:
-            if b != "PERIODIC":
-                raise ValueError("only PERIODIC boundaries are implemented (SURVEY 8f-3)")
+            if b not in kinds:
+                raise ValueError(f"{b} invalid value for grid:boundaries")          # src/grid.c:479
+        bnd = _ia([kinds[b] for b in cfg.boundaries])                                 # lower x,y,z then upper x,y,z
         ts, gl = _ia(cfg.trueSize), _ia(cfg.nGhostLayers)
         st.mpi = L.pincMpiAlloc(nD, nS, _ia(cfg.nSubdomains), gl, ts, r, self.R)
         per_rank = [-(-a // self.R) for a in cfg.nAlloc]                    # population.c:58-64
@@ -133,6 +134,9 @@ class World:
         st.phi = L.pincGridAlloc(nD, ts, gl, abi.SCALAR, bnd)
         st.solver = L.pincMgAllocSolver(st.rho, st.phi, cfg.mgLevels, cfg.mgCycles, cfg.nPreSmooth, cfg.nPostSmooth, cfg.nCoarseSolve)
         st.res = st.solver.contents.res
+        if any(b != "PERIODIC" for b in cfg.boundaries):
+            L.gSetBndSlices(st.phi, st.mpi)                                # src/main.c:102
+            L.mgRestrictBnd(st.solver.contents.mgPhi)                      # the coarse levels' boundary values (see mgRestrictBnd)
         ne = cfg.nEmigrantsAlloc
         L.pincCreateNeighborhood(st.mpi, st.rho, _la(ne), len(ne), _da(cfg.thresholds))
         err = C.create_string_buffer(256)
