@@ -236,6 +236,15 @@ void pincMgSetRowMode(int mode);
  * all-SM persistent kernel, 2 the cluster kernel; +4: a multi-rank solve done by replication (every rank gathers rho and
  * phi, solves the global problem with the single-GPU kernel and keeps its own sub-domain) */
 int pincMgLastPath(void);
+/* Cell-slotted particle storage: while the host loops pincAccMove3D1KE -> puExtractEmigrants3D -> puMigrate
+ * -> puDistr3D1, every cell keeps its particles in slots of its own and only the particles that change cell move (instead of a
+ * counting sort of the whole population every step); any other entry point first restores the contiguous cell-ordered planes.
+ * on = 0 disables it (also $PINC_B200_SLOTTED=0); headroomPercent / extraSlots (>= 0, default 25 / 16): free slots kept per cell on
+ * top of the fullest cell's count - a cell that outgrows them sends the population back to the sort for one step.
+ * pincPopLayout: 1 while `pop` is slotted, else 0.  pincSlottedOverflows: how often that fallback ran (this process). */
+void pincSetSlotted(int on, int headroomPercent, int extraSlots);
+int pincPopLayout(const Population *pop);
+long pincSlottedOverflows(void);
 /* execution mode of single-rank periodic solves (same arithmetic per node in all of them):
  *   0 ops            one kernel per reference call, ghost layers exchanged as the reference does;
  *   1 fused          one persistent cooperative kernel over all SMs, a grid barrier and gBnd after every half-sweep;

@@ -23,7 +23,7 @@ enum KClass { K_PUSH = 0, K_MOVE, K_DEPOSIT, K_EXTRACT, K_IMPORT, K_SORT, K_GRID
 extern const char *kclassName[K_NCLASS];
 
 // device-side error bits (Ctx::d_flags[0])
-enum DevErr { ERR_POS_RANGE = 1, ERR_CAPACITY = 2, ERR_VEL_MAX = 4, ERR_P2P_TIMEOUT = 8, ERR_FIX_OVERFLOW = 16 };
+enum DevErr { ERR_POS_RANGE = 1, ERR_CAPACITY = 2, ERR_VEL_MAX = 4, ERR_P2P_TIMEOUT = 8, ERR_FIX_OVERFLOW = 16, ERR_SLOT_OVERFLOW = 32 };
 
 // fixed-point scale of the deposition accumulators: weights in [0,1] are summed as
 // round(w * 2^46) in 64-bit integers, so a node can take 2^17 particles per species before the
@@ -74,6 +74,16 @@ struct DevPop {
 	long immigCap = 0;
 	bool extracted = false;     // emigrants sit behind iStop[s], binned by neighbour, not yet packed
 	DevGrid *predep = nullptr;  // the stayers of the current positions are already deposited into this grid's accumulators
+	// Cell-slotted storage (particles.cu, "slotted mode"): while pincAccMove3D1KE runs step after step, the particles
+	// of cell c of species s live in slots [slotOff[s] + c*slotCapS[s], ... + d_cnt[s][c]) of six planes of `slotPlane`
+	// doubles and only the ~5 % that change cell move; the contiguous planes above are stale until somebody needs them.
+	bool slotted = false;
+	double *slot = nullptr; long slotPlane = 0;
+	long slotOff[9] = {0}; int slotCapS[8] = {0};
+	unsigned *d_cnt[8] = {nullptr};       // particles per cell
+	unsigned *d_mvCount = nullptr;        // [8] movers per species (the mover list of species s is alt[iStart[s]..], keys in d_keys) + [8..8+8*27) emigrants per neighbour
+	bool mvPending = false;               // the last push left movers (other cell / other rank) in the mover lists
+	bool emigInMovers = false;            // puMigrate packs the emigrants from the mover lists
 };
 
 struct ProfEvent { cudaEvent_t a, b; int cls; };
@@ -136,7 +146,9 @@ struct Ctx {
 
 Ctx *cur();                                    // current context of this host thread (created lazily)
 DevGrid *devGrid(Ctx *c, const Grid *g, bool upload = true);
-DevPop *devPop(Ctx *c, const Population *p, bool upload = true);
+DevPop *devPop(Ctx *c, const Population *p, bool upload = true);       // contiguous planes current (leaves slotted mode)
+DevPop *devPopRaw(Ctx *c, const Population *p, bool upload = true);    // whatever mode the population is in
+void popLeaveSlotted(Ctx *c, DevPop *dp);                               // particles.cu: slots -> contiguous planes
 void *tmpBuffer(Ctx *c, size_t bytes);
 double *partialBuffer(Ctx *c, long n);
 void checkDeviceFlags(Ctx *c, const char *where);      // after a stream sync

@@ -159,6 +159,7 @@ static void popUpload(Ctx *c, DevPop *dp){
 	for(int s = 0; s < dp->nS; s++) dp->sortedN[s] = 0;
 	dp->keysValid = false;
 	dp->extracted = false;
+	dp->slotted = false; dp->mvPending = false; dp->emigInMovers = false;      // the host arrays are the truth now
 	if(dp->predep){ dp->predep->fixDirty = true; dp->predep = nullptr; }
 }
 
@@ -213,6 +214,11 @@ DevGrid *devGrid(Ctx *c, const Grid *g, bool upload){
 }
 
 DevPop *devPop(Ctx *c, const Population *p, bool upload){
+	DevPop *dp = devPopRaw(c, p, upload);
+	if(dp->slotted) popLeaveSlotted(c, dp);
+	return dp;
+}
+DevPop *devPopRaw(Ctx *c, const Population *p, bool upload){
 	auto it = c->pops.find(p);
 	if(it != c->pops.end()) return it->second;
 	if(p->nDims != 3) fatal("only 3-D populations are supported");
@@ -239,6 +245,8 @@ static void freeDevPop(DevPop *p){
 	cudaFree(p->base); if(p->alt) cudaFree(p->alt); cudaFree(p->d_keys);
 	for(int s = 0; s < 8; s++){ if(p->d_hist[s]) cudaFree(p->d_hist[s]); if(p->d_cursor[s]) cudaFree(p->d_cursor[s]); }
 	if(p->d_emig) cudaFree(p->d_emig); if(p->d_immig) cudaFree(p->d_immig);
+	if(p->slot) cudaFree(p->slot); if(p->d_mvCount) cudaFree(p->d_mvCount);
+	for(int s = 0; s < 8; s++) if(p->d_cnt[s]) cudaFree(p->d_cnt[s]);
 	delete p;
 }
 

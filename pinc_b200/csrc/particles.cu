@@ -419,6 +419,255 @@ __global__ void k_import(double *__restrict__ P, long cap, long dst0, long n, Im
 	}
 }
 
+// =================================================================================================================
+// Cell-slotted storage ("slotted mode"): the steady state of pincAccMove3D1KE -> puExtractEmigrants3D -> puMigrate ->
+// puDistr3D1.  The counting sort above rewrites all 48 B of every particle every step although ~95 % of them keep
+// their cell.  Here cell c of species s owns `cap` slots of six planes; one warp per cell pushes its particles, keeps the
+// ones that stay in place (compacted towards the front of the cell's run) and appends the others - to another cell of
+// this rank, or emigrants - to the species' mover list (the second population buffer, which the sort no longer needs);
+// puExtractEmigrants3D then drops the local movers into their new cells (one atomic per mover) and counts the emigrants,
+// puMigrate packs those from the list and imports the immigrants straight into their cells, puDistr3D1 runs its
+// warp-per-cell deposition over the slots.  Per particle and step the path moves 96 B (push) + 24 B (deposit) instead
+// of 96 + 4 + 100 + 24.  A cell that outgrows its slots raises ERR_SLOT_OVERFLOW; the host then goes back to the
+// contiguous layout (popLeaveSlotted) and re-enters with a larger capacity.  Same arithmetic per particle as k_acc, same
+// integer deposition: fields are bit-identical to the sorted path, the particle ORDER differs (as it already does
+// between two runs of the scatter).
+// =================================================================================================================
+#define SLOT_OVER_KEY 0xfffffffeu          // a mover that did not fit into its cell: waits in the list for popLeaveSlotted
+struct SlotPar { double *S; long plane; long off; int cap; unsigned *cnt; };
+
+template<int KE> __global__ void __launch_bounds__(256, 4) k_cell_push(SlotPar Q, const double *__restrict__ E, long sx3, long sxy3,
+		CellSpace C, Thr T, double *__restrict__ partial, double *__restrict__ M, long mPlane, unsigned *__restrict__ mKey, unsigned *mCount, int *flags){
+	const int lane = threadIdx.x & 31;
+	const unsigned lt = (1u << lane) - 1u;
+	long warp = (blockIdx.x*(long)blockDim.x + threadIdx.x) >> 5;
+	const long nWarps = ((long)gridDim.x*blockDim.x) >> 5;
+	__shared__ double evS[8][24];
+	double acc = 0;
+	for(long c = warp; c < C.nCells; c += nWarps){
+		const unsigned n = Q.cnt[c];
+		if(n == 0) continue;
+		const int cj = (int)(c % C.nc0); const long cr = c / C.nc0; const int ck = (int)(cr % C.nc1); const int cl = (int)(cr / C.nc1);
+		const double dj = (double)cj, dk = (double)ck, dl = (double)cl;
+		const double *e0 = E + 3L*cj + ck*sx3 + cl*sxy3, *e1 = e0 + sx3, *e2 = e0 + sxy3, *e3 = e2 + sx3;
+		// the cell's eight corner fields once per cell: lane q*3+v fetches component v of corner q into the warp's shared row
+		__syncwarp();
+		if(lane < 24){
+			const int q = lane/3, v = lane - 3*q;
+			const double *ep = (q & 4 ? ((q & 2) ? e3 : e2) : ((q & 2) ? e1 : e0)) + ((q & 1) ? 3 : 0) + v;
+			evS[threadIdx.x >> 5][lane] = __ldg(ep);
+		}
+		__syncwarp();
+		const double *ev = evS[threadIdx.x >> 5];
+		double *P = Q.S + Q.off + c*(long)Q.cap;
+		unsigned wr = 0;
+		for(unsigned i0 = 0; i0 < n; i0 += 32){
+			const unsigned i = i0 + lane;
+			const bool ok = i < n;
+			double x = 0, y = 0, z = 0, vx = 0, vy = 0, vz = 0;
+			unsigned key = 0xffffffffu;
+			if(ok){
+				x = P[i]; y = P[i + Q.plane]; z = P[i + 2*Q.plane];
+				vx = P[i + 3*Q.plane]; vy = P[i + 4*Q.plane]; vz = P[i + 5*Q.plane];
+				const double xf = x-dj, yf = y-dk, zf = z-dl;
+				const double xc = 1-xf, yc = 1-yf, zc = 1-zf;
+				double dv[3];
+				#pragma unroll
+				for(int v = 0; v < 3; v++)
+					dv[v] = zc*( yc*(xc*ev[v]+xf*ev[3+v]) + yf*(xc*ev[6+v]+xf*ev[9+v]) )
+					      + zf*( yc*(xc*ev[12+v]+xf*ev[15+v]) + yf*(xc*ev[18+v]+xf*ev[21+v]) );
+				if(KE){
+					double v2 = 0;
+					v2 += vx*(vx+dv[0]); v2 += vy*(vy+dv[1]); v2 += vz*(vz+dv[2]);
+					acc += v2;
+				}
+				vx += dv[0]; vy += dv[1]; vz += dv[2];
+				x += vx; y += vy; z += vz;
+				key = classify(x, y, z, T, C, flags);
+			}
+			const bool stay = ok && key == (unsigned)c;
+			// (the ballots need every lane's key, hence every lane's loads: no lane stores into a slot another lane still has to read)
+			const unsigned ms = __ballot_sync(0xffffffffu, stay), mm = __ballot_sync(0xffffffffu, ok && !stay);
+			if(stay){
+				const unsigned d = wr + __popc(ms & lt);
+				P[d] = x; P[d + Q.plane] = y; P[d + 2*Q.plane] = z;
+				P[d + 3*Q.plane] = vx; P[d + 4*Q.plane] = vy; P[d + 5*Q.plane] = vz;
+			}
+			if(mm){
+				unsigned b = 0;
+				const int leader = __ffs(mm) - 1;
+				if(lane == leader) b = atomicAdd(mCount, (unsigned)__popc(mm));
+				b = __shfl_sync(0xffffffffu, b, leader);
+				if(ok && !stay){
+					const unsigned d = b + __popc(mm & lt);
+					M[d] = x; M[d + mPlane] = y; M[d + 2*mPlane] = z;
+					M[d + 3*mPlane] = vx; M[d + 4*mPlane] = vy; M[d + 5*mPlane] = vz;
+					mKey[d] = key;
+				}
+			}
+			wr += __popc(ms);
+		}
+		if(lane == 0) Q.cnt[c] = wr;
+	}
+	if(KE){
+		acc = blockSumP<256>(acc);
+		if(threadIdx.x == 0) partial[blockIdx.x] = acc;
+	}
+}
+// movers of this rank into their new cells; emigrants are counted per neighbour (they stay in the list for puMigrate)
+__global__ void k_mv_insert(SlotPar Q, const double *__restrict__ M, long mPlane, unsigned *__restrict__ mKey, const unsigned *mCount,
+		CellSpace C, unsigned *__restrict__ emHist, int *flags){
+	const long n = *mCount;
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; i < n; i += st){
+		const unsigned key = mKey[i];
+		if(key >= (unsigned)C.nCells){ if(key != SLOT_OVER_KEY) atomicAdd(&emHist[key - (unsigned)C.nCells], 1u); continue; }
+		const unsigned slot = atomicAdd(&Q.cnt[key], 1u);
+		if(slot >= (unsigned)Q.cap){ atomicOr(flags, ERR_SLOT_OVERFLOW); mKey[i] = SLOT_OVER_KEY; continue; }
+		double *P = Q.S + Q.off + (long)key*Q.cap + slot;
+		#pragma unroll
+		for(int w = 0; w < 6; w++) P[w*Q.plane] = M[i + w*mPlane];
+	}
+}
+// emigrants from the mover list into the message buffer, neighbour by neighbour (order inside a neighbour: arrival)
+struct MvPackPar { long dstOff[27]; };
+__global__ void k_mv_pack(const double *__restrict__ M, long mPlane, const unsigned *__restrict__ mKey, const unsigned *mCount, CellSpace C,
+		MvPackPar pp, unsigned *__restrict__ cursor, double *__restrict__ out){
+	const long n = *mCount;
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; i < n; i += st){
+		const unsigned key = mKey[i];
+		if(key < (unsigned)C.nCells || key == SLOT_OVER_KEY) continue;
+		const int ne = (int)(key - (unsigned)C.nCells);
+		const long d = pp.dstOff[ne] + atomicAdd(&cursor[ne], 1u);
+		#pragma unroll
+		for(int w = 0; w < 6; w++) out[6*d + w] = M[i + w*mPlane];
+	}
+}
+// immigrants (records, shifted into the local frame as k_import does) straight into their cells
+__global__ void k_import_cells(SlotPar Q, long n, ImportPar ip, const double *__restrict__ in, CellSpace C,
+		double *__restrict__ M, long mPlane, unsigned *__restrict__ mKey, unsigned *mCount, int *flags){
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; i < n; i += st){
+		long r = i; int ne = 0;
+		while(ne < 26 && r >= ip.cnt[ne]){ r -= ip.cnt[ne]; ne++; }
+		const double *rec = in + 6*(ip.srcOff[ne] + r);
+		double v[6];
+		#pragma unroll
+		for(int w = 0; w < 3; w++){ v[w] = rec[w]; v[w] += ip.shift[ne][w]; }
+		#pragma unroll
+		for(int w = 3; w < 6; w++) v[w] = rec[w];
+		int j = (int)v[0], k = (int)v[1], l = (int)v[2];
+		if(!(v[0] >= 0) || !(v[1] >= 0) || !(v[2] >= 0) || j >= C.nc0 || k >= C.nc1 || l >= C.nc2){
+			atomicOr(flags, ERR_POS_RANGE);
+			j = min(max(j,0),C.nc0-1); k = min(max(k,0),C.nc1-1); l = min(max(l,0),C.nc2-1);
+		}
+		const unsigned key = (unsigned)(j + C.nc0*(k + (long)C.nc1*l));
+		const unsigned slot = atomicAdd(&Q.cnt[key], 1u);
+		if(slot >= (unsigned)Q.cap){
+			atomicOr(flags, ERR_SLOT_OVERFLOW);
+			const unsigned d = atomicAdd(mCount, 1u);
+			#pragma unroll
+			for(int w = 0; w < 6; w++) M[d + w*mPlane] = v[w];
+			mKey[d] = SLOT_OVER_KEY;
+			continue;
+		}
+		double *P = Q.S + Q.off + (long)key*Q.cap + slot;
+		#pragma unroll
+		for(int w = 0; w < 6; w++) P[w*Q.plane] = v[w];
+	}
+}
+// contiguous cell-ordered planes <-> slots: one warp per cell copies the cell's run
+__global__ void k_cells_copy(SlotPar Q, double *__restrict__ B, long bPlane, const unsigned *__restrict__ cellStart, long nCells, int toSlots){
+	const int lane = threadIdx.x & 31;
+	long warp = (blockIdx.x*(long)blockDim.x + threadIdx.x) >> 5;
+	const long nWarps = ((long)gridDim.x*blockDim.x) >> 5;
+	for(long c = warp; c < nCells; c += nWarps){
+		const unsigned b = cellStart[c], n = cellStart[c+1] - b;
+		double *P = Q.S + Q.off + c*(long)Q.cap;
+		for(unsigned i = lane; i < n; i += 32){
+			#pragma unroll
+			for(int w = 0; w < 6; w++){ if(toSlots) P[i + w*Q.plane] = B[b + i + w*bPlane]; else B[b + i + w*bPlane] = P[i + w*Q.plane]; }
+		}
+		if(toSlots && lane == 0) Q.cnt[c] = n;
+	}
+}
+// particles that are not in cell order (the unsorted tail behind sortedN) into their cells
+__global__ void k_tail_insert(SlotPar Q, const double *__restrict__ B, long bPlane, long n, CellSpace C, int *flags){
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; i < n; i += st){
+		double x = B[i], y = B[i + bPlane], z = B[i + 2*bPlane];
+		int j = (int)x, k = (int)y, l = (int)z;
+		if(!(x >= 0) || !(y >= 0) || !(z >= 0) || j >= C.nc0 || k >= C.nc1 || l >= C.nc2){ atomicOr(flags, ERR_SLOT_OVERFLOW); continue; }
+		const unsigned key = (unsigned)(j + C.nc0*(k + (long)C.nc1*l));
+		const unsigned slot = atomicAdd(&Q.cnt[key], 1u);
+		if(slot >= (unsigned)Q.cap){ atomicOr(flags, ERR_SLOT_OVERFLOW); continue; }
+		double *P = Q.S + Q.off + (long)key*Q.cap + slot;
+		#pragma unroll
+		for(int w = 0; w < 6; w++) P[w*Q.plane] = B[i + w*bPlane];
+	}
+}
+// cell counts (clipped to the capacity: an overflowing cell's extra particles wait in the mover list) -> histogram for the scan
+__global__ void k_cnt_to_hist(const unsigned *__restrict__ cnt, unsigned *__restrict__ hist, long nCells, long nKeys1, int cap){
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; i < nKeys1; i += st) hist[i] = i < nCells ? min(cnt[i], (unsigned)cap) : 0u;
+}
+// movers of the list that are still waiting (all of them before puExtractEmigrants3D, the overflowed ones after) -> behind the cells' particles
+__global__ void k_mv_append(const double *__restrict__ M, long mPlane, const unsigned *__restrict__ mKey, const unsigned *mCount, int onlyOver,
+		double *__restrict__ B, long bPlane, unsigned *cursor){
+	const long n = *mCount;
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; i < n; i += st){
+		if(onlyOver && mKey[i] != SLOT_OVER_KEY) continue;
+		const unsigned d = atomicAdd(cursor, 1u);
+		#pragma unroll
+		for(int w = 0; w < 6; w++) B[d + w*bPlane] = M[i + w*mPlane];
+	}
+}
+__global__ void k_max_run(const unsigned *__restrict__ cellStart, long nCells, unsigned *out){
+	unsigned m = 0;
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; i < nCells; i += st) m = max(m, cellStart[i+1] - cellStart[i]);
+	for(int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+	if((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+// deposition over the slots: k_distr_cells with the cell's run taken from the slot array
+__global__ void __launch_bounds__(256, 4) k_distr_slots(SlotPar Q, CellSpace C, long sx, long sxy, long long *__restrict__ fix){
+	int lane = threadIdx.x & 31;
+	long warp = (blockIdx.x*(long)blockDim.x + threadIdx.x) >> 5;
+	long nWarps = ((long)gridDim.x*blockDim.x) >> 5;
+	for(long c = warp; c < C.nCells; c += nWarps){
+		const unsigned e = Q.cnt[c];
+		if(e == 0) continue;
+		const double *X = Q.S + Q.off + c*(long)Q.cap, *Y = X + Q.plane, *Z = Y + Q.plane;
+		long long a[8];
+		#pragma unroll
+		for(int q = 0; q < 8; q++) a[q] = 0;
+		const int cj = (int)(c % C.nc0); const long cr = c / C.nc0; const int ck = (int)(cr % C.nc1); const int cl = (int)(cr / C.nc1);
+		const double dj = (double)cj, dk = (double)ck, dl = (double)cl;
+		for(unsigned i0 = 0; i0 < e; i0 += 96){
+			double x[3], y[3], z[3];
+			#pragma unroll
+			for(int u = 0; u < 3; u++){
+				unsigned i = i0 + lane + 32*u;
+				bool ok = i < e;
+				x[u] = ok ? X[i] : 0.0; y[u] = ok ? Y[i] : 0.0; z[u] = ok ? Z[i] : 0.0;
+			}
+			#pragma unroll
+			for(int u = 0; u < 3; u++){
+				if(i0 + lane + 32*u >= e) continue;
+				long long w[8];
+				cornerWeights(x[u]-dj, y[u]-dk, z[u]-dl, w);
+				#pragma unroll
+				for(int q = 0; q < 8; q++) a[q] += w[q];
+			}
+		}
+		long long tot = warpCornerTotal(a);
+		if((lane & 3) == 0 && tot != 0)
+			atomicAdd((unsigned long long*)&fix[cj + sx*ck + sxy*cl + cornerOffset(sx, sxy)], (unsigned long long)tot);
+	}
+}
+
 // ---- debug scans of the driver loop (src/population.c:316-365) ------------------------------------------------
 // three planes starting at `P` are compared with lo <= v <= hi[d]; the first offender is recorded (species-local index,
 // dimension) by an atomicMin on index*4+dimension
@@ -454,9 +703,11 @@ static void setupCells(Ctx *c, DevPop *dp, const MpiInfo *m){
 	if(nCells + 28 >= 0xffffffffL) fatal("cell space too large for 32-bit keys");
 	if(dp->nCells == nCells && dp->nc[0] == nc[0] && dp->nc[1] == nc[1] && dp->d_hist[0]) return;
 	streamSync(c);
+	if(dp->slotted) fatal("setupCells: the cell space changed under a slotted population");
 	for(int s = 0; s < dp->nS; s++){
 		if(dp->d_hist[s]) cudaFree(dp->d_hist[s]);
 		if(dp->d_cursor[s]) cudaFree(dp->d_cursor[s]);
+		if(dp->d_cnt[s]){ cudaFree(dp->d_cnt[s]); dp->d_cnt[s] = nullptr; }
 		PINC_CUDA(cudaMalloc(&dp->d_hist[s], (size_t)(nCells+28)*sizeof(unsigned)));
 		PINC_CUDA(cudaMalloc(&dp->d_cursor[s], (size_t)(nCells+28)*sizeof(unsigned)));
 		dp->sortedN[s] = 0;
@@ -481,6 +732,155 @@ static void invalidateOrder(DevPop *dp){
 	dp->keysValid = false;
 }
 
+static void scanHist(Ctx *c, unsigned *h, long n);
+// ---- slotted mode, host side --------------------------------------------------------------------------------
+static int g_slotted = -1;              // $PINC_B200_SLOTTED=0 keeps the counting sort every step
+static int g_slotHeadroom = 25;         // per cent of the fullest cell, plus g_slotExtra slots, kept free in every cell
+static int g_slotExtra = 16;
+static long g_slotOverflows = 0;        // how often a full cell sent a population back to the contiguous layout
+static bool slottedEnabled(){ if(g_slotted < 0) g_slotted = (getenv("PINC_B200_SLOTTED") && atoi(getenv("PINC_B200_SLOTTED")) == 0) ? 0 : 1; return g_slotted != 0; }
+static SlotPar slotPar(const DevPop *dp, int s){ return SlotPar{ dp->slot, dp->slotPlane, dp->slotOff[s], dp->slotCapS[s], dp->d_cnt[s] }; }
+static double *mvBase(const DevPop *dp, int s){ return dp->alt + dp->host->iStart[s]; }         // six planes of stride dp->cap
+static unsigned *mvKeys(const DevPop *dp, int s){ return dp->d_keys + dp->host->iStart[s]; }
+enum { MV_COUNT = 0, MV_EMHIST = 8, MV_SCRATCH = 8 + 8*27, MV_WORDS = 8 + 8*27 + 16 };
+static int cellBlocks(Ctx *c, long nCells){ return gridFor(nCells*32, 256, c->numSMs*8); }
+// did a cell run out of slots since the last call?  (other device errors stay fatal)
+static bool takeSlotOverflow(Ctx *c, const char *where){
+	PINC_CUDA(cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	streamSync(c);
+	int f = c->h_flags[0];
+	if(!(f & ERR_SLOT_OVERFLOW)){ if(f) checkDeviceFlags(c, where); return false; }
+	if(f & ~ERR_SLOT_OVERFLOW) checkDeviceFlags(c, where);
+	PINC_CUDA(cudaMemsetAsync(c->d_flags, 0, sizeof(int), c->stream));
+	return true;
+}
+// slots -> contiguous cell-ordered planes (+ whatever waits in the mover lists as an unsorted tail): the state the sorted
+// path leaves, so every other entry point works unchanged
+void popLeaveSlotted(Ctx *c, DevPop *dp){
+	if(!dp->slotted) return;
+	const Population *pop = dp->host;
+	const long nKeys = dp->nCells + 27;
+	for(int s = 0; s < dp->nS; s++){
+		const long a = pop->iStart[s];
+		PINC_LAUNCH(c, K_SORT, 8.0*nKeys, (k_cnt_to_hist<<<gridFor(nKeys+1,256,c->numSMs*8),256,0,c->stream>>>(dp->d_cnt[s], dp->d_hist[s], dp->nCells, nKeys+1, dp->slotCapS[s])));
+		scanHist(c, dp->d_hist[s], nKeys+1);
+		long nIn = pop->iStop[s] - a;
+		if(nIn > 0) PINC_LAUNCH(c, K_SORT, 96.0*nIn, (k_cells_copy<<<cellBlocks(c,dp->nCells),256,0,c->stream>>>(slotPar(dp,s), dp->base + a, dp->cap, dp->d_hist[s], dp->nCells, 0)));
+		unsigned *cursor = dp->d_mvCount + MV_SCRATCH + s;
+		PINC_CUDA(cudaMemcpyAsync(cursor, dp->d_hist[s] + dp->nCells, sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
+		PINC_LAUNCH(c, K_SORT, 96.0, (k_mv_append<<<pGrid(c, nIn/8 + 1024),256,0,c->stream>>>(mvBase(dp,s), dp->cap, mvKeys(dp,s), dp->d_mvCount + MV_COUNT + s,
+			dp->mvPending ? 0 : 1, dp->base + a, dp->cap, cursor)));
+		PINC_CUDA(cudaMemcpyAsync(c->h_long + 2*s, dp->d_hist[s] + dp->nCells, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+		PINC_CUDA(cudaMemcpyAsync((unsigned*)(c->h_long + 2*s) + 1, cursor, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+	}
+	streamSync(c);
+	for(int s = 0; s < dp->nS; s++){
+		const unsigned *h = (const unsigned*)(c->h_long + 2*s);
+		long n = pop->iStop[s] - pop->iStart[s];
+		if((long)h[1] != n) fatal("slotted population of species %d holds %u particles, the host counts %ld", s, h[1], n);
+		dp->sortedN[s] = h[0];
+	}
+	dp->slotted = false;
+	if(dp->mvPending){ dp->keysValid = false; dp->mvPending = false; }
+}
+// contiguous cell-ordered planes -> slots; false (population unchanged) if it is not binned yet or a cell would not fit
+static bool enterSlotted(Ctx *c, DevPop *dp, const MpiInfo *m){
+	const Population *pop = dp->host;
+	if(!slottedEnabled() || dp->extracted || dp->predep) return false;
+	setupCells(c, dp, m);
+	for(int s = 0; s < dp->nS; s++) if(pop->iStop[s] > pop->iStart[s] && dp->sortedN[s] == 0) return false;       // the sort has to run once
+	if(!dp->alt) PINC_CUDA(cudaMalloc(&dp->alt, (size_t)6*(dp->cap > 0 ? dp->cap : 1)*sizeof(double)));
+	if(!dp->d_mvCount) PINC_CUDA(cudaMalloc(&dp->d_mvCount, MV_WORDS*sizeof(unsigned)));
+	PINC_CUDA(cudaMemsetAsync(dp->d_mvCount, 0, MV_WORDS*sizeof(unsigned), c->stream));
+	for(int s = 0; s < dp->nS; s++)
+		if(dp->sortedN[s] > 0) PINC_LAUNCH(c, K_SORT, 4.0*dp->nCells, (k_max_run<<<gridFor(dp->nCells,256,c->numSMs*8),256,0,c->stream>>>(dp->d_hist[s], dp->nCells, dp->d_mvCount + MV_SCRATCH + s)));
+	PINC_CUDA(cudaMemcpyAsync(c->h_long, dp->d_mvCount + MV_SCRATCH, 8*sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+	streamSync(c);
+	long total = 0;
+	for(int s = 0; s < dp->nS; s++){
+		long mx = ((const unsigned*)c->h_long)[s];
+		long cap = mx + mx*g_slotHeadroom/100 + g_slotExtra;       // head room for fluctuations: a cell that outgrows it sends the population back to the sort
+		cap = (cap + 3) & ~3L;
+		dp->slotCapS[s] = (int)cap;
+		dp->slotOff[s] = total;
+		total += dp->nCells*cap;
+	}
+	dp->slotOff[dp->nS] = total;
+	if(total > dp->slotPlane){
+		size_t freeB = 0, totB = 0;
+		cudaMemGetInfo(&freeB, &totB);
+		size_t have = dp->slot ? (size_t)6*dp->slotPlane*sizeof(double) : 0;
+		if((size_t)6*total*sizeof(double) > (freeB + have)/2) return false;        // not worth squeezing the device for
+		if(dp->slot){ PINC_CUDA(cudaFree(dp->slot)); dp->slot = nullptr; dp->slotPlane = 0; }
+		long want = total + total/16;
+		if(cudaMalloc(&dp->slot, (size_t)6*want*sizeof(double)) != cudaSuccess){ cudaGetLastError(); return false; }
+		dp->slotPlane = want;
+	}
+	PINC_CUDA(cudaMemsetAsync(dp->d_mvCount, 0, MV_WORDS*sizeof(unsigned), c->stream));
+	for(int s = 0; s < dp->nS; s++){
+		if(!dp->d_cnt[s]) PINC_CUDA(cudaMalloc(&dp->d_cnt[s], (size_t)(dp->nCells+28)*sizeof(unsigned)));
+		PINC_CUDA(cudaMemsetAsync(dp->d_cnt[s], 0, (size_t)(dp->nCells+28)*sizeof(unsigned), c->stream));
+		const long a = pop->iStart[s], n = pop->iStop[s] - a, ns = dp->sortedN[s] < n ? dp->sortedN[s] : n;
+		if(ns > 0) PINC_LAUNCH(c, K_SORT, 96.0*ns, (k_cells_copy<<<cellBlocks(c,dp->nCells),256,0,c->stream>>>(slotPar(dp,s), dp->base + a, dp->cap, dp->d_hist[s], dp->nCells, 1)));
+		if(n - ns > 0) PINC_LAUNCH(c, K_SORT, 96.0*(n-ns), (k_tail_insert<<<pGrid(c,n-ns),256,0,c->stream>>>(slotPar(dp,s), dp->base + a + ns, dp->cap, n - ns, cellsOf(dp), c->d_flags)));
+	}
+	if(takeSlotOverflow(c, "entering slotted mode")){ g_slotOverflows++; return false; }
+	dp->slotted = true; dp->mvPending = false; dp->emigInMovers = false;
+	return true;
+}
+// pincAccMove3D1KE on the slots: kick + move + re-binning of every species, one warp per cell
+static void cellPush(Ctx *c, DevPop *dp, Population *pop, DevGrid *E, int ke, const MpiInfo *m){
+	const long sx3 = 3L*E->size[0], sxy3 = sx3*E->size[1];
+	if(dp->nc[0] > E->size[0]-1 || dp->nc[1] > E->size[1]-1 || dp->nc[2] > E->size[2]-1) fatal("pincAccMove3D1KE: E is smaller than the migration thresholds allow");
+	const Thr thr = thrOf(m); const CellSpace C = cellsOf(dp);
+	const int blocks = cellBlocks(c, dp->nCells);
+	double *partial = ke ? partialBuffer(c, (long)blocks*dp->nS) : nullptr;
+	PINC_CUDA(cudaMemsetAsync(dp->d_mvCount, 0, MV_WORDS*sizeof(unsigned), c->stream));
+	for(int s = 0; s < dp->nS; s++){
+		const long n = pop->iStop[s] - pop->iStart[s];
+		gridScale(c, E, pop->charge[s]/pop->mass[s]);          // quirk Q2, as accelerate()
+		double *part = ke ? partial + (long)s*blocks : nullptr;
+		if(n > 0){
+			if(ke) PINC_LAUNCH(c, K_PUSH, 96.0*n, (k_cell_push<1><<<blocks,256,0,c->stream>>>(slotPar(dp,s), E->d, sx3, sxy3, C, thr, part, mvBase(dp,s), dp->cap, mvKeys(dp,s), dp->d_mvCount + MV_COUNT + s, c->d_flags)));
+			else   PINC_LAUNCH(c, K_PUSH, 96.0*n, (k_cell_push<0><<<blocks,256,0,c->stream>>>(slotPar(dp,s), E->d, sx3, sxy3, C, thr, part, mvBase(dp,s), dp->cap, mvKeys(dp,s), dp->d_mvCount + MV_COUNT + s, c->d_flags)));
+		}
+		if(ke) PINC_LAUNCH(c, K_REDUCE, 8.0*blocks, (k_final_sum_p<<<1,256,0,c->stream>>>(part, n > 0 ? blocks : 0, c->d_scal + 16 + s)));
+		gridScale(c, E, pop->mass[s]/pop->charge[s]);
+	}
+	dp->mvPending = true;
+	for(int d = 0; d < 6; d++) dp->keyThr[d] = m->thresholds[d];
+	if(ke){
+		PINC_CUDA(cudaMemcpyAsync(c->h_scal + 16, c->d_scal + 16, dp->nS*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		streamSync(c);
+		for(int s = 0; s < dp->nS; s++){
+			pop->kinEnergy[s] = c->h_scal[16+s];
+			pop->kinEnergy[s] *= 0.5*pop->mass[s];
+		}
+	}
+}
+// puExtractEmigrants3D on the slots: the local movers drop into their cells, the emigrants are counted and wait in the list
+static void cellExtract(Ctx *c, DevPop *dp, Population *pop, MpiInfo *m){
+	const int nS = dp->nS;
+	const CellSpace C = cellsOf(dp);
+	for(int s = 0; s < nS; s++){
+		const long n = pop->iStop[s] - pop->iStart[s];
+		if(n > 0) PINC_LAUNCH(c, K_EXTRACT, 100.0*(n/16), (k_mv_insert<<<pGrid(c, n/8 + 1024),256,0,c->stream>>>(slotPar(dp,s), mvBase(dp,s), dp->cap, mvKeys(dp,s), dp->d_mvCount + MV_COUNT + s,
+			C, dp->d_mvCount + MV_EMHIST + 27*s, c->d_flags)));
+	}
+	PINC_CUDA(cudaMemcpyAsync(c->h_long, dp->d_mvCount, MV_SCRATCH*sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+	const bool over = takeSlotOverflow(c, "puExtractEmigrants3D");          // (synchronises)
+	const unsigned *h = (const unsigned*)c->h_long;
+	dp->mvPending = false;
+	dp->emigInMovers = true;
+	dp->extracted = true;
+	for(int s = 0; s < nS; s++){
+		long em = 0;
+		for(int ne = 0; ne < 27; ne++){ m->nEmigrants[ne*nS+s] = h[MV_EMHIST + 27*s + ne]; em += h[MV_EMHIST + 27*s + ne]; }
+		pop->iStop[s] -= em;
+	}
+	if(over){ g_slotOverflows++; popLeaveSlotted(c, dp); }       // the movers that found their cell full become the unsorted tail of the contiguous planes
+}
+
 enum AccKind { ACC_LEAP = 0, ACC_BORIS = 1 };
 static void ensureFix(Ctx *c, DevGrid *rho, int nS){
 	for(int s = 0; s < nS; s++) if(!rho->d_fixS[s]){
@@ -495,9 +895,15 @@ static void ensureFix(Ctx *c, DevGrid *rho, int nS){
 static void dropPredeposit(DevPop *dp){ if(dp->predep){ dp->predep->fixDirty = true; dp->predep = nullptr; } }
 
 static void accelerate(Ctx *c, Population *pop, Grid *Egrid, int kind, int ke, const double *T, const double *S, const MpiInfo *fuse, Grid *rhoGrid = nullptr){
-	DevPop *dp = devPop(c, pop);
+	DevPop *dp = devPopRaw(c, pop);
 	DevGrid *E = devGrid(c, Egrid);
 	if(E->nv != 3) fatal("accelerator needs a 3-vector field grid");
+	{	// slotted mode: the steady state of pincAccMove3D1KE (leapfrog kick + move + re-binning, no fused deposition)
+		const bool eligible = fuse && kind == ACC_LEAP && !rhoGrid && slottedEnabled();
+		if(dp->slotted && (!eligible || dp->mvPending || dp->extracted)) popLeaveSlotted(c, dp);
+		if(eligible && !dp->slotted) enterSlotted(c, dp, fuse);
+		if(dp->slotted){ cellPush(c, dp, pop, E, ke, fuse); return; }
+	}
 	long sx3 = 3L*E->size[0], sxy3 = sx3*E->size[1];
 	Thr thr{}; CellSpace C{1,1,1,1};
 	DevGrid *rho = nullptr;
@@ -605,8 +1011,14 @@ void pincGet3DRotationParameters(int nSpecies, const double *BExt, const double 
 
 // src/pusher.c:782-855 as a counting sort (see the header comment)
 void puExtractEmigrants3D(Population *pop, MpiInfo *mpiInfo){
-	Ctx *c = cur(); DevPop *dp = devPop(c, pop);
+	Ctx *c = cur(); DevPop *dp = devPopRaw(c, pop);
 	if(dp->extracted) fatal("puExtractEmigrants3D called twice without puMigrate");
+	if(dp->slotted){
+		bool sameThr = true;
+		for(int d = 0; d < 6; d++) if(dp->keyThr[d] != mpiInfo->thresholds[d]) sameThr = false;
+		if(dp->mvPending && sameThr){ cellExtract(c, dp, pop, mpiInfo); return; }
+		popLeaveSlotted(c, dp);
+	}
 	setupCells(c, dp, mpiInfo);
 	if(dp->keysValid) for(int d = 0; d < 6; d++) if(dp->keyThr[d] != mpiInfo->thresholds[d]) dp->keysValid = false;
 	if(!dp->alt) PINC_CUDA(cudaMalloc(&dp->alt, (size_t)6*(dp->cap > 0 ? dp->cap : 1)*sizeof(double)));
@@ -643,7 +1055,7 @@ void puExtractEmigrants3D(Population *pop, MpiInfo *mpiInfo){
 // src/pusher.c:914-1035: counts first, then the (x,y,z,vx,vy,vz) records; immigrants are shifted by
 // (direction they came from)*trueSize and appended species by species in ascending neighbour index.
 void puMigrate(Population *pop, MpiInfo *mpiInfo, Grid *grid){
-	Ctx *c = cur(); DevPop *dp = devPop(c, pop);
+	Ctx *c = cur(); DevPop *dp = devPopRaw(c, pop);
 	if(!dp->extracted) fatal("puMigrate: call puExtractEmigrants3D first");
 	int nS = dp->nS;
 	if(27*nS > 1024/2) fatal("too many species");
@@ -678,6 +1090,21 @@ void puMigrate(Population *pop, MpiInfo *mpiInfo, Grid *grid){
 		dp->immigCap = imOff[27] + imOff[27]/2 + 1024;
 		PINC_CUDA(cudaMalloc(&dp->d_immig, (size_t)dp->immigCap*6*sizeof(double)));
 	}
+	if(dp->emigInMovers){
+		// slotted mode: the emigrants wait in the species' mover lists (cellExtract)
+		for(int s = 0; s < nS; s++){
+			MvPackPar pp; long tot = 0;
+			for(int ne = 0; ne < 27; ne++){
+				long inMsg = 0;
+				for(int s2 = 0; s2 < s; s2++) inMsg += nEm[ne*nS+s2];
+				pp.dstOff[ne] = emOff[ne] + inMsg; tot += nEm[ne*nS+s];
+			}
+			if(tot <= 0) continue;
+			PINC_CUDA(cudaMemsetAsync(dp->d_cursor[s], 0, 27*sizeof(unsigned), c->stream));
+			long cap = pop->iStart[s+1] - pop->iStart[s];
+			PINC_LAUNCH(c, K_EXTRACT, 96.0*tot, (k_mv_pack<<<pGrid(c, cap/8 + 1024),256,0,c->stream>>>(mvBase(dp,s), dp->cap, mvKeys(dp,s), dp->d_mvCount + MV_COUNT + s, cellsOf(dp), pp, dp->d_cursor[s], dp->d_emig)));
+		}
+	} else
 	for(int s = 0; s < nS; s++){
 		PackPar pp;
 		long run = pop->iStop[s] - pop->iStart[s];          // emigrants start right behind the stayers
@@ -716,15 +1143,32 @@ void puMigrate(Population *pop, MpiInfo *mpiInfo, Grid *grid){
 		}
 		if(pop->iStop[s] + tot > pop->iStart[s+1])
 			fatal("puMigrate: species %d overflows its allocation (%ld + %ld immigrants > %ld)", s, pop->iStop[s]-pop->iStart[s], tot, pop->iStart[s+1]-pop->iStart[s]);
-		if(tot > 0) PINC_LAUNCH(c, K_IMPORT, 96.0*tot, (k_import<<<pGrid(c,tot),256,0,c->stream>>>(dp->base, dp->cap, pop->iStop[s], tot, ip, dp->d_immig)));
+		if(tot > 0 && dp->slotted) PINC_LAUNCH(c, K_IMPORT, 96.0*tot, (k_import_cells<<<pGrid(c,tot),256,0,c->stream>>>(slotPar(dp,s), tot, ip, dp->d_immig, cellsOf(dp),
+			mvBase(dp,s), dp->cap, mvKeys(dp,s), dp->d_mvCount + MV_COUNT + s, c->d_flags)));
+		else if(tot > 0) PINC_LAUNCH(c, K_IMPORT, 96.0*tot, (k_import<<<pGrid(c,tot),256,0,c->stream>>>(dp->base, dp->cap, pop->iStop[s], tot, ip, dp->d_immig)));
 		pop->iStop[s] += tot;
 	}
 	dp->extracted = false;
+	dp->emigInMovers = false;
+	if(dp->slotted && takeSlotOverflow(c, "puMigrate")){ g_slotOverflows++; popLeaveSlotted(c, dp); }      // immigrants that found their cell full are the tail now
 }
 
 void puDistr3D1(const Population *pop, Grid *rhoGrid){
-	Ctx *c = cur(); DevPop *dp = devPop(c, pop); DevGrid *rho = devGrid(c, rhoGrid);
+	Ctx *c = cur(); DevPop *dp = devPopRaw(c, pop); DevGrid *rho = devGrid(c, rhoGrid);
 	if(rho->nv != 1) fatal("puDistr3D1 needs a scalar grid");
+	if(dp->slotted && (dp->mvPending || dp->nc[0] > rho->size[0]-1 || dp->nc[1] > rho->size[1]-1 || dp->nc[2] > rho->size[2]-1)) popLeaveSlotted(c, dp);
+	if(dp->slotted){
+		dropPredeposit(dp);
+		ensureFix(c, rho, dp->nS);
+		gridZero(c, rho);
+		const long sx = rho->size[0], sxy = sx*rho->size[1];
+		for(int s = 0; s < dp->nS; s++){
+			const long n = pop->iStop[s] - pop->iStart[s];
+			if(n > 0) PINC_LAUNCH(c, K_DEPOSIT, 24.0*n, (k_distr_slots<<<cellBlocks(c,dp->nCells),256,0,c->stream>>>(slotPar(dp,s), cellsOf(dp), sx, sxy, rho->d_fixS[s])));
+			PINC_LAUNCH(c, K_DEPOSIT, 32.0*rho->n, (k_distr_finalize<<<gridFor(rho->n,256,c->numSMs*8),256,0,c->stream>>>(rho->d, rho->d_fixS[s], rho->n, 1.0/pop->charge[s], pop->charge[s], c->d_flags)));
+		}
+		return;
+	}
 	bool pre = dp->predep == rho;                 // the stayers were deposited by pincAccMoveDistr3D1KE
 	if(!pre) dropPredeposit(dp);
 	ensureFix(c, rho, dp->nS);
@@ -805,6 +1249,14 @@ void pVelAssertMax(const Population *pop, double max){
 }
 
 // src/population.c:700-710 (host arithmetic on the small per-species scalars)
+void pincSetSlotted(int on, int headroomPercent, int extraSlots){
+	g_slotted = on ? 1 : 0;
+	if(headroomPercent >= 0) g_slotHeadroom = headroomPercent;
+	if(extraSlots >= 0) g_slotExtra = extraSlots;
+}
+int pincPopLayout(const Population *pop){ Ctx *c = cur(); auto it = c->pops.find(pop); return it != c->pops.end() && it->second->slotted ? 1 : 0; }
+long pincSlottedOverflows(void){ return g_slotOverflows; }
+
 void pSumKinEnergy(Population *pop){
 	int nS = pop->nSpecies;
 	pop->kinEnergy[nS] = 0;

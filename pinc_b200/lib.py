@@ -80,6 +80,9 @@ SIGNATURES = {
     "pincMgSetMode": (None, [C.c_int]),
     "pincMgSetReplica": (None, [C.c_int]),
     "pincMgSetRowMode": (None, [C.c_int]),
+    "pincSetSlotted": (None, [C.c_int, C.c_int, C.c_int]),
+    "pincPopLayout": (C.c_int, [P(abi.Population)]),
+    "pincSlottedOverflows": (C.c_long, []),
     "pincMgSetHybrid": (None, [C.c_int]),
     "pincMgLastBarRes": (C.c_double, []),
     "pincMgLastPath": (C.c_int, []),
