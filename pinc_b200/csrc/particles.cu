@@ -434,42 +434,56 @@ __global__ void k_import(double *__restrict__ P, long cap, long dst0, long n, Im
 // between two runs of the scatter).
 // =================================================================================================================
 #define SLOT_OVER_KEY 0xfffffffeu          // a mover that did not fit into its cell: waits in the list for popLeaveSlotted
+#define SLOT_EMPTY_KEY 0xffffffffu         // an unused entry of the mover list (the list is handed out in chunks)
+#define MV_CHUNK 128u                      // >= the 96 particles of one trip of k_cell_push
 struct SlotPar { double *S; long plane; long off; int cap; unsigned *cnt; };
 
-template<int KE> __global__ void __launch_bounds__(256, 4) k_cell_push(SlotPar Q, const double *__restrict__ E, long sx3, long sxy3,
-		CellSpace C, Thr T, double *__restrict__ partial, double *__restrict__ M, long mPlane, unsigned *__restrict__ mKey, unsigned *mCount, int *flags){
+template<int KE> __global__ void __launch_bounds__(256, 2) k_cell_push(SlotPar Q, const double *__restrict__ E, long sx3, long sxy3,
+		CellSpace C, Thr T, double *__restrict__ partial, double *__restrict__ M, long mPlane, unsigned *__restrict__ mKey, unsigned *mCount, unsigned mCap, int *flags){
 	const int lane = threadIdx.x & 31;
 	const unsigned lt = (1u << lane) - 1u;
 	long warp = (blockIdx.x*(long)blockDim.x + threadIdx.x) >> 5;
 	const long nWarps = ((long)gridDim.x*blockDim.x) >> 5;
 	__shared__ double evS[8][24];
 	double acc = 0;
+	unsigned chBase = 0, chUsed = MV_CHUNK;          // this warp's chunk of the mover list: none yet
+	unsigned nNext = warp < C.nCells ? Q.cnt[warp] : 0u;
 	for(long c = warp; c < C.nCells; c += nWarps){
-		const unsigned n = Q.cnt[c];
+		const unsigned n = nNext;
+		if(c + nWarps < C.nCells) nNext = Q.cnt[c + nWarps];          // the next cell's count is on its way while this cell is pushed
 		if(n == 0) continue;
 		const int cj = (int)(c % C.nc0); const long cr = c / C.nc0; const int ck = (int)(cr % C.nc1); const int cl = (int)(cr / C.nc1);
 		const double dj = (double)cj, dk = (double)ck, dl = (double)cl;
 		const double *e0 = E + 3L*cj + ck*sx3 + cl*sxy3, *e1 = e0 + sx3, *e2 = e0 + sxy3, *e3 = e2 + sx3;
-		// the cell's eight corner fields once per cell: lane q*3+v fetches component v of corner q into the warp's shared row
-		__syncwarp();
-		if(lane < 24){
-			const int q = lane/3, v = lane - 3*q;
-			const double *ep = (q & 4 ? ((q & 2) ? e3 : e2) : ((q & 2) ? e1 : e0)) + ((q & 1) ? 3 : 0) + v;
-			evS[threadIdx.x >> 5][lane] = __ldg(ep);
-		}
-		__syncwarp();
-		const double *ev = evS[threadIdx.x >> 5];
 		double *P = Q.S + Q.off + c*(long)Q.cap;
 		unsigned wr = 0;
-		for(unsigned i0 = 0; i0 < n; i0 += 32){
-			const unsigned i = i0 + lane;
-			const bool ok = i < n;
-			double x = 0, y = 0, z = 0, vx = 0, vy = 0, vz = 0;
-			unsigned key = 0xffffffffu;
-			if(ok){
-				x = P[i]; y = P[i + Q.plane]; z = P[i + 2*Q.plane];
-				vx = P[i + 3*Q.plane]; vy = P[i + 4*Q.plane]; vz = P[i + 5*Q.plane];
-				const double xf = x-dj, yf = y-dk, zf = z-dl;
+		for(unsigned i0 = 0; i0 < n; i0 += 96){
+			// up to 96 particles per trip (nearly always the whole cell), every load in flight before the first use
+			double x[3], y[3], z[3], vx[3], vy[3], vz[3];
+			#pragma unroll
+			for(int u = 0; u < 3; u++){
+				const unsigned i = i0 + lane + 32*u;
+				const bool ok = i < n;
+				x[u] = ok ? P[i] : 0.0; y[u] = ok ? P[i + Q.plane] : 0.0; z[u] = ok ? P[i + 2*Q.plane] : 0.0;
+				vx[u] = ok ? P[i + 3*Q.plane] : 0.0; vy[u] = ok ? P[i + 4*Q.plane] : 0.0; vz[u] = ok ? P[i + 5*Q.plane] : 0.0;
+			}
+			if(i0 == 0){
+				// the cell's eight corner fields once per cell: lane q*3+v fetches component v of corner q into the warp's shared row
+				__syncwarp();
+				if(lane < 24){
+					const int q = lane/3, v = lane - 3*q;
+					const double *ep = (q & 4 ? ((q & 2) ? e3 : e2) : ((q & 2) ? e1 : e0)) + ((q & 1) ? 3 : 0) + v;
+					evS[threadIdx.x >> 5][lane] = __ldg(ep);
+				}
+				__syncwarp();
+			}
+			const double *ev = evS[threadIdx.x >> 5];
+			unsigned key[3];
+			#pragma unroll
+			for(int u = 0; u < 3; u++){
+				key[u] = 0xffffffffu;
+				if(i0 + lane + 32*u >= n) continue;
+				const double xf = x[u]-dj, yf = y[u]-dk, zf = z[u]-dl;
 				const double xc = 1-xf, yc = 1-yf, zc = 1-zf;
 				double dv[3];
 				#pragma unroll
@@ -478,37 +492,55 @@ template<int KE> __global__ void __launch_bounds__(256, 4) k_cell_push(SlotPar Q
 					      + zf*( yc*(xc*ev[12+v]+xf*ev[15+v]) + yf*(xc*ev[18+v]+xf*ev[21+v]) );
 				if(KE){
 					double v2 = 0;
-					v2 += vx*(vx+dv[0]); v2 += vy*(vy+dv[1]); v2 += vz*(vz+dv[2]);
+					v2 += vx[u]*(vx[u]+dv[0]); v2 += vy[u]*(vy[u]+dv[1]); v2 += vz[u]*(vz[u]+dv[2]);
 					acc += v2;
 				}
-				vx += dv[0]; vy += dv[1]; vz += dv[2];
-				x += vx; y += vy; z += vz;
-				key = classify(x, y, z, T, C, flags);
+				vx[u] += dv[0]; vy[u] += dv[1]; vz[u] += dv[2];
+				x[u] += vx[u]; y[u] += vy[u]; z[u] += vz[u];
+				key[u] = classify(x[u], y[u], z[u], T, C, flags);
 			}
-			const bool stay = ok && key == (unsigned)c;
-			// (the ballots need every lane's key, hence every lane's loads: no lane stores into a slot another lane still has to read)
-			const unsigned ms = __ballot_sync(0xffffffffu, stay), mm = __ballot_sync(0xffffffffu, ok && !stay);
-			if(stay){
-				const unsigned d = wr + __popc(ms & lt);
-				P[d] = x; P[d + Q.plane] = y; P[d + 2*Q.plane] = z;
-				P[d + 3*Q.plane] = vx; P[d + 4*Q.plane] = vy; P[d + 5*Q.plane] = vz;
+			// (every load of the trip has landed - the keys need them - before the first store: the compaction may overwrite
+			// slots that other lanes read in this trip, never slots of a later trip, since wr <= i0)
+			unsigned ms[3], mm[3], nm = 0;
+			#pragma unroll
+			for(int u = 0; u < 3; u++){
+				const bool ok = i0 + lane + 32*u < n;
+				ms[u] = __ballot_sync(0xffffffffu, ok && key[u] == (unsigned)c);
+				mm[u] = __ballot_sync(0xffffffffu, ok && key[u] != (unsigned)c);
+				nm += __popc(mm[u]);
 			}
-			if(mm){
-				unsigned b = 0;
-				const int leader = __ffs(mm) - 1;
-				if(lane == leader) b = atomicAdd(mCount, (unsigned)__popc(mm));
-				b = __shfl_sync(0xffffffffu, b, leader);
-				if(ok && !stay){
-					const unsigned d = b + __popc(mm & lt);
-					M[d] = x; M[d + mPlane] = y; M[d + 2*mPlane] = z;
-					M[d + 3*mPlane] = vx; M[d + 4*mPlane] = vy; M[d + 5*mPlane] = vz;
-					mKey[d] = key;
+			if(nm){
+				// room for the trip's movers in the species' list: a warp takes MV_CHUNK entries at a time (one atomic on the
+				// list's counter per ~30 cells instead of one per cell: every warp of the grid hits that one address)
+				if(chUsed + nm > MV_CHUNK){
+					for(unsigned k = chUsed + lane; k < MV_CHUNK; k += 32) mKey[chBase + k] = SLOT_EMPTY_KEY;
+					unsigned b = 0;
+					if(lane == 0) b = atomicAdd(mCount, (unsigned)MV_CHUNK);
+					chBase = __shfl_sync(0xffffffffu, b, 0);
+					chUsed = 0;
+					if(chBase + MV_CHUNK > mCap){ atomicOr(flags, ERR_CAPACITY); chBase = 0; }       // (the host sizes the grid so that this cannot happen)
 				}
 			}
-			wr += __popc(ms);
+			#pragma unroll
+			for(int u = 0; u < 3; u++){
+				const bool ok = i0 + lane + 32*u < n;
+				if(ok && key[u] == (unsigned)c){
+					const unsigned d = wr + __popc(ms[u] & lt);
+					P[d] = x[u]; P[d + Q.plane] = y[u]; P[d + 2*Q.plane] = z[u];
+					P[d + 3*Q.plane] = vx[u]; P[d + 4*Q.plane] = vy[u]; P[d + 5*Q.plane] = vz[u];
+				} else if(ok){
+					const unsigned d = chBase + chUsed + __popc(mm[u] & lt);
+					M[d] = x[u]; M[d + mPlane] = y[u]; M[d + 2*mPlane] = z[u];
+					M[d + 3*mPlane] = vx[u]; M[d + 4*mPlane] = vy[u]; M[d + 5*mPlane] = vz[u];
+					mKey[d] = key[u];
+				}
+				wr += __popc(ms[u]);
+				chUsed += __popc(mm[u]);
+			}
 		}
 		if(lane == 0) Q.cnt[c] = wr;
 	}
+	for(unsigned k = chUsed + lane; k < MV_CHUNK; k += 32) mKey[chBase + k] = SLOT_EMPTY_KEY;       // the unused rest of the last chunk
 	if(KE){
 		acc = blockSumP<256>(acc);
 		if(threadIdx.x == 0) partial[blockIdx.x] = acc;
@@ -521,7 +553,7 @@ __global__ void k_mv_insert(SlotPar Q, const double *__restrict__ M, long mPlane
 	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
 	for(; i < n; i += st){
 		const unsigned key = mKey[i];
-		if(key >= (unsigned)C.nCells){ if(key != SLOT_OVER_KEY) atomicAdd(&emHist[key - (unsigned)C.nCells], 1u); continue; }
+		if(key >= (unsigned)C.nCells){ if(key < SLOT_OVER_KEY) atomicAdd(&emHist[key - (unsigned)C.nCells], 1u); continue; }
 		const unsigned slot = atomicAdd(&Q.cnt[key], 1u);
 		if(slot >= (unsigned)Q.cap){ atomicOr(flags, ERR_SLOT_OVERFLOW); mKey[i] = SLOT_OVER_KEY; continue; }
 		double *P = Q.S + Q.off + (long)key*Q.cap + slot;
@@ -537,7 +569,7 @@ __global__ void k_mv_pack(const double *__restrict__ M, long mPlane, const unsig
 	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
 	for(; i < n; i += st){
 		const unsigned key = mKey[i];
-		if(key < (unsigned)C.nCells || key == SLOT_OVER_KEY) continue;
+		if(key < (unsigned)C.nCells || key >= SLOT_OVER_KEY) continue;
 		const int ne = (int)(key - (unsigned)C.nCells);
 		const long d = pp.dstOff[ne] + atomicAdd(&cursor[ne], 1u);
 		#pragma unroll
@@ -618,7 +650,7 @@ __global__ void k_mv_append(const double *__restrict__ M, long mPlane, const uns
 	const long n = *mCount;
 	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
 	for(; i < n; i += st){
-		if(onlyOver && mKey[i] != SLOT_OVER_KEY) continue;
+		if(mKey[i] == SLOT_EMPTY_KEY || (onlyOver && mKey[i] != SLOT_OVER_KEY)) continue;
 		const unsigned d = atomicAdd(cursor, 1u);
 		#pragma unroll
 		for(int w = 0; w < 6; w++) B[d + w*bPlane] = M[i + w*mPlane];
@@ -828,21 +860,35 @@ static bool enterSlotted(Ctx *c, DevPop *dp, const MpiInfo *m){
 	dp->slotted = true; dp->mvPending = false; dp->emigInMovers = false;
 	return true;
 }
+// warps k_cell_push may run for species s: the mover list (the species' share of the second buffer) must hold every particle
+// plus one unused chunk per warp
+static long slotWarpsFor(const Population *pop, int s){
+	long room = (pop->iStart[s+1] - pop->iStart[s]) - (pop->iStop[s] - pop->iStart[s]);
+	return room/(long)MV_CHUNK;
+}
+static bool slotRoom(const DevPop *dp){
+	const Population *pop = dp->host;
+	for(int s = 0; s < dp->nS; s++) if(pop->iStop[s] > pop->iStart[s] && slotWarpsFor(pop, s) < 64) return false;
+	return pop->iStart[dp->nS] < 0xfffffff0L;
+}
 // pincAccMove3D1KE on the slots: kick + move + re-binning of every species, one warp per cell
 static void cellPush(Ctx *c, DevPop *dp, Population *pop, DevGrid *E, int ke, const MpiInfo *m){
 	const long sx3 = 3L*E->size[0], sxy3 = sx3*E->size[1];
 	if(dp->nc[0] > E->size[0]-1 || dp->nc[1] > E->size[1]-1 || dp->nc[2] > E->size[2]-1) fatal("pincAccMove3D1KE: E is smaller than the migration thresholds allow");
 	const Thr thr = thrOf(m); const CellSpace C = cellsOf(dp);
-	const int blocks = cellBlocks(c, dp->nCells);
-	double *partial = ke ? partialBuffer(c, (long)blocks*dp->nS) : nullptr;
+	const int maxBlocks = cellBlocks(c, dp->nCells);
+	double *partial = ke ? partialBuffer(c, (long)maxBlocks*dp->nS) : nullptr;
 	PINC_CUDA(cudaMemsetAsync(dp->d_mvCount, 0, MV_WORDS*sizeof(unsigned), c->stream));
 	for(int s = 0; s < dp->nS; s++){
 		const long n = pop->iStop[s] - pop->iStart[s];
 		gridScale(c, E, pop->charge[s]/pop->mass[s]);          // quirk Q2, as accelerate()
-		double *part = ke ? partial + (long)s*blocks : nullptr;
+		double *part = ke ? partial + (long)s*maxBlocks : nullptr;
+		// every warp may leave up to one chunk of the mover list unused: as many warps as the species' allocation has room for
+		const long mCap = pop->iStart[s+1] - pop->iStart[s];
+		int blocks = (int)std::min<long>(maxBlocks, slotWarpsFor(pop, s)/8);
 		if(n > 0){
-			if(ke) PINC_LAUNCH(c, K_PUSH, 96.0*n, (k_cell_push<1><<<blocks,256,0,c->stream>>>(slotPar(dp,s), E->d, sx3, sxy3, C, thr, part, mvBase(dp,s), dp->cap, mvKeys(dp,s), dp->d_mvCount + MV_COUNT + s, c->d_flags)));
-			else   PINC_LAUNCH(c, K_PUSH, 96.0*n, (k_cell_push<0><<<blocks,256,0,c->stream>>>(slotPar(dp,s), E->d, sx3, sxy3, C, thr, part, mvBase(dp,s), dp->cap, mvKeys(dp,s), dp->d_mvCount + MV_COUNT + s, c->d_flags)));
+			if(ke) PINC_LAUNCH(c, K_PUSH, 96.0*n, (k_cell_push<1><<<blocks,256,0,c->stream>>>(slotPar(dp,s), E->d, sx3, sxy3, C, thr, part, mvBase(dp,s), dp->cap, mvKeys(dp,s), dp->d_mvCount + MV_COUNT + s, (unsigned)mCap, c->d_flags)));
+			else   PINC_LAUNCH(c, K_PUSH, 96.0*n, (k_cell_push<0><<<blocks,256,0,c->stream>>>(slotPar(dp,s), E->d, sx3, sxy3, C, thr, part, mvBase(dp,s), dp->cap, mvKeys(dp,s), dp->d_mvCount + MV_COUNT + s, (unsigned)mCap, c->d_flags)));
 		}
 		if(ke) PINC_LAUNCH(c, K_REDUCE, 8.0*blocks, (k_final_sum_p<<<1,256,0,c->stream>>>(part, n > 0 ? blocks : 0, c->d_scal + 16 + s)));
 		gridScale(c, E, pop->mass[s]/pop->charge[s]);
@@ -900,8 +946,8 @@ static void accelerate(Ctx *c, Population *pop, Grid *Egrid, int kind, int ke, c
 	if(E->nv != 3) fatal("accelerator needs a 3-vector field grid");
 	{	// slotted mode: the steady state of pincAccMove3D1KE (leapfrog kick + move + re-binning, no fused deposition)
 		const bool eligible = fuse && kind == ACC_LEAP && !rhoGrid && slottedEnabled();
-		if(dp->slotted && (!eligible || dp->mvPending || dp->extracted)) popLeaveSlotted(c, dp);
-		if(eligible && !dp->slotted) enterSlotted(c, dp, fuse);
+		if(dp->slotted && (!eligible || dp->mvPending || dp->extracted || !slotRoom(dp))) popLeaveSlotted(c, dp);
+		if(eligible && !dp->slotted && slotRoom(dp)) enterSlotted(c, dp, fuse);
 		if(dp->slotted){ cellPush(c, dp, pop, E, ke, fuse); return; }
 	}
 	long sx3 = 3L*E->size[0], sxy3 = sx3*E->size[1];

@@ -90,14 +90,16 @@ def test_slotted_steps_match_oracle(gpu_lib, sub):
 
 def test_slot_overflow_falls_back_to_the_sort(gpu_lib):
     L = gpu_lib
-    L.pincSetSlotted(1, 0, 0)                                   # no head room: the fullest cell overflows with the first arrival
+    L.pincSetSlotted(1, 0, 0)                                   # no head room beyond the fullest cell's count
     try:
-        # a lattice start fills every cell with exactly 8 particles per species; the perturbation compresses the plasma
-        # around the nodes of the wave, so those cells gain particles and have no free slot
-        text, cfg = small_cfg("cold", grid__nsubdomains="1,1,1", grid__truesize="16,8,8", multigrid__mglevels=3, population__nparticles="8 pc",
-                              population__nalloc="24 pc", population__perturbamplitude="0.3,0,0,0,0,0", grid__nemigrantsalloc="8 pc")
+        # every particle drifts towards the plane x = L/2 at 0.3 cells per step: the cells there fill up beyond any head room
+        text, cfg = warm("1,1,1", ppc=12, vth="0.02,0.001")
+        per_rank = initial.maxwellian(cfg, seed=23)
+        for r in range(cfg.nRanks):
+            for s, (pos, vel) in enumerate(per_rank[r]):
+                vel[:, 0] = -0.3 * np.sign(pos[:, 0] - (1 + cfg.trueSize[0] / 2))
         before = L.pincSlottedOverflows()
-        run_against_oracle(L, cfg, 8, expect_slotted=False, per_rank=initial.perturb(cfg, initial.lattice(cfg)))
+        run_against_oracle(L, cfg, 6, expect_slotted=False, per_rank=per_rank)
         assert L.pincSlottedOverflows() > before
     finally:
         L.pincSetSlotted(1, 25, 16)
