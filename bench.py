@@ -343,6 +343,14 @@ def run_ours(args, n_gpus, rank, world_size):
     # algorithmic GB/s of each class against the measured copy bandwidth
     hbm_kernels = {k: {"achieved": v["alg_GBps"], "frac": v["alg_GBps"] / peak, "ms_per_step": v["ms_per_step"]}
                    for k, v in kernels.items() if k in ("push", "deposit", "move", "sort", "findiff") and v["alg_GBps"]}
+    # the whole particle phase against the HBM roofline: SURVEY 8d's 120 algorithmic B per particle-step (push 96 + deposit 24)
+    # over everything the phase launches (push, move, deposit, re-binning/sort, emigrant extraction, import)
+    pp_ms = sum(kernels[k]["ms_per_step"] for k in ("push", "move", "deposit", "sort", "extract", "import") if k in kernels)
+    particle_phase = None
+    if pp_ms > 0:
+        ach_pp = 120.0 * n_live / (pp_ms * 1e-3) / 1e9
+        particle_phase = {"ms_per_step": pp_ms, "alg_bytes_per_particle": 120, "achieved": ach_pp, "peak": peak, "unit": "GB/s", "frac": ach_pp / peak,
+                          "layout": "cell-slotted (only particles that change cell move)" if L.pincPopLayout(st.pop) else "contiguous, counting sort every step"}
     roofline = None
     if dom:
         kms, cnt, by = prof[dom]
@@ -355,7 +363,8 @@ def run_ours(args, n_gpus, rank, world_size):
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "traffic_source": "static: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/traffic.json), not measured in this run",
                     "peak_source": peak_src,
-                    "alg_bytes_per_launch": by / cnt, "avg_launch_ms": kms / cnt, "hbm_bound_kernels": hbm_kernels}
+                    "alg_bytes_per_launch": by / cnt, "avg_launch_ms": kms / cnt, "hbm_bound_kernels": hbm_kernels,
+                    "particle_phase": particle_phase}
         if dom == "mgfused":
             # the multigrid kernel is bound by the latency of its dependent half-sweeps, not by bytes: say so
             phases = sum(2 * (cfg.nCoarseSolve if q == cfg.mgLevels - 1 else cfg.nPreSmooth + cfg.nPostSmooth)

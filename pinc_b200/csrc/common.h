@@ -84,6 +84,8 @@ struct DevPop {
 	unsigned *d_mvCount = nullptr;        // [8] movers per species (the mover list of species s is alt[iStart[s]..], keys in d_keys) + [8..8+8*27) emigrants per neighbour
 	bool mvPending = false;               // the last push left movers (other cell / other rank) in the mover lists
 	bool emigInMovers = false;            // puMigrate packs the emigrants from the mover lists
+	double thr6[6] = {0}; bool haveThr = false;     // migration thresholds of the most recent extraction (puMove has no MpiInfo)
+	int slotKicks = 0;                    // how often an entry point without a slotted form forced the contiguous layout back
 };
 
 struct ProfEvent { cudaEvent_t a, b; int cls; };
@@ -132,7 +134,7 @@ struct Ctx {
 	double mgTol = 1e-10, mgLastBarRes = 0;
 	int mgMaxCycles = 0, mgLastCycles = 0;
 	// per-device launch attributes of the persistent kernels (cudaFuncSetAttribute applies to the current device only)
-	size_t mgAttrSmem[3] = {0, 0, 0};
+	size_t mgAttrSmem[4] = {0, 0, 0, 0};
 	int clNc = -1; size_t clSmem = 0;
 	std::unordered_map<const void*, CycleGraph> cycleGraphs;     // keyed by the solver's mgRho
 	std::unordered_map<const void*, void*> mgGlobal;             // replicated global hierarchies of multi-rank solves (multigrid.cu)

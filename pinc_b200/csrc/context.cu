@@ -215,7 +215,7 @@ DevGrid *devGrid(Ctx *c, const Grid *g, bool upload){
 
 DevPop *devPop(Ctx *c, const Population *p, bool upload){
 	DevPop *dp = devPopRaw(c, p, upload);
-	if(dp->slotted) popLeaveSlotted(c, dp);
+	if(dp->slotted){ dp->slotKicks++; popLeaveSlotted(c, dp); }
 	return dp;
 }
 DevPop *devPopRaw(Ctx *c, const Population *p, bool upload){

@@ -1114,7 +1114,9 @@ __device__ __noinline__ void xHalo(double *v, int s0, int s1, int s2, Scope &S, 
 }
 
 // X: level q is distributed (hybrid multi-rank solve); its coarse level q+1 is the first replicated one (qDist = q+1)
-template<bool X = false> __device__ __noinline__ void fDown(const MgPlan &P, int q, Scope &S, unsigned &seq){
+// ROWS: the plan has a row-smoothed level (mgrows.cuh); a compile-time switch because the persistent kernel is sensitive to
+// its instruction footprint (the row smoother's code cost the 64^3 solve 7 % while it was part of the default kernel)
+template<bool X = false, bool ROWS = false> __device__ __noinline__ void fDown(const MgPlan &P, int q, Scope &S, unsigned &seq){
 	const Lvl &L = P.L[q], &C = P.L[q+1];
 	const bool blk = P.B[q].on && !S.single && P.nPre > 0;
 	if constexpr(X){
@@ -1122,10 +1124,12 @@ template<bool X = false> __device__ __noinline__ void fDown(const MgPlan &P, int
 		bGS<true>(L, P.B[q], P.nPre, 0.0, S, S.xMail);
 		xHalo(L.phi, L.s0, L.s1, L.s2, S);
 	} else {
-	if(blk && P.B[q].on == 3){ if(P.B[q].bx == 32) rNeutRho<16>(L, P.B[q], S); else rNeutRho<8>(L, P.B[q], S); }
-	else if(blk && P.B[q].on == 1) bNeutRho<false>(L, P.B[q], S); else fNeutralize(L.rho, L.s0, L.s1, L.s2, S);
-	if(blk && P.B[q].on == 3){ if(P.B[q].bx == 32) rGS<16>(L, P.B[q], P.nPre, 0.0, S, seq); else rGS<8>(L, P.B[q], P.nPre, 0.0, S, seq); }
-	else if(blk) bGS<false>(L, P.B[q], P.nPre, 0.0, S, seq); else fGS(L, P.nPre, 0.0, P.exact, S);
+	bool rows = false;
+	if constexpr(ROWS) rows = blk && P.B[q].on == 3;
+	if constexpr(ROWS){ if(rows){ if(P.B[q].bx == 32) rNeutRho<16>(L, P.B[q], S); else rNeutRho<8>(L, P.B[q], S); } }
+	if(!rows){ if(blk && P.B[q].on == 1) bNeutRho<false>(L, P.B[q], S); else fNeutralize(L.rho, L.s0, L.s1, L.s2, S); }
+	if constexpr(ROWS){ if(rows){ if(P.B[q].bx == 32) rGS<16>(L, P.B[q], P.nPre, 0.0, S, seq); else rGS<8>(L, P.B[q], P.nPre, 0.0, S, seq); } }
+	if(!rows){ if(blk) bGS<false>(L, P.B[q], P.nPre, 0.0, S, seq); else fGS(L, P.nPre, 0.0, P.exact, S); }
 	}
 	{
 		ProfScope psr(*S.K, S.single ? 27 : 29);
@@ -1170,7 +1174,7 @@ __device__ __noinline__ void fBottom(const MgPlan &P, Scope &S){
 	if(P.exact || P.nCoarse <= 0) fNeutralize(L.phi, L.s0, L.s1, L.s2, S);      // batched mode: fGS just ended with this gBnd
 }
 // res(q) := P(phi(q+1)); phi(q) += res(q); gBnd; post-smooth; gBnd
-template<bool X = false> __device__ __noinline__ void fUp(const MgPlan &P, int q, Scope &S, unsigned &seq){
+template<bool X = false, bool ROWS = false> __device__ __noinline__ void fUp(const MgPlan &P, int q, Scope &S, unsigned &seq){
 	const Lvl &L = P.L[q], &C = P.L[q+1];
 	int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2; long nt = (long)t0*t1*t2;
 	const long long tUp = clock64();
@@ -1192,8 +1196,12 @@ template<bool X = false> __device__ __noinline__ void fUp(const MgPlan &P, int q
 	}
 	double avg = S.allSum(acc)/(double)nt;
 	if(S.K->prof && blockIdx.x == 0 && threadIdx.x == 0 && !S.single){ S.K->prof[2*31] += clock64() - tUp; S.K->prof[2*31+1] += 1; }
-	if(P.B[q].on == 3 && !S.single && P.nPost > 0){ if(P.B[q].bx == 32) rGS<16>(L, P.B[q], P.nPost, avg, S, seq); else rGS<8>(L, P.B[q], P.nPost, avg, S, seq); }
-	else if(P.B[q].on && !S.single && P.nPost > 0) bGS<false>(L, P.B[q], P.nPost, avg, S, seq); else fGS(L, P.nPost, avg, P.exact, S);
+	bool rows = false;
+	if constexpr(ROWS){
+		rows = P.B[q].on == 3 && !S.single && P.nPost > 0;
+		if(rows){ if(P.B[q].bx == 32) rGS<16>(L, P.B[q], P.nPost, avg, S, seq); else rGS<8>(L, P.B[q], P.nPost, avg, S, seq); }
+	}
+	if(!rows){ if(P.B[q].on && !S.single && P.nPost > 0) bGS<false>(L, P.B[q], P.nPost, avg, S, seq); else fGS(L, P.nPost, avg, P.exact, S); }
 	if(P.exact || P.nPost <= 0) fNeutralize(L.phi, L.s0, L.s1, L.s2, S);
 }
 __device__ __noinline__ void fGhosts(double *v, int s0, int s1, int s2, Scope &S){
@@ -1277,7 +1285,7 @@ __device__ __noinline__ void smallPyramid(const MgPlan &P, CK &K){
 
 // EXACT (gBnd after every half-sweep, modes 1 and 3) is a compile-time parameter only to keep the code of the default
 // kernel small: the persistent kernel is latency-bound and sensitive to its instruction footprint
-template<bool EXACT, bool DIST> __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(const __grid_constant__ MgPlan P){
+template<bool EXACT, bool DIST, bool ROWS> __global__ void __launch_bounds__(MG_BLOCK, 1) k_mg_solve(const __grid_constant__ MgPlan P){
 	__shared__ double sh[18];
 	__shared__ double red[40];
 	CK K{ cg::this_cluster(), (int)blockIdx.x, 1, mgS, red, 0, P.prof, P.offZ };
@@ -1315,7 +1323,7 @@ template<bool EXACT, bool DIST> __global__ void __launch_bounds__(MG_BLOCK, 1) k
 	while(barRes > P.tol && cycles < P.maxCycles){
 		for(int q = 0; q <= b && q < qs; q++){
 			if(DIST && q < P.X.qDist) fDown<DIST>(P, q, Sg, seq);
-			else if(q < b) fDown(P, q, Sg, seq); else fBottom(P, Sg);
+			else if(q < b) fDown<false,ROWS>(P, q, Sg, seq); else fBottom(P, Sg);
 		}
 		if(qs <= b){
 			if(blockIdx.x == 0){
@@ -1331,7 +1339,7 @@ template<bool EXACT, bool DIST> __global__ void __launch_bounds__(MG_BLOCK, 1) k
 			}
 			Sg.sync();
 		}
-		for(int q = (qs <= b ? qs : b) - 1; q >= 0; q--){ if(DIST && q < P.X.qDist) fUp<DIST>(P, q, Sg, seq); else fUp(P, q, Sg, seq); }
+		for(int q = (qs <= b ? qs : b) - 1; q >= 0; q--){ if(DIST && q < P.X.qDist) fUp<DIST>(P, q, Sg, seq); else fUp<false,ROWS>(P, q, Sg, seq); }
 		// mgSolveRaw :1700-1704: residual, square in place, true-grid sum, RMS
 		const Lvl &L = P.L[0];
 		ProfScope psn(K, PS_NORM);
@@ -1565,7 +1573,7 @@ static bool fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 				if(g_mgRowMode < 0) g_mgRowMode = getenv("PINC_B200_MG_ROWMODE") ? atoi(getenv("PINC_B200_MG_ROWMODE")) : 1;
 				const int rowMode = g_mgRowMode;
 				const bool big = (B.bx/2)*B.by*B.bz > 2*MG_BLOCK || B.by*B.bz + B.bx*B.bz + B.bx*B.by > MG_BLOCK;
-				if(rowMode && (big || rowMode == 2) && (B.bx == 16 || B.bx == 32) && B.by*B.bz <= MG_BLOCK){
+				if(rowMode && !XH && (big || rowMode == 2) && (B.bx == 16 || B.bx == 32) && B.by*B.bz <= MG_BLOCK){
 					B.on = 3; B.offRho = -1;
 					mailOff[q] = mailSlots;
 					mailSlots += (size_t)B.nb*2*(B.by*B.bz + B.bx*B.bz + B.bx*B.by);
@@ -1631,9 +1639,13 @@ static bool fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 		P.X.ctr = (unsigned*)A->mine;
 		for(int q = 0; q < qDist; q++) P.B[q].mail = (uint4*)A->mine + offMail + xMailOff[q];
 	}
-	const void *kern = XH ? (const void*)k_mg_solve<false,true> : exact ? (const void*)k_mg_solve<true,false> : (const void*)k_mg_solve<false,false>;
+	bool rows = false;
+	for(int q = 0; q < nL; q++) if(P.B[q].on == 3) rows = true;
+	if(rows && (XH || exact)) fatal("multigrid plan: a row-smoothed level in a hybrid or exact solve");
+	const void *kern = XH ? (const void*)k_mg_solve<false,true,false> : exact ? (const void*)k_mg_solve<true,false,false>
+		: rows ? (const void*)k_mg_solve<false,false,true> : (const void*)k_mg_solve<false,false,false>;
 	{	// one high-water mark for the kernel's dynamic shared memory
-		size_t &attrSet = c->mgAttrSmem[XH ? 2 : exact ? 1 : 0];       // per context: the attribute belongs to the device
+		size_t &attrSet = c->mgAttrSmem[XH ? 2 : exact ? 1 : rows ? 3 : 0];       // per context: the attribute belongs to the device
 		if(smem > attrSet){
 			if(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) attrSet = smem;
 			else { cudaGetLastError(); if(XH) return false; for(int q = 0; q < nL; q++) P.B[q].on = 0; P.smemSmall = 0; P.pyramid = 0; smem = 0; }
@@ -1653,7 +1665,7 @@ static bool fusedSolve(Ctx *c, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 		LaunchScope ls(c, K_MGFUSED, work);
 		if(XH && share > 1){
 			// (a cooperative launch only adds the co-residency check, which does not know about the other ranks' kernels)
-			k_mg_solve<false,true><<<dim3(grid), dim3(MG_BLOCK), smem, c->stream>>>(P);
+			k_mg_solve<false,true,false><<<dim3(grid), dim3(MG_BLOCK), smem, c->stream>>>(P);
 			PINC_CUDA(cudaGetLastError());
 		} else
 			PINC_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(MG_BLOCK), args, smem, c->stream));

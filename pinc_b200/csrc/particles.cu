@@ -438,7 +438,9 @@ __global__ void k_import(double *__restrict__ P, long cap, long dst0, long n, Im
 #define MV_CHUNK 128u                      // >= the 96 particles of one trip of k_cell_push
 struct SlotPar { double *S; long plane; long off; int cap; unsigned *cnt; };
 
-template<int KE> __global__ void __launch_bounds__(256, 2) k_cell_push(SlotPar Q, const double *__restrict__ E, long sx3, long sxy3,
+// MODE 0: pincAccMove3D1KE (kick + move + re-binning); 1: puAcc3D1(KE) alone (velocities in place, nothing moves);
+// 2: puMove alone (pos += vel, re-binning).  1 followed by 2 is the reference's call order and leaves the same bits as 0.
+template<int KE, int MODE> __global__ void __launch_bounds__(256, 2) k_cell_push(SlotPar Q, const double *__restrict__ E, long sx3, long sxy3,
 		CellSpace C, Thr T, double *__restrict__ partial, double *__restrict__ M, long mPlane, unsigned *__restrict__ mKey, unsigned *mCount, unsigned mCap, int *flags){
 	const int lane = threadIdx.x & 31;
 	const unsigned lt = (1u << lane) - 1u;
@@ -467,7 +469,7 @@ template<int KE> __global__ void __launch_bounds__(256, 2) k_cell_push(SlotPar Q
 				x[u] = ok ? P[i] : 0.0; y[u] = ok ? P[i + Q.plane] : 0.0; z[u] = ok ? P[i + 2*Q.plane] : 0.0;
 				vx[u] = ok ? P[i + 3*Q.plane] : 0.0; vy[u] = ok ? P[i + 4*Q.plane] : 0.0; vz[u] = ok ? P[i + 5*Q.plane] : 0.0;
 			}
-			if(i0 == 0){
+			if(MODE != 2 && i0 == 0){
 				// the cell's eight corner fields once per cell: lane q*3+v fetches component v of corner q into the warp's shared row
 				__syncwarp();
 				if(lane < 24){
@@ -483,22 +485,30 @@ template<int KE> __global__ void __launch_bounds__(256, 2) k_cell_push(SlotPar Q
 			for(int u = 0; u < 3; u++){
 				key[u] = 0xffffffffu;
 				if(i0 + lane + 32*u >= n) continue;
-				const double xf = x[u]-dj, yf = y[u]-dk, zf = z[u]-dl;
-				const double xc = 1-xf, yc = 1-yf, zc = 1-zf;
-				double dv[3];
-				#pragma unroll
-				for(int v = 0; v < 3; v++)
-					dv[v] = zc*( yc*(xc*ev[v]+xf*ev[3+v]) + yf*(xc*ev[6+v]+xf*ev[9+v]) )
-					      + zf*( yc*(xc*ev[12+v]+xf*ev[15+v]) + yf*(xc*ev[18+v]+xf*ev[21+v]) );
-				if(KE){
-					double v2 = 0;
-					v2 += vx[u]*(vx[u]+dv[0]); v2 += vy[u]*(vy[u]+dv[1]); v2 += vz[u]*(vz[u]+dv[2]);
-					acc += v2;
+				if(MODE != 2){
+					const double xf = x[u]-dj, yf = y[u]-dk, zf = z[u]-dl;
+					const double xc = 1-xf, yc = 1-yf, zc = 1-zf;
+					double dv[3];
+					#pragma unroll
+					for(int v = 0; v < 3; v++)
+						dv[v] = zc*( yc*(xc*ev[v]+xf*ev[3+v]) + yf*(xc*ev[6+v]+xf*ev[9+v]) )
+						      + zf*( yc*(xc*ev[12+v]+xf*ev[15+v]) + yf*(xc*ev[18+v]+xf*ev[21+v]) );
+					if(KE){
+						double v2 = 0;
+						v2 += vx[u]*(vx[u]+dv[0]); v2 += vy[u]*(vy[u]+dv[1]); v2 += vz[u]*(vz[u]+dv[2]);
+						acc += v2;
+					}
+					vx[u] += dv[0]; vy[u] += dv[1]; vz[u] += dv[2];
 				}
-				vx[u] += dv[0]; vy[u] += dv[1]; vz[u] += dv[2];
+				if(MODE == 1){
+					const unsigned i = i0 + lane + 32*u;
+					P[i + 3*Q.plane] = vx[u]; P[i + 4*Q.plane] = vy[u]; P[i + 5*Q.plane] = vz[u];
+					continue;
+				}
 				x[u] += vx[u]; y[u] += vy[u]; z[u] += vz[u];
 				key[u] = classify(x[u], y[u], z[u], T, C, flags);
 			}
+			if(MODE == 1) continue;
 			// (every load of the trip has landed - the keys need them - before the first store: the compaction may overwrite
 			// slots that other lanes read in this trip, never slots of a later trip, since wr <= i0)
 			unsigned ms[3], mm[3], nm = 0;
@@ -527,7 +537,7 @@ template<int KE> __global__ void __launch_bounds__(256, 2) k_cell_push(SlotPar Q
 				if(ok && key[u] == (unsigned)c){
 					const unsigned d = wr + __popc(ms[u] & lt);
 					P[d] = x[u]; P[d + Q.plane] = y[u]; P[d + 2*Q.plane] = z[u];
-					P[d + 3*Q.plane] = vx[u]; P[d + 4*Q.plane] = vy[u]; P[d + 5*Q.plane] = vz[u];
+					if(MODE == 0 || d != i0 + lane + 32*u){ P[d + 3*Q.plane] = vx[u]; P[d + 4*Q.plane] = vy[u]; P[d + 5*Q.plane] = vz[u]; }      // (puMove leaves velocities alone)
 				} else if(ok){
 					const unsigned d = chBase + chUsed + __popc(mm[u] & lt);
 					M[d] = x[u]; M[d + mPlane] = y[u]; M[d + 2*mPlane] = z[u];
@@ -538,7 +548,7 @@ template<int KE> __global__ void __launch_bounds__(256, 2) k_cell_push(SlotPar Q
 				chUsed += __popc(mm[u]);
 			}
 		}
-		if(lane == 0) Q.cnt[c] = wr;
+		if(MODE != 1 && lane == 0) Q.cnt[c] = wr;
 	}
 	for(unsigned k = chUsed + lane; k < MV_CHUNK; k += 32) mKey[chBase + k] = SLOT_EMPTY_KEY;       // the unused rest of the last chunk
 	if(KE){
@@ -718,19 +728,24 @@ __global__ void k_assert_range(const double *__restrict__ P, long cap, long n, d
 // ---- host side ----------------------------------------------------------------------------------------------
 static inline int pGrid(Ctx *c, long n){ return gridFor(n, 256, c->numSMs*8); }
 
-static Thr thrOf(const MpiInfo *m){
+static Thr thrOf(const double *thr6){
 	Thr T;
-	for(int d = 0; d < 3; d++){ T.lo[d] = m->thresholds[d]; T.up[d] = m->thresholds[3+d]; }
+	for(int d = 0; d < 3; d++){ T.lo[d] = thr6[d]; T.up[d] = thr6[3+d]; }
 	return T;
 }
+static Thr thrOf(const MpiInfo *m){ return thrOf(m->thresholds); }
+static void setupCells(Ctx *c, DevPop *dp, const double *thr6);
+static void setupCells(Ctx *c, DevPop *dp, const MpiInfo *m){ setupCells(c, dp, m->thresholds); }
 // the cell space every non-emigrant position falls into: 0 <= lower threshold, x < upper threshold <= nc
-static void setupCells(Ctx *c, DevPop *dp, const MpiInfo *m){
+static void setupCells(Ctx *c, DevPop *dp, const double *thr6){
 	int nc[3];
 	for(int d = 0; d < 3; d++){
-		if(m->thresholds[d] < 0) fatal("negative lower migration threshold");
-		nc[d] = (int)ceil(m->thresholds[3+d]);
+		if(thr6[d] < 0) fatal("negative lower migration threshold");
+		nc[d] = (int)ceil(thr6[3+d]);
 		if(nc[d] < 1) nc[d] = 1;
+		dp->thr6[d] = thr6[d]; dp->thr6[3+d] = thr6[3+d];
 	}
+	dp->haveThr = true;
 	long nCells = (long)nc[0]*nc[1]*nc[2];
 	if(nCells + 28 >= 0xffffffffL) fatal("cell space too large for 32-bit keys");
 	if(dp->nCells == nCells && dp->nc[0] == nc[0] && dp->nc[1] == nc[1] && dp->d_hist[0]) return;
@@ -816,10 +831,10 @@ void popLeaveSlotted(Ctx *c, DevPop *dp){
 	if(dp->mvPending){ dp->keysValid = false; dp->mvPending = false; }
 }
 // contiguous cell-ordered planes -> slots; false (population unchanged) if it is not binned yet or a cell would not fit
-static bool enterSlotted(Ctx *c, DevPop *dp, const MpiInfo *m){
+static bool enterSlotted(Ctx *c, DevPop *dp, const double *thr6){
 	const Population *pop = dp->host;
-	if(!slottedEnabled() || dp->extracted || dp->predep) return false;
-	setupCells(c, dp, m);
+	if(!slottedEnabled() || dp->extracted || dp->predep || dp->slotKicks >= 3) return false;       // (a host whose loop keeps calling entry points without a slotted form gains nothing)
+	{ double t[6]; for(int d = 0; d < 6; d++) t[d] = thr6[d]; setupCells(c, dp, t); }
 	for(int s = 0; s < dp->nS; s++) if(pop->iStop[s] > pop->iStart[s] && dp->sortedN[s] == 0) return false;       // the sort has to run once
 	if(!dp->alt) PINC_CUDA(cudaMalloc(&dp->alt, (size_t)6*(dp->cap > 0 ? dp->cap : 1)*sizeof(double)));
 	if(!dp->d_mvCount) PINC_CUDA(cudaMalloc(&dp->d_mvCount, MV_WORDS*sizeof(unsigned)));
@@ -872,29 +887,36 @@ static bool slotRoom(const DevPop *dp){
 	return pop->iStart[dp->nS] < 0xfffffff0L;
 }
 // pincAccMove3D1KE on the slots: kick + move + re-binning of every species, one warp per cell
-static void cellPush(Ctx *c, DevPop *dp, Population *pop, DevGrid *E, int ke, const MpiInfo *m){
-	const long sx3 = 3L*E->size[0], sxy3 = sx3*E->size[1];
-	if(dp->nc[0] > E->size[0]-1 || dp->nc[1] > E->size[1]-1 || dp->nc[2] > E->size[2]-1) fatal("pincAccMove3D1KE: E is smaller than the migration thresholds allow");
-	const Thr thr = thrOf(m); const CellSpace C = cellsOf(dp);
+// mode 0: kick + move + re-binning (pincAccMove3D1KE); 1: kick only (puAcc3D1[KE]); 2: move + re-binning only (puMove)
+static void cellPush(Ctx *c, DevPop *dp, Population *pop, DevGrid *E, int ke, const double *thr6, int mode){
+	const long sx3 = E ? 3L*E->size[0] : 0, sxy3 = E ? sx3*E->size[1] : 0;
+	if(E && (dp->nc[0] > E->size[0]-1 || dp->nc[1] > E->size[1]-1 || dp->nc[2] > E->size[2]-1)) fatal("accelerator: E is smaller than the migration thresholds allow");
+	const Thr thr = thrOf(thr6); const CellSpace C = cellsOf(dp);
+	if(mode == 2) ke = 0;
 	const int maxBlocks = cellBlocks(c, dp->nCells);
 	double *partial = ke ? partialBuffer(c, (long)maxBlocks*dp->nS) : nullptr;
-	PINC_CUDA(cudaMemsetAsync(dp->d_mvCount, 0, MV_WORDS*sizeof(unsigned), c->stream));
+	if(mode != 1) PINC_CUDA(cudaMemsetAsync(dp->d_mvCount, 0, MV_WORDS*sizeof(unsigned), c->stream));
 	for(int s = 0; s < dp->nS; s++){
 		const long n = pop->iStop[s] - pop->iStart[s];
-		gridScale(c, E, pop->charge[s]/pop->mass[s]);          // quirk Q2, as accelerate()
+		if(E) gridScale(c, E, pop->charge[s]/pop->mass[s]);          // quirk Q2, as accelerate()
 		double *part = ke ? partial + (long)s*maxBlocks : nullptr;
 		// every warp may leave up to one chunk of the mover list unused: as many warps as the species' allocation has room for
 		const long mCap = pop->iStart[s+1] - pop->iStart[s];
 		int blocks = (int)std::min<long>(maxBlocks, slotWarpsFor(pop, s)/8);
 		if(n > 0){
-			if(ke) PINC_LAUNCH(c, K_PUSH, 96.0*n, (k_cell_push<1><<<blocks,256,0,c->stream>>>(slotPar(dp,s), E->d, sx3, sxy3, C, thr, part, mvBase(dp,s), dp->cap, mvKeys(dp,s), dp->d_mvCount + MV_COUNT + s, (unsigned)mCap, c->d_flags)));
-			else   PINC_LAUNCH(c, K_PUSH, 96.0*n, (k_cell_push<0><<<blocks,256,0,c->stream>>>(slotPar(dp,s), E->d, sx3, sxy3, C, thr, part, mvBase(dp,s), dp->cap, mvKeys(dp,s), dp->d_mvCount + MV_COUNT + s, (unsigned)mCap, c->d_flags)));
+#define CELL_LAUNCH(KEE,MODE,CLS,BYTES) PINC_LAUNCH(c, CLS, (BYTES)*n, (k_cell_push<KEE,MODE><<<blocks,256,0,c->stream>>>(slotPar(dp,s), E ? E->d : nullptr, sx3, sxy3, C, thr, part, mvBase(dp,s), dp->cap, mvKeys(dp,s), dp->d_mvCount + MV_COUNT + s, (unsigned)mCap, c->d_flags)))
+			if(mode == 0){ if(ke) CELL_LAUNCH(1,0,K_PUSH,96.0); else CELL_LAUNCH(0,0,K_PUSH,96.0); }
+			else if(mode == 1){ if(ke) CELL_LAUNCH(1,1,K_PUSH,72.0); else CELL_LAUNCH(0,1,K_PUSH,72.0); }
+			else CELL_LAUNCH(0,2,K_MOVE,72.0);
+#undef CELL_LAUNCH
 		}
 		if(ke) PINC_LAUNCH(c, K_REDUCE, 8.0*blocks, (k_final_sum_p<<<1,256,0,c->stream>>>(part, n > 0 ? blocks : 0, c->d_scal + 16 + s)));
-		gridScale(c, E, pop->mass[s]/pop->charge[s]);
+		if(E) gridScale(c, E, pop->mass[s]/pop->charge[s]);
 	}
-	dp->mvPending = true;
-	for(int d = 0; d < 6; d++) dp->keyThr[d] = m->thresholds[d];
+	if(mode != 1){
+		dp->mvPending = true;
+		for(int d = 0; d < 6; d++) dp->keyThr[d] = thr6[d];
+	}
 	if(ke){
 		PINC_CUDA(cudaMemcpyAsync(c->h_scal + 16, c->d_scal + 16, dp->nS*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 		streamSync(c);
@@ -945,10 +967,11 @@ static void accelerate(Ctx *c, Population *pop, Grid *Egrid, int kind, int ke, c
 	DevGrid *E = devGrid(c, Egrid);
 	if(E->nv != 3) fatal("accelerator needs a 3-vector field grid");
 	{	// slotted mode: the steady state of pincAccMove3D1KE (leapfrog kick + move + re-binning, no fused deposition)
-		const bool eligible = fuse && kind == ACC_LEAP && !rhoGrid && slottedEnabled();
+		// (with `fuse` also the move and the re-binning; without, the kick alone - the reference's call order)
+		const bool eligible = kind == ACC_LEAP && !rhoGrid && slottedEnabled() && (fuse || dp->haveThr);
 		if(dp->slotted && (!eligible || dp->mvPending || dp->extracted || !slotRoom(dp))) popLeaveSlotted(c, dp);
-		if(eligible && !dp->slotted && slotRoom(dp)) enterSlotted(c, dp, fuse);
-		if(dp->slotted){ cellPush(c, dp, pop, E, ke, fuse); return; }
+		if(eligible && !dp->slotted && slotRoom(dp)) enterSlotted(c, dp, fuse ? fuse->thresholds : dp->thr6);
+		if(dp->slotted){ double t[6]; for(int d = 0; d < 6; d++) t[d] = fuse ? fuse->thresholds[d] : dp->thr6[d]; cellPush(c, dp, pop, E, ke, t, fuse ? 0 : 1); return; }
 	}
 	long sx3 = 3L*E->size[0], sxy3 = sx3*E->size[1];
 	Thr thr{}; CellSpace C{1,1,1,1};
@@ -1027,7 +1050,13 @@ extern "C" {
 
 void puMove(Population *pop, Object *obj){
 	(void)obj;
-	Ctx *c = cur(); DevPop *dp = devPop(c, pop);
+	Ctx *c = cur(); DevPop *dp = devPopRaw(c, pop);
+	if(dp->slotted && !dp->mvPending && !dp->extracted && dp->haveThr && slotRoom(dp)){
+		double t[6]; for(int d = 0; d < 6; d++) t[d] = dp->thr6[d];
+		cellPush(c, dp, pop, nullptr, 0, t, 2);          // pos += vel and the re-binning of the next puExtractEmigrants3D in one pass
+		return;
+	}
+	if(dp->slotted) popLeaveSlotted(c, dp);
 	for(int s = 0; s < dp->nS; s++){
 		long a = pop->iStart[s], n = pop->iStop[s] - a;
 		if(n > 0) PINC_LAUNCH(c, K_MOVE, 72.0*n, (k_move<<<pGrid(c,n),256,0,c->stream>>>(dp->base, dp->base + 3*dp->cap, dp->cap, a, n)));

@@ -33,7 +33,7 @@ def layouts(W):
     return out
 
 
-def run_against_oracle(L, cfg, steps, expect_slotted=True, per_rank=None):
+def run_against_oracle(L, cfg, steps, expect_slotted=True, per_rank=None, fused="nodeposit"):
     per_rank = initial.maxwellian(cfg, seed=17) if per_rank is None else per_rank
     W, O = sim.World(cfg), orc.OrcWorld(cfg)
     try:
@@ -42,7 +42,7 @@ def run_against_oracle(L, cfg, steps, expect_slotted=True, per_rank=None):
             X.migrate(); X.field_solve(); X.half_kick()
         seen = 0
         for it in range(steps):
-            W.step(fused="nodeposit"); O.step()
+            W.step(fused=fused); O.step()
             seen += sum(layouts(W).values())
             for r in range(cfg.nRanks):
                 for name in ("rho", "phi", "E"):
@@ -56,7 +56,7 @@ def run_against_oracle(L, cfg, steps, expect_slotted=True, per_rank=None):
         if expect_slotted:
             assert seen >= cfg.nRanks * (steps - 2), seen       # slotted from the second step on (the first one has to sort once)
         # the fused pass leaves the positions one puMove ahead of the oracle: bring the oracle there, then compare phase space
-        for r in range(cfg.nRanks):
+        for r in range(cfg.nRanks if fused else 0):
             O.lib.orc_move(orc.dp(O.pos[r]), orc.dp(O.vel[r]), cfg.nSpecies, orc.lp(O.iStart[r]), orc.lp(O.iStop[r]))
         for r in range(cfg.nRanks):
             got, ref = W.particles(r), O.particles(r)           # (reading the particles leaves slotted mode)
@@ -70,17 +70,19 @@ def run_against_oracle(L, cfg, steps, expect_slotted=True, per_rank=None):
         W.close()
 
 
-@pytest.mark.parametrize("sub", ["1,1,1", "1,2,2"])
-def test_slotted_steps_match_oracle(gpu_lib, sub):
+@pytest.mark.parametrize("sub,fused", [("1,1,1", "nodeposit"), ("1,2,2", "nodeposit"), ("1,1,1", False), ("2,1,2", False)])
+def test_slotted_steps_match_oracle(gpu_lib, sub, fused):
+    """fused="nodeposit": pincAccMove3D1KE (kick + move + re-binning in one pass); False: the reference's call order, puAcc3D1KE
+    and puMove as separate slotted passes."""
     L = gpu_lib
     L.pincSetSlotted(1, 25, 16)
     text, cfg = warm(sub)
     before = L.pincSlottedOverflows()
-    a = run_against_oracle(L, cfg, 6)
+    a = run_against_oracle(L, cfg, 6, fused=fused)
     assert L.pincSlottedOverflows() == before
     L.pincSetSlotted(0, -1, -1)                                 # the counting sort every step: bit-identical fields
     try:
-        b = run_against_oracle(L, cfg, 6, expect_slotted=False)
+        b = run_against_oracle(L, cfg, 6, expect_slotted=False, fused=fused)
     finally:
         L.pincSetSlotted(1, 25, 16)
     for r in a:
