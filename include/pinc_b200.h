@@ -202,6 +202,10 @@ void mgSolveRaw(funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mg
 void mgRestrictBnd(Multigrid *mgGrid);                                          /* multigrid.h:366 (multigrid.c:1314); host arrays */
 void mgVRecursive(int level, int bottom, int top, Multigrid *mgRho, Multigrid *mgPhi,
                   Multigrid *mgRes, const MpiInfo *mpiInfo);                    /* multigrid.c:1550 */
+void mgVRegular(int level, int bottom, int top, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *mpiInfo); /* multigrid.c:1559 */
+void mgW(int level, int bottom, int top, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *mpiInfo);        /* multigrid.c:1675 */
+void mgFMG(int level, int bottom, int top, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *mpiInfo);      /* multigrid.c:1652; fails loudly: the reference's destroys mgRho->grids[0] */
+void mgJacob3D(Grid *phi, const Grid *rho, const int nCycles, const MpiInfo *mpiInfo);                                          /* multigrid.c:500 ("jacobian") */
 void mgGS3D(Grid *phi, const Grid *rho, int nCycles, const MpiInfo *mpiInfo);  /* multigrid.c:683 */
 void mgHalfRestrict3D(const Grid *fine, Grid *coarse);                          /* multigrid.c:844 */
 void mgBilinProl3D(Grid *fine, const Grid *coarse, const MpiInfo *mpiInfo);     /* multigrid.c:1127 */

@@ -89,6 +89,10 @@ def load():
     lib.orc_mg_solve.restype = C.c_int
     lib.orc_mg_solve.argtypes = [C.c_void_p, PP, PP, PP, C.c_double, C.c_int, c_double_p, C.c_int]
     lib.orc_mg_vcycle.argtypes = [C.c_void_p, PP, PP, PP]
+    lib.orc_mg_wcycle.argtypes = [C.c_void_p, PP, PP, PP]
+    lib.orc_mg_vregular.argtypes = [C.c_void_p, PP, PP, PP]
+    lib.orc_mg_set_smoothers.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.orc_jacobi3d.argtypes = [P(OrcTopo), PP, PP, c_int_p, C.c_int, c_int_p, PP]
     lib.orc_mg_level.restype = c_double_p
     lib.orc_mg_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p]
     lib.orc_slice_max.restype = C.c_long

@@ -376,6 +376,29 @@ void orc_gs3d(const OrcTopo *t, double **phi, double **rho, const int *size, int
 	}
 }
 
+/* mgJacob3D (src/multigrid.c:500-551): all true nodes from the old values, then halo + gBnd (bnd == NULL: periodic) */
+void orc_bnd(const OrcTopo *t, double **val, const int *size, const int *bnd, double **bndSlice);
+void orc_jacobi3d(const OrcTopo *t, double **phi, double **rho, const int *size, int nCycles, const int *bnd, double **bndSlice){
+	long sx = size[0], sxy = (long)size[0]*size[1], n = sxy*size[2];
+	const double coeff = 1./6;
+	double *tmp = malloc(sizeof(double)*n);
+	for(int c=0;c<nCycles;c++){
+		for(int r=0;r<t->nRanks;r++){
+			for(int l=1;l<size[2]-1;l++) for(int k=1;k<size[1]-1;k++) for(int j=1;j<size[0]-1;j++){
+				long g = IDX(j,k,l,size[0],size[1]);
+				tmp[g] = coeff*(phi[r][g+1] + phi[r][g-1] + phi[r][g+sx] + phi[r][g-sx] + phi[r][g+sxy] + phi[r][g-sxy] + rho[r][g]);
+			}
+			for(int l=1;l<size[2]-1;l++) for(int k=1;k<size[1]-1;k++) for(int j=1;j<size[0]-1;j++){
+				long g = IDX(j,k,l,size[0],size[1]);
+				phi[r][g] = tmp[g];
+			}
+		}
+		orc_halo(t,phi,size,1,0,0);
+		if(bnd) orc_bnd(t,phi,size,bnd,bndSlice); else orc_neutralize(t,phi,size);
+	}
+	free(tmp);
+}
+
 /* ---- boundary conditions (src/grid.c:921-1023) -------------------------------------------------------------------
  * bnd[8]: bndType per boundary index as in Grid::bnd of a rank-4 grid (1..3 lower x,y,z; 5..7 upper; 0 and 4 unused):
  * 1 PERIODIC, 2 DIRICHLET, 3 NEUMANN.  bndSlice[r]: 8 slices of orc_slice_max() doubles, slice `boundary` in the element
@@ -487,6 +510,7 @@ struct OrcMg {
 	int size[16][3];
 	double **rho[16], **phi[16], **res[16];   /* [level][rank]; level 0 borrowed per call */
 	int nonPeriodic, bnd[8];                  /* orc_mg_set_bnd: boundary types of every level */
+	int smoother[3];                          /* orc_mg_set_smoothers: pre, post, coarse; 0 gaussSeidelRB, 1 jacobian */
 	double **bndSlice[16];                    /* [level][rank], 8 slices each */
 };
 
@@ -531,7 +555,12 @@ static void mg_bnd(OrcMg *mg, int level){
 	if(mg->nonPeriodic) orc_bnd(&mg->topo,mg->phi[level],mg->size[level],mg->bnd,mg->bndSlice[level]);
 	else orc_neutralize(&mg->topo,mg->phi[level],mg->size[level]);
 }
-static void mg_gs(OrcMg *mg, int level, int nCycles){
+void orc_mg_set_smoothers(OrcMg *mg, int pre, int post, int coarse){ mg->smoother[0] = pre; mg->smoother[1] = post; mg->smoother[2] = coarse; }
+static void mg_gs(OrcMg *mg, int level, int nCycles, int which){
+	if(mg->smoother[which] == 1){
+		orc_jacobi3d(&mg->topo,mg->phi[level],mg->rho[level],mg->size[level],nCycles,mg->nonPeriodic ? mg->bnd : 0,mg->nonPeriodic ? mg->bndSlice[level] : 0);
+		return;
+	}
 	if(mg->nonPeriodic) orc_gs3d_bnd(&mg->topo,mg->phi[level],mg->rho[level],mg->size[level],nCycles,mg->bnd,mg->bndSlice[level]);
 	else orc_gs3d(&mg->topo,mg->phi[level],mg->rho[level],mg->size[level],nCycles);
 }
@@ -549,7 +578,9 @@ double *orc_mg_level(OrcMg *mg, int which, int level, int rank, int *sizeOut){
 }
 
 /* src/multigrid.c:1496-1548 */
-static void vcycle(OrcMg *mg, int level){
+static void vcycle_top(OrcMg *mg, int level, int top);
+static void vcycle(OrcMg *mg, int level){ vcycle_top(mg, level, 0); }
+static void vcycle_top(OrcMg *mg, int level, int top){
 	const OrcTopo *t = &mg->topo;
 	int R = t->nRanks, bottom = mg->nLevels-1;
 	const int *sz = mg->size[level];
@@ -559,24 +590,69 @@ static void vcycle(OrcMg *mg, int level){
 		orc_halo(t,phi,sz,1,0,0);
 		orc_halo(t,rho,sz,1,0,0);
 		orc_neutralize(t,rho,sz);
-		mg_gs(mg,level,mg->nCoarse);
+		mg_gs(mg,level,mg->nCoarse,2);
 		mg_bnd(mg,level);
 		orc_bilin_prol3d(t,mg->res[level-1],mg->size[level-1],phi,sz);
 		return;
 	}
 	orc_halo(t,rho,sz,1,0,0);
 	orc_neutralize(t,rho,sz);
-	mg_gs(mg,level,mg->nPre);
+	mg_gs(mg,level,mg->nPre,0);
 	for(int r=0;r<R;r++) orc_residual(res[r],rho[r],phi[r],sz);
 	orc_halo(t,res,sz,1,0,0);
 	for(int r=0;r<R;r++) orc_half_restrict3d(res[r],sz,mg->rho[level+1][r],mg->size[level+1]);
-	vcycle(mg,level+1);
+	vcycle_top(mg,level+1,top);
 	for(int r=0;r<R;r++) for(long g=0;g<n;g++) phi[r][g] += res[r][g];
 	orc_halo(t,phi,sz,1,0,0);
 	mg_bnd(mg,level);
-	mg_gs(mg,level,mg->nPost);
+	mg_gs(mg,level,mg->nPost,1);
 	mg_bnd(mg,level);
-	if(level>0) orc_bilin_prol3d(t,mg->res[level-1],mg->size[level-1],phi,sz);
+	if(level>top) orc_bilin_prol3d(t,mg->res[level-1],mg->size[level-1],phi,sz);
+}
+/* mgW (src/multigrid.c:1675-1683): two recursive V-cycles that meet at level bottom/2 */
+void orc_mg_wcycle(OrcMg *mg, double **rho0, double **phi0, double **res0){
+	for(int r=0;r<mg->topo.nRanks;r++){ mg->rho[0][r] = rho0[r]; mg->phi[0][r] = phi0[r]; mg->res[0][r] = res0[r]; }
+	int bottom = mg->nLevels-1, middle = bottom/2;
+	vcycle_top(mg,0,middle);
+	vcycle_top(mg,middle,0);
+}
+/* mgVRegular (src/multigrid.c:1559-1650), call for call (it SUBTRACTS the prolonged correction) */
+void orc_mg_vregular(OrcMg *mg, double **rho0, double **phi0, double **res0){
+	const OrcTopo *t = &mg->topo;
+	int R = t->nRanks, bottom = mg->nLevels-1;
+	for(int r=0;r<R;r++){ mg->rho[0][r] = rho0[r]; mg->phi[0][r] = phi0[r]; mg->res[0][r] = res0[r]; }
+	for(int cur=0;cur<bottom;cur++){
+		const int *sz = mg->size[cur];
+		long n = (long)sz[0]*sz[1]*sz[2];
+		orc_halo(t,mg->phi[cur],sz,1,0,0);
+		mg_bnd(mg,cur);
+		orc_neutralize(t,mg->rho[cur],sz);
+		mg_gs(mg,cur,mg->nPre,0);
+		orc_halo(t,mg->rho[cur],sz,1,0,0);
+		mg_bnd(mg,cur);
+		for(int r=0;r<R;r++){ for(long g=0;g<n;g++) mg->res[cur][r][g] = 0; orc_residual(mg->res[cur][r],mg->rho[cur][r],mg->phi[cur][r],sz); }
+		orc_halo(t,mg->res[cur],sz,1,0,0);
+		for(int r=0;r<R;r++) orc_half_restrict3d(mg->res[cur][r],sz,mg->rho[cur+1][r],mg->size[cur+1]);
+	}
+	{
+		const int *sz = mg->size[bottom];
+		orc_neutralize(t,mg->rho[bottom],sz);
+		orc_halo(t,mg->rho[bottom],sz,1,0,0);
+		mg_gs(mg,bottom,mg->nCoarse,2);
+		orc_halo(t,mg->phi[bottom],sz,1,0,0);
+		mg_bnd(mg,bottom);
+		orc_bilin_prol3d(t,mg->res[bottom-1],mg->size[bottom-1],mg->phi[bottom],sz);
+	}
+	for(int cur=bottom-1;cur>=0;cur--){
+		const int *sz = mg->size[cur];
+		long n = (long)sz[0]*sz[1]*sz[2];
+		for(int r=0;r<R;r++) for(long g=0;g<n;g++) mg->phi[cur][r][g] -= mg->res[cur][r][g];
+		orc_halo(t,mg->phi[cur],sz,1,0,0);
+		mg_bnd(mg,cur);
+		mg_gs(mg,cur,mg->nPost,1);
+		mg_bnd(mg,cur);
+		if(cur>0) orc_bilin_prol3d(t,mg->res[cur-1],mg->size[cur-1],mg->phi[cur],sz);
+	}
 }
 
 void orc_mg_vcycle(OrcMg *mg, double **rho0, double **phi0, double **res0){

@@ -86,6 +86,12 @@ void   orc_mg_restrict_bnd(OrcMg *mg);
 int    orc_mg_solve(OrcMg *mg, double **rho0, double **phi0, double **res0, double tol,
                     int maxCycles, double *barRes, int cap);
 void   orc_mg_vcycle(OrcMg *mg, double **rho0, double **phi0, double **res0);
+/* the other select() targets of the solver: mgW (multigrid.c:1675), mgVRegular (:1559), and the smoothers of mgSetSolver (:28-83):
+ * 0 gaussSeidelRB (mgGS3D), 1 jacobian (mgJacob3D :500), for the pre-, post- and coarse-level smoother */
+void   orc_mg_wcycle(OrcMg *mg, double **rho0, double **phi0, double **res0);
+void   orc_mg_vregular(OrcMg *mg, double **rho0, double **phi0, double **res0);
+void   orc_mg_set_smoothers(OrcMg *mg, int pre, int post, int coarse);
+void   orc_jacobi3d(const OrcTopo *t, double **phi, double **rho, const int *size, int nCycles, const int *bnd, double **bndSlice);
 /* access to a coarse level (for parity checks): which = 0 rho, 1 phi, 2 res */
 double *orc_mg_level(OrcMg *mg, int which, int level, int rank, int *sizeOut);
 

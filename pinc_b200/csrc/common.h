@@ -227,6 +227,7 @@ void gridBnd(Ctx *c, DevGrid *g, const MpiInfo *m);             // gBnd (src/gri
 void gridEdge(Ctx *c, DevGrid *g, int boundary, int kind);     // gDirichlet / gNeumann of one edge
 void gridUploadBnd(Ctx *c, DevGrid *g);                          // host bndSlice -> device (after the host changed it)
 void gridAddTo(Ctx *c, DevGrid *r, const DevGrid *a);
+void gridSubFrom(Ctx *c, DevGrid *r, const DevGrid *a);
 // sum over the true grid of val (mode 0), val^2 after squaring in place (mode 1) or val*other (mode 2);
 // the result lands in c->d_scal[slot] (this rank only, no all-reduce)
 void gridSumTrue(Ctx *c, DevGrid *g, int mode, const DevGrid *other, int slot);

@@ -48,6 +48,10 @@ void gridAddTo(Ctx *c, DevGrid *r, const DevGrid *a){
 	if(a->n != r->n) fatal("gAddTo: grids differ in size");
 	PINC_LAUNCH(c, K_GRIDOP, 24.0*r->n, (k_addto<<<ewGrid(c,r->n),256,0,c->stream>>>(r->d, a->d, r->n)));
 }
+void gridSubFrom(Ctx *c, DevGrid *r, const DevGrid *a){
+	if(a->n != r->n) fatal("gSubFrom: grids differ in size");
+	PINC_LAUNCH(c, K_GRIDOP, 24.0*r->n, (k_subfrom<<<ewGrid(c,r->n),256,0,c->stream>>>(r->d, a->d, r->n)));
+}
 void gridZero(Ctx *c, DevGrid *g){
 	PINC_CUDA(cudaMemsetAsync(g->d, 0, (size_t)g->n*sizeof(double), c->stream));
 }
@@ -342,11 +346,7 @@ void gAddTo(Grid *result, Grid *addition){
 	Ctx *c = cur();
 	gridAddTo(c, devGrid(c, result), devGrid(c, addition));
 }
-void gSubFrom(Grid *result, const Grid *subtraction){
-	Ctx *c = cur(); DevGrid *r = devGrid(c, result), *a = devGrid(c, subtraction);
-	if(a->n != r->n) fatal("gSubFrom: grids differ in size");
-	PINC_LAUNCH(c, K_GRIDOP, 24.0*r->n, (k_subfrom<<<ewGrid(c,r->n),256,0,c->stream>>>(r->d, a->d, r->n)));
-}
+void gSubFrom(Grid *result, const Grid *subtraction){ Ctx *c = cur(); gridSubFrom(c, devGrid(c, result), devGrid(c, subtraction)); }
 double gSumTruegrid(const Grid *grid){
 	Ctx *c = cur();
 	gridSumTrue(c, devGrid(c, grid), 0, nullptr, 1);

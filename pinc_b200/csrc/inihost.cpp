@@ -65,13 +65,30 @@ MultigridSolver *mgAllocSolver(const dictionary *ini, Grid *rho, Grid *phi){
 	int nPre = iniGetInt(ini, "multigrid:nPreSmooth");
 	int nPost = iniGetInt(ini, "multigrid:nPostSmooth");
 	int nCoarse = iniGetInt(ini, "multigrid:nCoarseSolve");
-	wantStr(ini, "multigrid:preSmooth", "gaussSeidelRB");
-	wantStr(ini, "multigrid:postSmooth", "gaussSeidelRB");
-	wantStr(ini, "multigrid:coarseSolver", "gaussSeidelRB");
 	wantStr(ini, "multigrid:restrictor", "halfWeight");
 	wantStr(ini, "multigrid:prolongator", "bilinear");
-	wantStr(ini, "multigrid:cycle", "mgVRecursive");
-	return pincMgAllocSolver(rho, phi, nLevels, nMGCycles, nPre, nPost, nCoarse);      /* the same sanity checks as mgAlloc */
+	MultigridSolver *s = pincMgAllocSolver(rho, phi, nLevels, nMGCycles, nPre, nPost, nCoarse);      /* the same sanity checks as mgAlloc */
+	/* mgSetSolver (multigrid.c:28-83) and getMgAlgo (:113-125) for what the library provides */
+	typedef void (*Smooth)(Grid*, const Grid*, const int, const MpiInfo*);
+	auto smoother = [&](const char *key) -> Smooth {
+		char *v = iniGetStr(ini, key);
+		Smooth f = nullptr;
+		if(v && !strcmp(v, "gaussSeidelRB")) f = mgGS3D;
+		else if(v && !strcmp(v, "jacobian")) f = mgJacob3D;
+		else fatal("%s = %s: libpinc_b200 provides gaussSeidelRB and jacobian (3-D)", key, v ? v : "(missing)");
+		free(v);
+		return f;
+	};
+	Smooth pre = smoother("multigrid:preSmooth"), post = smoother("multigrid:postSmooth"), coarse = smoother("multigrid:coarseSolver");
+	Multigrid *mgs[3] = { s->mgRho, s->mgPhi, s->mgRes };
+	for(Multigrid *mg : mgs){ mg->preSmooth = pre; mg->postSmooth = post; mg->coarseSolv = coarse; }
+	char *cyc = iniGetStr(ini, "multigrid:cycle");
+	if(cyc && !strcmp(cyc, "mgVRecursive")) s->mgAlgo = (funPtr)mgVRecursive;
+	else if(cyc && !strcmp(cyc, "mgVRegular")) s->mgAlgo = (funPtr)mgVRegular;
+	else if(cyc && !strcmp(cyc, "mgW")) s->mgAlgo = (funPtr)mgW;
+	else fatal("multigrid:cycle = %s: libpinc_b200 provides mgVRecursive, mgVRegular and mgW (the reference's mgFMG destroys mgRho->grids[0])", cyc ? cyc : "(missing)");
+	free(cyc);
+	return s;
 }
 
 void puGet3DRotationParameters(dictionary *ini, double *T, double *S){                                                /* pusher.c:485 */

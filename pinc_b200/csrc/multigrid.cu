@@ -450,6 +450,49 @@ static void opGS(Ctx *c, DevGrid *phi, DevGrid *rho, int nCycles, const MpiInfo 
 			gridBnd(c, phi, m);
 		}
 }
+// "jacobian" smoother.  The reference's mgJacob3D (src/multigrid.c:500-551) is undefined behaviour as written: its loop
+// never advances the write index (`tempVal[g]` with g fixed), its neighbour indices start at +-sizeProd[d] instead of
+// g +- sizeProd[d] (the first read is phiVal[-1]), and it then copies the uninitialised scratch array over phi.  Provided
+// here is the iteration its comments describe - every true node from the OLD values of its six neighbours, then gHaloOp and
+// gBnd - so that `multigrid:preSmooth = jacobian` selects something usable; parity for this one function is against the
+// oracle's restatement of the same intent only (tests/cycles_common.py).
+__global__ void k_jacobi(const double *__restrict__ phi, const double *__restrict__ rho, double *__restrict__ out, int s0, int s1, int s2){
+	int t0 = s0-2, t1 = s1-2, t2 = s2-2;
+	long nt = (long)t0*t1*t2;
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	const double coeff = 1./6;
+	for(; i < nt; i += st){
+		int j, k, l; truePoint(i, t0, t1, j, k, l);
+		long g = ix(j,k,l,s0,s1); const long sx = s0, sxy = (long)s0*s1;
+		out[g] = coeff*(phi[g+1] + phi[g-1] + phi[g+sx] + phi[g-sx] + phi[g+sxy] + phi[g-sxy] + rho[g]);
+	}
+}
+__global__ void k_copy_true(double *__restrict__ dst, const double *__restrict__ src, int s0, int s1, int s2){
+	int t0 = s0-2, t1 = s1-2, t2 = s2-2;
+	long nt = (long)t0*t1*t2;
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	for(; i < nt; i += st){ int j, k, l; truePoint(i, t0, t1, j, k, l); long g = ix(j,k,l,s0,s1); dst[g] = src[g]; }
+}
+static void opJacobi(Ctx *c, DevGrid *phi, DevGrid *rho, int nCycles, const MpiInfo *m){
+	long nt = trueCount(phi);
+	double *tmp = (double*)tmpBuffer(c, (size_t)phi->n*sizeof(double));
+	for(int cyc = 0; cyc < nCycles; cyc++){
+		PINC_LAUNCH(c, K_GS, 24.0*nt, (k_jacobi<<<tGrid(c,nt),256,0,c->stream>>>(phi->d, rho->d, tmp, phi->size[0], phi->size[1], phi->size[2])));
+		PINC_LAUNCH(c, K_GS, 16.0*nt, (k_copy_true<<<tGrid(c,nt),256,0,c->stream>>>(phi->d, tmp, phi->size[0], phi->size[1], phi->size[2])));
+		gridHalo(c, phi, m, 0, 0);
+		gridBnd(c, phi, m);
+	}
+}
+} // namespace pinc
+extern "C" void mgJacob3D(Grid *phi, const Grid *rho, const int nCycles, const MpiInfo *mpiInfo);
+namespace pinc {
+typedef void (*SmoothFn)(Grid*, const Grid*, const int, const MpiInfo*);
+// the smoother a Multigrid names (mgSetSolver, src/multigrid.c:28-83): red-black Gauss-Seidel (default) or Jacobi
+static void opSmooth(Ctx *c, SmoothFn fn, DevGrid *phi, DevGrid *rho, int nCycles, const MpiInfo *m){
+	if(!fn || fn == (SmoothFn)mgGS3D) opGS(c, phi, rho, nCycles, m);
+	else if(fn == (SmoothFn)mgJacob3D) opJacobi(c, phi, rho, nCycles, m);
+	else fatal("multigrid: smoother is neither mgGS3D (gaussSeidelRB) nor mgJacob3D (jacobian)");
+}
 static void opResidual(Ctx *c, DevGrid *res, DevGrid *rho, DevGrid *phi){
 	long nt = trueCount(phi);
 	PINC_LAUNCH(c, K_RESIDUAL, 24.0*nt, (k_residual<<<tGrid(c,nt),256,0,c->stream>>>(res->d, rho->d, phi->d, phi->size[0], phi->size[1], phi->size[2])));
@@ -475,14 +518,14 @@ static void opVCycle(Ctx *c, int level, int bottom, int top, Multigrid *mgRho, M
 		gridHalo(c, phi, m, 0, 0);
 		gridHalo(c, rho, m, 0, 0);
 		gridNeutralize(c, rho, m);
-		opGS(c, phi, rho, mgRho->nCoarseSolve, m);
+		opSmooth(c, (SmoothFn)mgRho->coarseSolv, phi, rho, mgRho->nCoarseSolve, m);
 		gridBnd(c, phi, m);
 		if(level > 0) opProlong(c, devGrid(c, mgRes->grids[level-1]), phi, m);
 		return;
 	}
 	gridHalo(c, rho, m, 0, 0);
 	gridNeutralize(c, rho, m);
-	opGS(c, phi, rho, mgRho->nPreSmooth, m);
+	opSmooth(c, (SmoothFn)mgRho->preSmooth, phi, rho, mgRho->nPreSmooth, m);
 	opResidual(c, res, rho, phi);
 	gridHalo(c, res, m, 0, 0);
 	opRestrict(c, res, devGrid(c, mgRho->grids[level+1]));
@@ -490,9 +533,64 @@ static void opVCycle(Ctx *c, int level, int bottom, int top, Multigrid *mgRho, M
 	gridAddTo(c, phi, res);
 	gridHalo(c, phi, m, 0, 0);
 	gridBnd(c, phi, m);
-	opGS(c, phi, rho, mgRho->nPostSmooth, m);
+	opSmooth(c, (SmoothFn)mgRho->postSmooth, phi, rho, mgRho->nPostSmooth, m);
 	gridBnd(c, phi, m);
 	if(level > top) opProlong(c, devGrid(c, mgRes->grids[level-1]), phi, m);
+}
+
+// mgVRegular (src/multigrid.c:1559-1650), call for call - including its gSubFrom(phi, res) where mgVRecursive adds
+static void opVRegular(Ctx *c, int level, int bottom, int top, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *m){
+	for(int cur = level; cur < bottom; cur++){
+		DevGrid *phi = devGrid(c, mgPhi->grids[cur]), *rho = devGrid(c, mgRho->grids[cur]), *res = devGrid(c, mgRes->grids[cur]);
+		gridHalo(c, phi, m, 0, 0);
+		gridBnd(c, phi, m);
+		gridNeutralize(c, rho, m);
+		opSmooth(c, (SmoothFn)mgRho->preSmooth, phi, rho, mgRho->nPreSmooth, m);
+		gridHalo(c, rho, m, 0, 0);
+		gridBnd(c, phi, m);
+		gridZero(c, res);
+		opResidual(c, res, rho, phi);
+		gridHalo(c, res, m, 0, 0);
+		opRestrict(c, res, devGrid(c, mgRho->grids[cur+1]));
+	}
+	{
+		DevGrid *phi = devGrid(c, mgPhi->grids[bottom]), *rho = devGrid(c, mgRho->grids[bottom]);
+		gridNeutralize(c, rho, m);
+		gridHalo(c, rho, m, 0, 0);
+		opSmooth(c, (SmoothFn)mgRho->coarseSolv, phi, rho, mgRho->nCoarseSolve, m);
+		gridHalo(c, phi, m, 0, 0);
+		gridBnd(c, phi, m);
+		opProlong(c, devGrid(c, mgRes->grids[bottom-1]), phi, m);
+	}
+	for(int cur = bottom-1; cur >= top; cur--){
+		DevGrid *phi = devGrid(c, mgPhi->grids[cur]), *rho = devGrid(c, mgRho->grids[cur]), *res = devGrid(c, mgRes->grids[cur]);
+		gridSubFrom(c, phi, res);
+		gridHalo(c, phi, m, 0, 0);
+		gridBnd(c, phi, m);
+		opSmooth(c, (SmoothFn)mgRho->postSmooth, phi, rho, mgRho->nPostSmooth, m);
+		gridBnd(c, phi, m);
+		if(cur > top) opProlong(c, devGrid(c, mgRes->grids[cur-1]), phi, m);
+	}
+}
+// one pass of the cycle a solver names (getMgAlgo, src/multigrid.c:113-125)
+} // namespace pinc
+extern "C" {
+void mgVRegular(int level, int bottom, int top, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *mpiInfo);
+void mgFMG(int level, int bottom, int top, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *mpiInfo);
+void mgW(int level, int bottom, int top, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *mpiInfo);
+void mgVRecursive(int level, int bottom, int top, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *mpiInfo);
+}
+namespace pinc {
+static void opCycle(Ctx *c, funPtr algo, int level, int bottom, int top, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *m){
+	if(!algo || algo == (funPtr)mgVRecursive) opVCycle(c, level, bottom, top, mgRho, mgPhi, mgRes, m);
+	else if(algo == (funPtr)mgVRegular) opVRegular(c, level, bottom, top, mgRho, mgPhi, mgRes, m);
+	else if(algo == (funPtr)mgW){                        // src/multigrid.c:1675-1683
+		int middle = bottom/2;
+		opVCycle(c, 0, bottom, middle, mgRho, mgPhi, mgRes, m);
+		opVCycle(c, middle, bottom, 0, mgRho, mgPhi, mgRes, m);
+	} else if(algo == (funPtr)mgFMG)
+		fatal("multigrid: cycle = mgFMG is not provided: the reference's mgFMG (src/multigrid.c:1652-1672) overwrites mgRho->grids[0] with the coarsest grid, after which mgSolveRaw reads out of bounds");
+	else fatal("multigrid: unknown cycle function");
 }
 
 // =================================================================================================
@@ -1739,8 +1837,8 @@ __global__ void k_seq_advance(unsigned long long *base, unsigned long long n){ *
 // (host enqueue cost was the bottleneck: 28 000 launches per time step).  The sequence numbers of the peer-memory
 // operations are offsets from a device word that the graph itself advances, so a replay continues the sequence.
 
-static void oneCycle(Ctx *c, int bottom, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *m, DevGrid *res, DevGrid *rho, DevGrid *phi){
-	opVCycle(c, 0, bottom, 0, mgRho, mgPhi, mgRes, m);
+static void oneCycle(Ctx *c, funPtr algo, int bottom, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *m, DevGrid *res, DevGrid *rho, DevGrid *phi){
+	opCycle(c, algo, 0, bottom, 0, mgRho, mgPhi, mgRes, m);
 	opResidual(c, res, rho, phi);
 	gridHalo(c, res, m, 0, 0);
 	gridSumTrueAll(c, res, 1, 3, m);
@@ -1748,7 +1846,6 @@ static void oneCycle(Ctx *c, int bottom, Multigrid *mgRho, Multigrid *mgPhi, Mul
 
 static void opsSolve(Ctx *c, funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *m, double tol, int maxCycles){
 	int bottom = mgRho->nLevels - 1;
-	(void)mgAlgo;
 	c->mgHistory.clear();
 	c->mgHistPending = false;
 	if(mgRho->nLevels > 1){
@@ -1771,7 +1868,7 @@ static void opsSolve(Ctx *c, funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, 
 				cudaGraph_t graph = nullptr;
 				cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
 				if(e == cudaSuccess){
-					oneCycle(c, bottom, mgRho, mgPhi, mgRes, m, res, rho, phi);
+					oneCycle(c, mgAlgo, bottom, mgRho, mgPhi, mgRes, m, res, rho, phi);
 					unsigned long long nOps = p->seq - seq0;
 					k_seq_advance<<<1,1,0,c->stream>>>(P2P::flag(p->arena, 10), nOps);
 					e = cudaStreamEndCapture(c->stream, &graph);
@@ -1788,10 +1885,10 @@ static void opsSolve(Ctx *c, funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, 
 					fprintf(stderr, "PINC-B200 WARNING: CUDA graph capture of the V-cycle failed (%s); staying with eager launches\n", cudaGetErrorString(e));
 					G.state = -1;
 					p->seq = seq0;                                        // nothing of the captured cycle ran
-					oneCycle(c, bottom, mgRho, mgPhi, mgRes, m, res, rho, phi);
+					oneCycle(c, mgAlgo, bottom, mgRho, mgPhi, mgRes, m, res, rho, phi);
 				}
 			} else {
-				oneCycle(c, bottom, mgRho, mgPhi, mgRes, m, res, rho, phi);
+				oneCycle(c, mgAlgo, bottom, mgRho, mgPhi, mgRes, m, res, rho, phi);
 			}
 			barRes = readScalar(c, 3);
 			barRes /= (double)gTotTruesize(mgRho->grids[0], m);
@@ -1807,7 +1904,7 @@ static void opsSolve(Ctx *c, funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, 
 		for(int cyc = 0; cyc < mgRho->nMGCycles; cyc++){
 			gridHalo(c, rho, m, 0, 0);
 			gridNeutralize(c, rho, m);
-			opGS(c, phi, rho, mgRho->nCoarseSolve, m);
+			opSmooth(c, (SmoothFn)mgRho->coarseSolv, phi, rho, mgRho->nCoarseSolve, m);
 		}
 	}
 }
@@ -2097,50 +2194,46 @@ double mgSumTrueSquared(Grid *error, const MpiInfo *mpiInfo){
 
 static void checkPlugins(const Multigrid *mg){
 	if(mg->nLevels < 1) fatal("multigrid: nLevels < 1");
-	if((mg->coarseSolv && mg->coarseSolv != mgGS3D) || (mg->preSmooth && mg->preSmooth != mgGS3D) || (mg->postSmooth && mg->postSmooth != mgGS3D))
-		fatal("multigrid: only the gaussSeidelRB smoother (mgGS3D) is implemented");
+	auto okS = [](const void *f){ return !f || f == (const void*)mgGS3D || f == (const void*)mgJacob3D; };
+	if(!okS((const void*)mg->coarseSolv) || !okS((const void*)mg->preSmooth) || !okS((const void*)mg->postSmooth))
+		fatal("multigrid: the smoothers provided are gaussSeidelRB (mgGS3D) and jacobian (mgJacob3D)");
 	if((mg->restrictor && mg->restrictor != mgHalfRestrict3D) || (mg->prolongator && mg->prolongator != mgBilinProl3D))
 		fatal("multigrid: only halfWeight restriction and bilinear prolongation are implemented");
 }
-
-// src/multigrid.c:1314-1379: boundary values of every coarser level := every second value of the finer level's slices
-// (host arrays; the reference defines this function and never calls it - its coarse bndSlice arrays stay uninitialised,
-// so a host that wants non-periodic multigrid calls it after gSetBndSlices on the finest level)
-void mgRestrictBnd(Multigrid *mg){
-	Ctx *c = cur();
-	for(int lvl = 0; lvl < mg->nLevels-1; lvl++){
-		Grid *f = mg->grids[lvl], *g = mg->grids[lvl+1];
-		const int rank = f->rank;
-		if(!f->bndSlice || !g->bndSlice) fatal("mgRestrictBnd: level %d has no bndSlice", lvl);
-		long nF = 0, nC = 0;
-		for(int d = 0; d < rank; d++){
-			long a = 1, b = 1;
-			for(int dd = 0; dd < rank; dd++) if(dd != d){ a *= f->size[dd]; b *= g->size[dd]; }
-			if(a > nF) nF = a;
-			if(b > nC) nC = b;
-		}
-		for(int d = 1; d < 2*rank; d++){
-			if(d == rank) continue;
-			for(long s = 0; s < nC; s++) g->bndSlice[s + nC*d] = f->bndSlice[2*s + nF*d];
-		}
-		auto it = c->grids.find(g);
-		if(it != c->grids.end() && it->second->nonPeriodic) gridUploadBnd(c, it->second);
-	}
+// the persistent kernels implement exactly one configuration: mgVRecursive with red-black Gauss-Seidel everywhere
+static bool defaultPlugins(funPtr algo, const Multigrid *mg){
+	auto gs = [](const void *f){ return !f || f == (const void*)mgGS3D; };
+	return (!algo || algo == (funPtr)mgVRecursive) && gs((const void*)mg->coarseSolv) && gs((const void*)mg->preSmooth) && gs((const void*)mg->postSmooth);
 }
 
+void mgJacob3D(Grid *phi, const Grid *rho, const int nCycles, const MpiInfo *mpiInfo){
+	Ctx *c = cur(); opJacobi(c, devGrid(c, phi), devGrid(c, rho), nCycles, mpiInfo);
+}
 void mgVRecursive(int level, int bottom, int top, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *mpiInfo){
 	checkPlugins(mgRho);
 	opVCycle(cur(), level, bottom, top, mgRho, mgPhi, mgRes, mpiInfo);
 }
+void mgVRegular(int level, int bottom, int top, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *mpiInfo){
+	checkPlugins(mgRho);
+	opVRegular(cur(), level, bottom, top, mgRho, mgPhi, mgRes, mpiInfo);
+}
+void mgW(int level, int bottom, int top, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *mpiInfo){
+	(void)level; (void)top;
+	checkPlugins(mgRho);
+	opCycle(cur(), (funPtr)mgW, 0, bottom, 0, mgRho, mgPhi, mgRes, mpiInfo);
+}
+void mgFMG(int level, int bottom, int top, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *mpiInfo){
+	opCycle(cur(), (funPtr)mgFMG, level, bottom, top, mgRho, mgPhi, mgRes, mpiInfo);
+}
 
 void mgSolveRaw(funPtr mgAlgo, Multigrid *mgRho, Multigrid *mgPhi, Multigrid *mgRes, const MpiInfo *mpiInfo){
-	if(mgAlgo && mgAlgo != (funPtr)mgVRecursive) fatal("multigrid: only cycle = mgVRecursive is implemented");
 	checkPlugins(mgRho);
 	Ctx *c = cur();
 	const double tol = 1.E-10;                       // src/multigrid.c:1695
 	const int maxCycles = pinc::mgMaxCyclesDefault();    // the reference has no bound (it would hang); this one fails loudly, see mgConvergenceCheck
-	if(fusedEligible(c, mgRho, mgPhi, mgRes, mpiInfo)) pinc::solveSingle(c, mgRho, mgPhi, mgRes, tol, maxCycles);
-	else if(pinc::replicaEligible(c, mgRho, mpiInfo)){
+	const bool dflt = defaultPlugins(mgAlgo, mgRho);
+	if(dflt && fusedEligible(c, mgRho, mgPhi, mgRes, mpiInfo)) pinc::solveSingle(c, mgRho, mgPhi, mgRes, tol, maxCycles);
+	else if(dflt && pinc::replicaEligible(c, mgRho, mpiInfo)){
 		if(!pinc::hybridSolve(c, mgRho, mgPhi, mgRes, mpiInfo, tol, maxCycles)) pinc::replicaSolve(c, mgRho, mgPhi, mgRes, mpiInfo, tol, maxCycles);
 	}
 	else { opsSolve(c, mgAlgo, mgRho, mgPhi, mgRes, mpiInfo, tol, maxCycles); c->mgLastPath = 0; }

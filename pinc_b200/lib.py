@@ -69,6 +69,10 @@ SIGNATURES = {
     "mgSolveRaw": (None, [C.c_void_p, P(abi.Multigrid), P(abi.Multigrid), P(abi.Multigrid), P(abi.MpiInfo)]),
     "mgVRecursive": (None, [C.c_int, C.c_int, C.c_int, P(abi.Multigrid), P(abi.Multigrid), P(abi.Multigrid), P(abi.MpiInfo)]),
     "mgGS3D": (None, [P(abi.Grid), P(abi.Grid), C.c_int, P(abi.MpiInfo)]),
+    "mgJacob3D": (None, [P(abi.Grid), P(abi.Grid), C.c_int, P(abi.MpiInfo)]),
+    "mgVRegular": (None, [C.c_int, C.c_int, C.c_int, P(abi.Multigrid), P(abi.Multigrid), P(abi.Multigrid), P(abi.MpiInfo)]),
+    "mgW": (None, [C.c_int, C.c_int, C.c_int, P(abi.Multigrid), P(abi.Multigrid), P(abi.Multigrid), P(abi.MpiInfo)]),
+    "mgFMG": (None, [C.c_int, C.c_int, C.c_int, P(abi.Multigrid), P(abi.Multigrid), P(abi.Multigrid), P(abi.MpiInfo)]),
     "mgHalfRestrict3D": (None, [P(abi.Grid), P(abi.Grid)]),
     "mgBilinProl3D": (None, [P(abi.Grid), P(abi.Grid), P(abi.MpiInfo)]),
     "mgResidual": (None, [P(abi.Grid), P(abi.Grid), P(abi.Grid), P(abi.MpiInfo)]),
