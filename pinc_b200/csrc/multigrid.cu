@@ -2206,6 +2206,31 @@ static bool defaultPlugins(funPtr algo, const Multigrid *mg){
 	return (!algo || algo == (funPtr)mgVRecursive) && gs((const void*)mg->coarseSolv) && gs((const void*)mg->preSmooth) && gs((const void*)mg->postSmooth);
 }
 
+// src/multigrid.c:1314-1379: boundary values of every coarser level := every second value of the finer level's slices
+// (host arrays; the reference defines this function and never calls it - its coarse bndSlice arrays stay uninitialised,
+// so a host that wants non-periodic multigrid calls it after gSetBndSlices on the finest level)
+void mgRestrictBnd(Multigrid *mg){
+	Ctx *c = cur();
+	for(int lvl = 0; lvl < mg->nLevels-1; lvl++){
+		Grid *f = mg->grids[lvl], *g = mg->grids[lvl+1];
+		const int rank = f->rank;
+		if(!f->bndSlice || !g->bndSlice) fatal("mgRestrictBnd: level %d has no bndSlice", lvl);
+		long nF = 0, nC = 0;
+		for(int d = 0; d < rank; d++){
+			long a = 1, b = 1;
+			for(int dd = 0; dd < rank; dd++) if(dd != d){ a *= f->size[dd]; b *= g->size[dd]; }
+			if(a > nF) nF = a;
+			if(b > nC) nC = b;
+		}
+		for(int d = 1; d < 2*rank; d++){
+			if(d == rank) continue;
+			for(long s = 0; s < nC; s++) g->bndSlice[s + nC*d] = f->bndSlice[2*s + nF*d];
+		}
+		auto it = c->grids.find(g);
+		if(it != c->grids.end() && it->second->nonPeriodic) gridUploadBnd(c, it->second);
+	}
+}
+
 void mgJacob3D(Grid *phi, const Grid *rho, const int nCycles, const MpiInfo *mpiInfo){
 	Ctx *c = cur(); opJacobi(c, devGrid(c, phi), devGrid(c, rho), nCycles, mpiInfo);
 }

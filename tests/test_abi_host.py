@@ -144,7 +144,7 @@ def test_ini_entry_points_from_a_pinc_style_host(tmp_path):
     r = subprocess.run([exe, "ok"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "ini-host-ok" in r.stdout, (r.returncode, r.stderr)
     r = subprocess.run([exe, "badcycle"], capture_output=True, text=True, timeout=120)
-    assert r.returncode != 0 and "PINC-B200 ERROR" in r.stderr and "mgVRecursive only" in r.stderr
+    assert r.returncode != 0 and "PINC-B200 ERROR" in r.stderr and "multigrid:cycle = mgFMG" in r.stderr
     r = subprocess.run([exe, "baddims"], capture_output=True, text=True, timeout=120)
     assert r.returncode != 0 and "only supports grid:nDims=3" in r.stderr
 
