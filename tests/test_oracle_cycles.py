@@ -41,13 +41,15 @@ def run_reference(text, cfg, init, cycle, smoothers):
     return out
 
 
-def run_oracle(cfg, init, cycle, smoothers):
+def run_oracle(cfg, init, cycle, smoothers, halo_first=False):
     O = orc.OrcWorld(cfg)
     O.lib.orc_mg_set_smoothers(O.mg, *smoothers)
     for r in range(cfg.nRanks):
         O.phi[r][:] = init[r][0]
         O.rho[r][:] = init[r][1]
     k = O._keep
+    if halo_first:
+        O.lib.orc_halo(C.byref(O.topo), k["phi"], orc.ip(O.size), 1, 0, 0)
     if cycle == "smoother":
         O.lib.orc_jacobi3d(C.byref(O.topo), k["phi"], k["rho"], orc.ip(O.size), 3, None, None)
     else:
