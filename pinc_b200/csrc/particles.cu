@@ -1267,9 +1267,41 @@ void puDistr3D1(const Population *pop, Grid *rhoGrid){
 	dp->predep = nullptr;
 }
 
+// the same over the occupied slots of a slotted population (the offender is reported by its slot index)
+__global__ void k_assert_slots(SlotPar Q, int which, long nCells, double lo0, double lo1, double lo2,
+		double hi0, double hi1, double hi2, int useLo, unsigned long long *first){
+	const long n = nCells*Q.cap;
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	const double lo[3] = {lo0, lo1, lo2}, hi[3] = {hi0, hi1, hi2};
+	for(; i < n; i += st){
+		const long c = i / Q.cap;
+		if((unsigned)(i - c*Q.cap) >= Q.cnt[c]) continue;
+		#pragma unroll
+		for(int d = 0; d < 3; d++){
+			double v = Q.S[Q.off + i + (3*which + d)*Q.plane];
+			if(v > hi[d] || (useLo && v < lo[d])) atomicMin(first, (unsigned long long)i*4 + d);
+		}
+	}
+}
 static void assertScan(Ctx *c, const Population *pop, int which, const double *lo, const double *hi, int useLo, const char *what){
-	DevPop *dp = devPop(c, pop);
+	DevPop *dp = devPopRaw(c, pop);
 	unsigned long long *first = (unsigned long long*)c->d_long;
+	if(dp->slotted && dp->mvPending) popLeaveSlotted(c, dp);
+	if(dp->slotted){
+		// the reference's main loop runs these scans every step (src/main.c:207,221): they must not cost the slotted layout
+		for(int s = 0; s < dp->nS; s++){
+			long n = pop->iStop[s] - pop->iStart[s];
+			if(n <= 0) continue;
+			PINC_CUDA(cudaMemsetAsync(first, 0xff, sizeof(unsigned long long), c->stream));
+			PINC_LAUNCH(c, K_MOVE, 24.0*n, (k_assert_slots<<<pGrid(c,dp->nCells*dp->slotCapS[s]),256,0,c->stream>>>(slotPar(dp,s), which, dp->nCells,
+				lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], useLo, first)));
+			PINC_CUDA(cudaMemcpyAsync(c->h_long, first, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+			streamSync(c);
+			unsigned long long f = (unsigned long long)c->h_long[0];
+			if(f != ~0ULL) fatal("Particle in slot %llu (of specie %i) %s in dimension %i", (unsigned long long)(f/4), s, what, (int)(f%4));
+		}
+		return;
+	}
 	for(int s = 0; s < dp->nS; s++){
 		long a = pop->iStart[s], n = pop->iStop[s] - a;
 		if(n <= 0) continue;

@@ -42,6 +42,10 @@ def run_against_oracle(L, cfg, steps, expect_slotted=True, per_rank=None, fused=
             X.migrate(); X.field_solve(); X.half_kick()
         seen = 0
         for it in range(steps):
+            if not fused:
+                # the debug scans of the reference's main loop (src/main.c:207, 221) have slotted forms: they must pass and
+                # must not cost the layout
+                W.run(lambda r, st: (L.pVelAssertMax(st.pop, 1.0), L.pPosAssertInLocalFrame(st.pop, st.rho)))
             W.step(fused=fused); O.step()
             seen += sum(layouts(W).values())
             for r in range(cfg.nRanks):
