@@ -147,6 +147,7 @@ struct Ctx {
 };
 
 Ctx *cur();                                    // current context of this host thread (created lazily)
+Ctx *curOrNull();                              // ... or nullptr if this thread never touched the device (host-array entry points)
 DevGrid *devGrid(Ctx *c, const Grid *g, bool upload = true);
 DevPop *devPop(Ctx *c, const Population *p, bool upload = true);       // contiguous planes current (leaves slotted mode)
 DevPop *devPopRaw(Ctx *c, const Population *p, bool upload = true);    // whatever mode the population is in

@@ -51,6 +51,7 @@ static Ctx *createCtx(int device, int rank, int size){
 	return c;
 }
 
+Ctx *curOrNull(){ return t_ctx; }
 Ctx *cur(){
 	if(t_ctx){ return t_ctx; }
 	int device = 0;

@@ -376,7 +376,8 @@ void gSetBndSlices(Grid *grid, MpiInfo *mpiInfo){
 		if(mpiInfo->subdomain[d-1] == mpiInfo->nSubdomains[d-1]-1 && (grid->bnd[d+rank] == DIRICHLET || grid->bnd[d+rank] == NEUMANN))
 			for(long s = 0; s < nMax; s++) grid->bndSlice[s + nMax*(d+rank)] = grid->bnd[d+rank] == DIRICHLET ? 1. : 2.;
 	}
-	Ctx *c = cur();
+	Ctx *c = curOrNull();                        // host arrays only; the device mirror follows if the grid already has one
+	if(!c) return;
 	auto it = c->grids.find(grid);
 	if(it != c->grids.end() && it->second->nonPeriodic) gridUploadBnd(c, it->second);
 }

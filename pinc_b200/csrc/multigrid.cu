@@ -2210,7 +2210,7 @@ static bool defaultPlugins(funPtr algo, const Multigrid *mg){
 // (host arrays; the reference defines this function and never calls it - its coarse bndSlice arrays stay uninitialised,
 // so a host that wants non-periodic multigrid calls it after gSetBndSlices on the finest level)
 void mgRestrictBnd(Multigrid *mg){
-	Ctx *c = cur();
+	Ctx *c = curOrNull();                        // host arrays only; the device mirrors follow where they exist
 	for(int lvl = 0; lvl < mg->nLevels-1; lvl++){
 		Grid *f = mg->grids[lvl], *g = mg->grids[lvl+1];
 		const int rank = f->rank;
@@ -2226,6 +2226,7 @@ void mgRestrictBnd(Multigrid *mg){
 			if(d == rank) continue;
 			for(long s = 0; s < nC; s++) g->bndSlice[s + nC*d] = f->bndSlice[2*s + nF*d];
 		}
+		if(!c) continue;
 		auto it = c->grids.find(g);
 		if(it != c->grids.end() && it->second->nonPeriodic) gridUploadBnd(c, it->second);
 	}

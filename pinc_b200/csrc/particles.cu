@@ -20,6 +20,7 @@
 // All arithmetic that reaches particle state follows the reference's expression order and the library is
 // compiled with -fmad=false (the reference's x86 build has no FMA contraction).
 #include "common.h"
+#include <atomic>
 
 namespace pinc {
 
@@ -784,7 +785,7 @@ static void scanHist(Ctx *c, unsigned *h, long n);
 static int g_slotted = -1;              // $PINC_B200_SLOTTED=0 keeps the counting sort every step
 static int g_slotHeadroom = 25;         // per cent of the fullest cell, plus g_slotExtra slots, kept free in every cell
 static int g_slotExtra = 16;
-static long g_slotOverflows = 0;        // how often a full cell sent a population back to the contiguous layout
+static std::atomic<long> g_slotOverflows{0};   // how often a full cell sent a population back to the contiguous layout (rank threads share it)
 static bool slottedEnabled(){ if(g_slotted < 0) g_slotted = (getenv("PINC_B200_SLOTTED") && atoi(getenv("PINC_B200_SLOTTED")) == 0) ? 0 : 1; return g_slotted != 0; }
 static SlotPar slotPar(const DevPop *dp, int s){ return SlotPar{ dp->slot, dp->slotPlane, dp->slotOff[s], dp->slotCapS[s], dp->d_cnt[s] }; }
 static double *mvBase(const DevPop *dp, int s){ return dp->alt + dp->host->iStart[s]; }         // six planes of stride dp->cap
@@ -1362,7 +1363,7 @@ void pincSetSlotted(int on, int headroomPercent, int extraSlots){
 	if(extraSlots >= 0) g_slotExtra = extraSlots;
 }
 int pincPopLayout(const Population *pop){ Ctx *c = cur(); auto it = c->pops.find(pop); return it != c->pops.end() && it->second->slotted ? 1 : 0; }
-long pincSlottedOverflows(void){ return g_slotOverflows; }
+long pincSlottedOverflows(void){ return g_slotOverflows.load(); }
 
 void pSumKinEnergy(Population *pop){
 	int nS = pop->nSpecies;

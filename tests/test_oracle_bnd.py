@@ -121,3 +121,34 @@ def test_oracle_boundaries_match_reference(sub, boundaries):
             a, b = O[stage][r], R[stage][r]
             err = np.abs(a - b).max() / np.abs(b).max()
             assert err <= 1e-13, (stage, r, err)
+
+
+def test_library_boundary_slices_on_host_arrays():
+    """gSetBndSlices (src/grid.c:608) and mgRestrictBnd (src/multigrid.c:1314) of libpinc_b200 work on the host arrays of the
+    structs (no device needed): same slices as the oracle's on every level, for every rank of a 1,2,2 decomposition."""
+    from helpers import ia
+    from pinc_b200 import lib as plib
+    L = plib.load()
+    sub, boundaries = bc.CASES[1]
+    text, cfg = small_cfg("warm", **bc.overrides(sub, boundaries))
+    O = orc.OrcWorld(cfg)
+    O.set_boundaries(cfg.boundaries)
+    kinds = {"PERIODIC": abi.PERIODIC, "DIRICHLET": abi.DIRICHLET, "NEUMANN": abi.NEUMANN}
+    bnd = ia([kinds[b] for b in cfg.boundaries])
+    for r in range(cfg.nRanks):
+        ts, gl = ia(cfg.trueSize), ia(cfg.nGhostLayers)
+        mpi = L.pincMpiAlloc(3, cfg.nSpecies, ia(cfg.nSubdomains), gl, ts, r, cfg.nRanks)
+        rho = L.pincGridAlloc(3, ts, gl, abi.SCALAR, bnd)
+        phi = L.pincGridAlloc(3, ts, gl, abi.SCALAR, bnd)
+        solver = L.pincMgAllocSolver(rho, phi, cfg.mgLevels, 1, 2, 2, 2)
+        L.gSetBndSlices(phi, mpi)
+        L.mgRestrictBnd(solver.contents.mgPhi)
+        for q in range(cfg.mgLevels):
+            g = solver.contents.mgPhi.contents.grids[q].contents
+            n = int(g.sizeProd[4])
+            mine = np.ctypeslib.as_array(g.bndSlice, shape=(8 * n,))
+            want = np.ctypeslib.as_array(O.lib.orc_mg_bnd_slice(O.mg, q, r), shape=(8 * n,))
+            for bd in (1, 2, 3, 5, 6, 7):
+                assert np.array_equal(mine[bd * n:(bd + 1) * n], want[bd * n:(bd + 1) * n]), (r, q, bd)
+        L.mgFreeSolver(solver)
+        L.pincGridFree(rho); L.pincGridFree(phi)
