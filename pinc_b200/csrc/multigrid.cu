@@ -870,27 +870,9 @@ template<bool X> __device__ __forceinline__ void fastSend(uint4 *mail, uint4 *co
 		if(n.t2 != LL_NONE) llStore(mail + n.t2, v, stag);
 	}
 }
-// rem (X only): bit 0 / 1 - node a / b lies on a face whose neighbour block belongs to ANOTHER RANK, bit 2 - so does the halo
-// slot this thread receives, bit 3 - the block has such a face at all.  A half-sweep then runs in two phases: the nodes that
-// only need this GPU's data are updated (and sent) as soon as the local slots have arrived - ~0.85 us after the neighbours'
-// stores -, the ones next to a remote face after the remote slots have (~1.5 us over NVLink), so the NVLink latency overlaps
-// the local exchange and the bulk of the arithmetic instead of adding to them (3.0 -> ~1.9 us per distributed half-sweep).
 template<bool X> __device__ __forceinline__ void fastHalf(double *Ph, int ex, int pl, uint4 *mail, uint4 *const *xBase, const uint4 *pAddr, int pIdx, bool recv, unsigned tagIn,
-		const FastNode &a, const FastNode &b, unsigned stag, bool send, unsigned rem){
-	if constexpr(X){
-		if(recv && pAddr && !(rem & 4u)) Ph[pIdx] = llWaitSys(pAddr, tagIn);
-		__syncthreads();
-		if(a.idx && !(rem & 1u)){ const double va = fastVal(Ph, a.idx, ex, pl, a.rho); Ph[a.idx] = va; if(send) fastSend<X>(mail, xBase, a, va, stag); }
-		if(b.idx && !(rem & 2u)){ const double vb = fastVal(Ph, b.idx, ex, pl, b.rho); Ph[b.idx] = vb; if(send) fastSend<X>(mail, xBase, b, vb, stag); }
-		if(rem & 8u){
-			if(recv && pAddr && (rem & 4u)) Ph[pIdx] = llWaitSys(pAddr, tagIn);
-			__syncthreads();
-			if(a.idx && (rem & 1u)){ const double va = fastVal(Ph, a.idx, ex, pl, a.rho); Ph[a.idx] = va; if(send) fastSend<X>(mail, xBase, a, va, stag); }
-			if(b.idx && (rem & 2u)){ const double vb = fastVal(Ph, b.idx, ex, pl, b.rho); Ph[b.idx] = vb; if(send) fastSend<X>(mail, xBase, b, vb, stag); }
-		}
-		return;
-	}
-	if(recv && pAddr) Ph[pIdx] = llWait(pAddr, tagIn);
+		const FastNode &a, const FastNode &b, unsigned stag, bool send){
+	if(recv && pAddr) Ph[pIdx] = X ? llWaitSys(pAddr, tagIn) : llWait(pAddr, tagIn);
 	__syncthreads();
 	double va = 0, vb = 0;
 	if(a.idx) va = fastVal(Ph, a.idx, ex, pl, a.rho);
@@ -902,9 +884,8 @@ template<bool X> __device__ __forceinline__ void fastHalf(double *Ph, int ex, in
 // colour 1 (h even) or 0 (h odd) and first receives the other colour's face nodes of half-sweep h-1.
 // X: the halo loaded from this rank's memory is not the neighbour rank's data, so the call starts with an exchange of the
 // colour-0 boundary nodes (tag seq+1) and the half-sweeps use tags seq+2 .. (the caller advances seq by 2*nCycles + 2).
-// rem0 / rem1: fastHalf's `rem` for the colour-0 / colour-1 nodes and halo slot of this thread.
 template<bool X> __device__ __noinline__ void bSmoothFast(double *Ph, int ex, int pl, uint4 *mail, uint4 *const *xBase, const uint4 *p0Addr, int p0Idx, const uint4 *p1Addr, int p1Idx,
-		FastNode a0, FastNode b0, FastNode a1, FastNode b1, int nCycles, unsigned seq, long long *pf, long long tEnter, unsigned rem0, unsigned rem1){
+		FastNode a0, FastNode b0, FastNode a1, FastNode b1, int nCycles, unsigned seq, long long *pf, long long tEnter){
 	long long tW = 0;
 	if(pf){ pf[2*9] += clock64() - tEnter; pf[2*9+1] += 1; tW = clock64(); }
 	if constexpr(X){
@@ -914,9 +895,8 @@ template<bool X> __device__ __noinline__ void bSmoothFast(double *Ph, int ex, in
 	}
 	for(int h2 = 0; h2 < nCycles; h2++){
 		const unsigned t = seq + 2u*(unsigned)h2;
-		// (updating colour 1 receives the colour-0 halo slot and vice versa)
-		fastHalf<X>(Ph, ex, pl, mail, xBase, p0Addr, p0Idx, X || h2 > 0, t, a1, b1, t + 1u, true, (rem1 & 11u) | (rem0 & 4u));
-		fastHalf<X>(Ph, ex, pl, mail, xBase, p1Addr, p1Idx, true, t + 1u, a0, b0, t + 2u, h2 + 1 < nCycles, (rem0 & 11u) | (rem1 & 4u));
+		fastHalf<X>(Ph, ex, pl, mail, xBase, p0Addr, p0Idx, X || h2 > 0, t, a1, b1, t + 1u, true);
+		fastHalf<X>(Ph, ex, pl, mail, xBase, p1Addr, p1Idx, true, t + 1u, a0, b0, t + 2u, h2 + 1 < nCycles);
 	}
 	if(pf){ pf[2*10] += clock64() - tW; pf[2*10+1] += 2*nCycles; }
 }
@@ -1046,27 +1026,10 @@ template<bool X> __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, i
 			// rho and mailbox slots are worked out once per call and handed to a lean routine, so that a half-sweep is
 			// wait -> barrier -> 12 shared loads -> 14 additions -> stores
 			FastNode nd[2][2]; const uint4 *pAddr[2]; int pIdx[2];
-			unsigned remC[2] = {0u, 0u};
-			bool fr[6] = {false, false, false, false, false, false};          // X: face f's neighbour block belongs to another rank
-			if constexpr(X){
-				const XDist &x = *S.X;
-				const int cx = bid % B.nbx, cr = bid / B.nbx, cy = cr % B.nby, cz = cr / B.nby;
-				fr[0] = cx == 0 && x.ns[0] > 1; fr[1] = cx == B.nbx-1 && x.ns[0] > 1;
-				fr[2] = cy == 0 && x.ns[1] > 1; fr[3] = cy == B.nby-1 && x.ns[1] > 1;
-				fr[4] = cz == 0 && x.ns[2] > 1; fr[5] = cz == B.nbz-1 && x.ns[2] > 1;
-				if(fr[0] || fr[1] || fr[2] || fr[3] || fr[4] || fr[5]){ remC[0] |= 8u; remC[1] |= 8u; }
-			}
 			#pragma unroll
 			for(int c = 0; c < 2; c++){
 				pAddr[c] = nullptr; pIdx[c] = 0;
-				if((int)threadIdx.x < nHalo){
-					int slot; haloNode(threadIdx.x, c, slot, pIdx[c]); pAddr[c] = mine + slot;
-					if constexpr(X){
-						const int i = threadIdx.x;       // haloNode's face: x faces first (lower half, upper half), then y, then z
-						const int f = i < nA ? (i >= nA/2) : (i < nA + nB ? 2 + (i - nA >= nB/2) : 4 + (i - nA - nB >= nC/2));
-						if(fr[f]) remC[c] |= 4u;
-					}
-				}
+				if((int)threadIdx.x < nHalo){ int slot; haloNode(threadIdx.x, c, slot, pIdx[c]); pAddr[c] = mine + slot; }
 				#pragma unroll
 				for(int w = 0; w < 2; w++){
 					int iw = threadIdx.x + w*(int)blockDim.x;
@@ -1090,15 +1053,11 @@ template<bool X> __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, i
 						if(nt > 0) n.t0 = t[0];
 						if(nt > 1) n.t1 = t[1];
 						if(nt > 2) n.t2 = t[2];
-						if constexpr(X){
-							if((j == 1 && fr[0]) || (j == bx && fr[1]) || (k == 1 && fr[2]) || (k == by && fr[3]) || (l == 1 && fr[4]) || (l == bz && fr[5]))
-								remC[c] |= 1u << w;
-						}
 					}
 				}
 			}
 			bSmoothFast<X>(Ph, ex, pl, B.mail, xBase, pAddr[0], pIdx[0], pAddr[1], pIdx[1], nd[0][0], nd[0][1], nd[1][0], nd[1][1], nCycles, seq,
-				(S.K->prof && bid == 0 && threadIdx.x == 0) ? S.K->prof : nullptr, tEnter, remC[0], remC[1]);
+				(S.K->prof && bid == 0 && threadIdx.x == 0) ? S.K->prof : nullptr, tEnter);
 		} else {
 		const unsigned seqG = X ? seq + 1u : seq;
 		if constexpr(X){
