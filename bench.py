@@ -276,12 +276,15 @@ def run_ours(args, n_gpus, rank, world_size):
     barrier()
     t0 = time.perf_counter()
     L.pincSyncPopToDevice(st.pop)                               # H2D: 48 B per live particle
+    t_h2d = time.perf_counter() - t0
     for _ in range(e2e_steps):
         W.step(fused=False)
         for g in (st.rho, st.phi, st.E):                        # D2H of the step's field results
             L.pincSyncGridToHost(g)
         W.energies()
+    t1 = time.perf_counter()
     L.pincSyncPopToHost(st.pop)                                 # D2H: 48 B per live particle
+    t_d2h = time.perf_counter() - t1
     barrier()
     t_e2e = allmax(time.perf_counter() - t0)
     n_global_e2e = allsum(float(n_live))
@@ -289,6 +292,9 @@ def run_ours(args, n_gpus, rank, world_size):
            "h2d_bytes_per_step": int(48 * n_live / e2e_steps),
            "d2h_bytes_per_step": int(48 * n_live / e2e_steps + grid_bytes + 8 * (p.nSpecies + 2)),
            "ms_per_step": 1e3 * t_e2e / e2e_steps,
+           # the two population copies happen once per job, not once per step: their cost per call (rank 0) and what remains per step
+           "population_h2d_ms": 1e3 * t_h2d, "population_d2h_ms": 1e3 * t_d2h,
+           "ms_per_step_without_population_copies": 1e3 * (t_e2e - t_h2d - t_d2h) / e2e_steps,
            "path": "PINC entry points in reference order; population H2D at start and D2H at end inside the timed region (page-locked), fields+energies D2H every step"}
 
     # ---------------- device-resident throughput (fused particle pass) ------------------------------------------
