@@ -139,6 +139,15 @@ void puAcc3D1KE(Population *pop, Grid *E);                                      
 void puBoris3D1(Population *pop, Grid *E, const double *T, const double *S);    /* pusher.h:125 (pusher.c:394) */
 void puBoris3D1KE(Population *pop, Grid *E, const double *T, const double *S);  /* pusher.h:126 (pusher.c:433) */
 void puDistr3D1(const Population *pop, Grid *rho);                              /* pusher.h:163 (pusher.c:512) */
+/* the N-dimensional / zeroth-order select() targets of src/main.c:55-70, for nDims = 3: first order with the operation order of
+ * the reference's recursion (puInterpND1Inner, puDistrND1Inner), zeroth order = nearest grid point */
+void puAccND1(Population *pop, Grid *E);                                         /* pusher.h (pusher.c:269) */
+void puAccND1KE(Population *pop, Grid *E);                                       /* pusher.c:219 */
+void puAccND0(Population *pop, Grid *E);                                         /* pusher.c:357 */
+void puAccND0KE(Population *pop, Grid *E);                                       /* pusher.c:311 */
+void puDistrND1(const Population *pop, Grid *rho);                               /* pusher.c:578 */
+void puDistrND0(const Population *pop, Grid *rho);                               /* pusher.c:644 */
+void puExtractEmigrantsND(Population *pop, MpiInfo *mpiInfo);                    /* pusher.c:864 */
 void puExtractEmigrants3D(Population *pop, MpiInfo *mpiInfo);                   /* pusher.h:180 (pusher.c:782) */
 void puMigrate(Population *pop, MpiInfo *mpiInfo, Grid *grid);                  /* pusher.h:184 (pusher.c:1030) */
 int  puRankToNeighbor(MpiInfo *mpiInfo, int rank);                              /* pusher.h:186 (pusher.c:1214) */
@@ -165,6 +174,8 @@ funPtr puAcc3D1_set(dictionary *ini);                                           
 funPtr puAcc3D1KE_set(dictionary *ini);                                         /* pusher.h:120 (pusher.c:174) */
 funPtr puDistr3D1_set(dictionary *ini);                                         /* pusher.h:163 (pusher.c:508) */
 funPtr puExtractEmigrants3D_set(const dictionary *ini);                         /* pusher.h:180 (pusher.c:777) */
+funPtr puAccND1_set(dictionary *ini); funPtr puAccND1KE_set(dictionary *ini); funPtr puAccND0_set(dictionary *ini); funPtr puAccND0KE_set(dictionary *ini);
+funPtr puDistrND1_set(dictionary *ini); funPtr puDistrND0_set(dictionary *ini); funPtr puExtractEmigrantsND_set(const dictionary *ini);   /* pusher.c:215-391, 574-646, 860 */
 void puGet3DRotationParameters(dictionary *ini, double *T, double *S);          /* pusher.h:128 (pusher.c:485) */
 
 /* ---------------------------------------------------------------------------------

@@ -61,6 +61,8 @@ def load():
     lib.orc_boris3d1.argtypes = [c_double_p, c_double_p, C.c_int, c_long_p, c_long_p, c_double_p, c_double_p, c_double_p, c_int_p, c_double_p, c_double_p, c_double_p, C.c_int]
     lib.orc_rotation_parameters.argtypes = [C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]
     lib.orc_distr3d1.argtypes = [c_double_p, C.c_int, c_long_p, c_long_p, c_double_p, c_double_p, c_int_p]
+    lib.orc_acc_nd.argtypes = [c_double_p, c_double_p, C.c_int, c_long_p, c_long_p, c_double_p, c_double_p, c_double_p, c_int_p, C.c_int, c_double_p]
+    lib.orc_distr_nd.argtypes = [c_double_p, C.c_int, c_long_p, c_long_p, c_double_p, c_double_p, c_int_p, C.c_int]
     lib.orc_extract3d.argtypes = [c_double_p, c_double_p, C.c_int, c_long_p, c_long_p, c_double_p, PP, c_long_p]
     lib.orc_pnew.argtypes = [c_double_p, c_double_p, c_long_p, c_long_p, C.c_int, c_double_p, c_double_p]
     lib.orc_pnew.restype = C.c_int

@@ -141,6 +141,80 @@ void orc_distr3d1(const double *pos, int nSpecies, const long *iStart, const lon
 	}
 }
 
+/* The N-dimensional select() targets for nDims = 3 (src/pusher.c:215-391, 574-678, 1124-1180).  The reference recurses over the
+ * dimensions (puInterpND1Inner :1147, puDistrND1Inner :626): the factor handed down is (z weight)*1, then (y weight)*that, and
+ * the innermost level adds (x complement*factor)*value, then (x decimal*factor)*value, to the running result; corners are
+ * visited z-stay before z-incr, y-stay before y-incr.  Written here as loops over (dz, dy) with the same operation order.
+ * order 0 = nearest grid point, (int)(pos+0.5) (:1164, :644). */
+void orc_acc_nd(double *pos, double *vel, int nSpecies, const long *iStart, const long *iStop,
+                const double *charge, const double *mass, double *E, const int *size, int order, double *kinEnergy){
+	long sx = size[0], sy = size[1], n = 3L*size[0]*size[1]*size[2];
+	for(int s=0;s<nSpecies;s++){
+		orc_gmul(E,n,charge[s]/mass[s]);
+		double acc = 0;
+		for(long p=3*iStart[s]; p<3*iStop[s]; p+=3){
+			double dv[3] = {0,0,0};
+			if(order==0){
+				int j = (int)(pos[p]+0.5), k = (int)(pos[p+1]+0.5), l = (int)(pos[p+2]+0.5);
+				for(int d=0;d<3;d++) dv[d] = E[3*IDX(j,k,l,sx,sy)+d];
+			} else {
+				int j = (int)pos[p], k = (int)pos[p+1], l = (int)pos[p+2];
+				double dec[3] = {pos[p]-j, pos[p+1]-k, pos[p+2]-l};
+				double com[3] = {1-dec[0], 1-dec[1], 1-dec[2]};
+				for(int dz=0;dz<2;dz++){
+					double fz = (dz ? dec[2] : com[2])*1.0;
+					for(int dy=0;dy<2;dy++){
+						double f = (dy ? dec[1] : com[1])*fz;
+						long q = 3*IDX(j,k+dy,l+dz,sx,sy);
+						for(int d=0;d<3;d++){
+							dv[d] += com[0]*f*E[q+d];
+							dv[d] += dec[0]*f*E[q+d+3];
+						}
+					}
+				}
+			}
+			double v2 = 0;
+			for(int d=0;d<3;d++){
+				v2 += vel[p+d]*(vel[p+d]+dv[d]);
+				vel[p+d] += dv[d];
+			}
+			acc += v2;
+		}
+		if(kinEnergy){ kinEnergy[s] = acc; kinEnergy[s] *= 0.5*mass[s]; }
+		orc_gmul(E,n,mass[s]/charge[s]);
+	}
+}
+
+void orc_distr_nd(const double *pos, int nSpecies, const long *iStart, const long *iStop,
+                  const double *charge, double *rho, const int *size, int order){
+	long sx = size[0], sy = size[1], n = (long)size[0]*size[1]*size[2];
+	for(long g=0;g<n;g++) rho[g] = 0;
+	for(int s=0;s<nSpecies;s++){
+		orc_gmul(rho,n,1.0/charge[s]);
+		for(long i=iStart[s]; i<iStop[s]; i++){
+			const double *r = &pos[3*i];
+			if(order==0){
+				int j = (int)(r[0]+0.5), k = (int)(r[1]+0.5), l = (int)(r[2]+0.5);
+				rho[IDX(j,k,l,sx,sy)]++;
+				continue;
+			}
+			int j = (int)r[0], k = (int)r[1], l = (int)r[2];
+			double dec[3] = {r[0]-j, r[1]-k, r[2]-l};
+			double com[3] = {1-dec[0], 1-dec[1], 1-dec[2]};
+			for(int dz=0;dz<2;dz++){
+				double fz = (dz ? dec[2] : com[2])*1.0;
+				for(int dy=0;dy<2;dy++){
+					double f = (dy ? dec[1] : com[1])*fz;
+					long q = IDX(j,k+dy,l+dz,sx,sy);
+					rho[q]   += com[0]*f;
+					rho[q+1] += dec[0]*f;
+				}
+			}
+		}
+		orc_gmul(rho,n,charge[s]);
+	}
+}
+
 /* src/grid.c:1094-1099: upper thresholds are counted from the upper edge. */
 void orc_thresholds(const int *size, const double *thrIn, double *thrOut){
 	for(int d=0;d<3;d++){

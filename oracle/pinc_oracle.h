@@ -40,6 +40,11 @@ void orc_rotation_parameters(int nSpecies, const double *BExt, const double *cha
                              const double *mass, double *T, double *S);
 void orc_distr3d1(const double *pos, int nSpecies, const long *iStart, const long *iStop,
                   const double *charge, double *rho, const int *size);
+/* the N-dimensional / zeroth-order select() targets for nDims = 3 (src/pusher.c:215-391, 574-678); order = 1 or 0 */
+void orc_acc_nd(double *pos, double *vel, int nSpecies, const long *iStart, const long *iStop,
+                const double *charge, const double *mass, double *E, const int *size, int order, double *kinEnergy);
+void orc_distr_nd(const double *pos, int nSpecies, const long *iStart, const long *iStop,
+                  const double *charge, double *rho, const int *size, int order);
 void orc_extract3d(double *pos, double *vel, int nSpecies, const long *iStart, long *iStop,
                    const double *thresholds, double **emigrants /*27*/, long *nEmigrants /*27*nSpecies*/);
 int  orc_pnew(double *pos, double *vel, const long *iStart, long *iStop, int s, const double *p3, const double *v3);

@@ -50,6 +50,9 @@ def load():
     for f in ("puBoris3D1", "puBoris3D1KE"):
         getattr(lib, f).argtypes = [P(abi.Population), P(abi.Grid), abi.c_double_p, abi.c_double_p]
     lib.puDistr3D1.argtypes = [P(abi.Population), P(abi.Grid)]
+    for f in ("puAccND1", "puAccND1KE", "puAccND0", "puAccND0KE", "puDistrND1", "puDistrND0"):
+        getattr(lib, f).argtypes = [P(abi.Population), P(abi.Grid)]
+    lib.puExtractEmigrantsND.argtypes = [P(abi.Population), P(abi.MpiInfo)]
     lib.puExtractEmigrants3D.argtypes = [P(abi.Population), P(abi.MpiInfo)]
     lib.puMigrate.argtypes = [P(abi.Population), P(abi.MpiInfo), P(abi.Grid)]
     lib.puNeighborToRank.argtypes = [P(abi.MpiInfo), C.c_int]

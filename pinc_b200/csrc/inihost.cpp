@@ -54,6 +54,19 @@ funPtr puExtractEmigrants3D_set(const dictionary *ini){                         
 	if(iniGetInt(ini, "grid:nDims") != 3) fatal("puExtractEmigrants3D requires grid:nDims=3");
 	return (funPtr)puExtractEmigrants3D;
 }
+/* the N-dimensional and zeroth-order select() targets (pusher.c:215-391, 574-678, 857-862); nDims = 3 only */
+static funPtr selectorND(dictionary *ini, const char *name, int order, funPtr f){
+	needIni(name);
+	if(iniGetInt(ini, "grid:nDims") != 3) fatal("%s: libpinc_b200 is 3-D only (grid:nDims=%d)", name, iniGetInt(ini, "grid:nDims"));
+	return selector(ini, name, 0, order, f);
+}
+funPtr puAccND1_set(dictionary *ini){ return selectorND(ini, "puAccND1", 1, (funPtr)puAccND1); }
+funPtr puAccND1KE_set(dictionary *ini){ return selectorND(ini, "puAccND1KE", 1, (funPtr)puAccND1KE); }
+funPtr puAccND0_set(dictionary *ini){ return selectorND(ini, "puAccND0", 0, (funPtr)puAccND0KE); }       /* (the reference returns the KE form here, pusher.c:355) */
+funPtr puAccND0KE_set(dictionary *ini){ return selectorND(ini, "puAccND0KE", 0, (funPtr)puAccND0KE); }
+funPtr puDistrND1_set(dictionary *ini){ return selectorND(ini, "puDistrND1", 1, (funPtr)puDistrND1); }
+funPtr puDistrND0_set(dictionary *ini){ return selectorND(ini, "puDistrND0", 0, (funPtr)puDistrND0); }
+funPtr puExtractEmigrantsND_set(const dictionary *ini){ (void)ini; return (funPtr)puExtractEmigrantsND; }
 funPtr mgSolver_set(const dictionary *ini){ (void)ini; return (funPtr)mgSolver; }                                    /* multigrid.c:398 */
 
 /* multigrid.c:364-382 with mgAlloc's reads and checks (:297-349) and the method names of mgSetSolver,

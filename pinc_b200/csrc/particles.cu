@@ -711,6 +711,88 @@ __global__ void __launch_bounds__(256, 4) k_distr_slots(SlotPar Q, CellSpace C, 
 	}
 }
 
+// ---- the N-dimensional select() targets of the accelerator and the distributor, for nDims = 3 (src/pusher.c:215-391, 574-678):
+// puAccND1[KE] / puDistrND1 are first order like the 3D1 forms but evaluate the trilinear weights in the order of the
+// reference's recursion (puInterpND1Inner :1147, puDistrND1Inner :626: factor = (y weight)*(z weight), then (x weight*factor)*E,
+// corners visited x fastest, z slowest, each term added to the running sum); puAccND0[KE] / puDistrND0 are zeroth order
+// (nearest grid point, (int)(pos + 0.5), :1164, :644).  One thread per particle, per-particle integer REDs for the deposit:
+// these are the slow-path variants, the 3D1 forms are the ones the time loop is built around.
+template<int ORDER, int KE> __global__ void __launch_bounds__(256) k_acc_nd(double *__restrict__ P, long cap, long a, long n,
+		const double *__restrict__ E, long sx3, long sxy3, int gs0, int gs1, int gs2, double *__restrict__ partial, int *flags){
+	double acc = 0;
+	long stride = (long)gridDim.x*blockDim.x;
+	for(long i = blockIdx.x*(long)blockDim.x + threadIdx.x; i < n; i += stride){
+		const long q = a + i;
+		const double x = P[q], y = P[q+cap], z = P[q+2*cap];
+		double vx = P[q+3*cap], vy = P[q+4*cap], vz = P[q+5*cap];
+		double dv[3] = {0, 0, 0};
+		if(ORDER == 0){
+			int j = (int)(x+0.5), k = (int)(y+0.5), l = (int)(z+0.5);
+			if(!(x >= -0.5) || !(y >= -0.5) || !(z >= -0.5) || j > gs0-1 || k > gs1-1 || l > gs2-1){ atomicOr(flags, ERR_POS_RANGE); j = min(max(j,0),gs0-1); k = min(max(k,0),gs1-1); l = min(max(l,0),gs2-1); }
+			const double *e = E + 3L*j + k*sx3 + l*sxy3;
+			dv[0] = __ldg(e); dv[1] = __ldg(e+1); dv[2] = __ldg(e+2);
+		} else {
+			int j = (int)x, k = (int)y, l = (int)z;
+			if(!(x >= 0) || !(y >= 0) || !(z >= 0) || j > gs0-2 || k > gs1-2 || l > gs2-2){ atomicOr(flags, ERR_POS_RANGE); j = min(max(j,0),gs0-2); k = min(max(k,0),gs1-2); l = min(max(l,0),gs2-2); }
+			const double xf = x-j, yf = y-k, zf = z-l, xc = 1-xf, yc = 1-yf, zc = 1-zf;
+			const double *e = E + 3L*j + k*sx3 + l*sxy3;
+			#pragma unroll
+			for(int dz = 0; dz < 2; dz++){
+				const double fz = (dz ? zf : zc)*1.0;
+				#pragma unroll
+				for(int dy = 0; dy < 2; dy++){
+					const double f = (dy ? yf : yc)*fz;
+					const double *ep = e + dy*sx3 + dz*sxy3;
+					#pragma unroll
+					for(int d = 0; d < 3; d++){
+						dv[d] += xc*f*__ldg(ep+d);
+						dv[d] += xf*f*__ldg(ep+3+d);
+					}
+				}
+			}
+		}
+		if(KE){
+			double v2 = 0;
+			v2 += vx*(vx+dv[0]); v2 += vy*(vy+dv[1]); v2 += vz*(vz+dv[2]);
+			acc += v2;
+		}
+		vx += dv[0]; vy += dv[1]; vz += dv[2];
+		P[q+3*cap] = vx; P[q+4*cap] = vy; P[q+5*cap] = vz;
+	}
+	if(KE){
+		acc = blockSumP<256>(acc);
+		if(threadIdx.x == 0) partial[blockIdx.x] = acc;
+	}
+}
+template<int ORDER> __global__ void __launch_bounds__(256) k_distr_nd(const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ Z,
+		long n, int s0, int s1, int s2, long long *__restrict__ fix, int *flags){
+	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
+	const long sx = s0, sxy = (long)s0*s1;
+	for(; i < n; i += st){
+		const double x = X[i], y = Y[i], z = Z[i];
+		if(ORDER == 0){
+			int j = (int)(x+0.5), k = (int)(y+0.5), l = (int)(z+0.5);
+			if(!(x >= -0.5) || !(y >= -0.5) || !(z >= -0.5) || j > s0-1 || k > s1-1 || l > s2-1){ atomicOr(flags, ERR_POS_RANGE); continue; }
+			atomicAdd((unsigned long long*)fix + (j + sx*k + sxy*l), (unsigned long long)fixw(1.0));
+		} else {
+			int j = (int)x, k = (int)y, l = (int)z;
+			if(!(x >= 0) || !(y >= 0) || !(z >= 0) || j > s0-2 || k > s1-2 || l > s2-2){ atomicOr(flags, ERR_POS_RANGE); continue; }
+			const double xf = x-j, yf = y-k, zf = z-l, xc = 1-xf, yc = 1-yf, zc = 1-zf;
+			unsigned long long *f = (unsigned long long*)fix + (j + sx*k + sxy*l);
+			#pragma unroll
+			for(int dz = 0; dz < 2; dz++){
+				const double fz = (dz ? zf : zc)*1.0;
+				#pragma unroll
+				for(int dy = 0; dy < 2; dy++){
+					const double fy = (dy ? yf : yc)*fz;
+					atomicAdd(f + dy*sx + dz*sxy,     (unsigned long long)fixw(xc*fy));
+					atomicAdd(f + dy*sx + dz*sxy + 1, (unsigned long long)fixw(xf*fy));
+				}
+			}
+		}
+	}
+}
+
 // ---- debug scans of the driver loop (src/population.c:316-365) ------------------------------------------------
 // three planes starting at `P` are compared with lo <= v <= hi[d]; the first offender is recorded (species-local index,
 // dimension) by an atomicMin on index*4+dimension
@@ -1035,6 +1117,53 @@ static void accelerate(Ctx *c, Population *pop, Grid *Egrid, int kind, int ke, c
 	}
 }
 
+// puAccND1[KE], puAccND0[KE] (src/pusher.c:215-391) for nDims = 3
+static void accelerateND(Ctx *c, Population *pop, Grid *Egrid, int order, int ke){
+	DevPop *dp = devPop(c, pop);
+	DevGrid *E = devGrid(c, Egrid);
+	if(E->nv != 3) fatal("accelerator needs a 3-vector field grid");
+	const long sx3 = 3L*E->size[0], sxy3 = sx3*E->size[1];
+	int maxBlocks = 0;
+	for(int s = 0; s < dp->nS; s++){ int b = pGrid(c, pop->iStop[s]-pop->iStart[s]); if(b > maxBlocks) maxBlocks = b; }
+	double *partial = ke ? partialBuffer(c, (long)maxBlocks*dp->nS) : nullptr;
+	for(int s = 0; s < dp->nS; s++){
+		long a = pop->iStart[s], n = pop->iStop[s] - a;
+		gridScale(c, E, pop->charge[s]/pop->mass[s]);
+		int blocks = pGrid(c, n);
+		double *part = ke ? partial + (long)s*maxBlocks : nullptr;
+		if(n > 0){
+#define ND_LAUNCH(O,K) PINC_LAUNCH(c, K_PUSH, 72.0*n, (k_acc_nd<O,K><<<blocks,256,0,c->stream>>>(dp->base, dp->cap, a, n, E->d, sx3, sxy3, E->size[0], E->size[1], E->size[2], part, c->d_flags)))
+			if(order == 1){ if(ke) ND_LAUNCH(1,1); else ND_LAUNCH(1,0); } else { if(ke) ND_LAUNCH(0,1); else ND_LAUNCH(0,0); }
+#undef ND_LAUNCH
+		}
+		if(ke) PINC_LAUNCH(c, K_REDUCE, 8.0*blocks, (k_final_sum_p<<<1,256,0,c->stream>>>(part, n > 0 ? blocks : 0, c->d_scal + 16 + s)));
+		gridScale(c, E, pop->mass[s]/pop->charge[s]);
+	}
+	if(ke){
+		PINC_CUDA(cudaMemcpyAsync(c->h_scal + 16, c->d_scal + 16, dp->nS*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		streamSync(c);
+		for(int s = 0; s < dp->nS; s++){ pop->kinEnergy[s] = c->h_scal[16+s]; pop->kinEnergy[s] *= 0.5*pop->mass[s]; }
+	}
+	checkDeviceFlags(c, "puAccND");
+}
+// puDistrND1, puDistrND0 (src/pusher.c:578-678) for nDims = 3
+static void distributeND(Ctx *c, const Population *pop, Grid *rhoGrid, int order){
+	DevPop *dp = devPop(c, pop); DevGrid *rho = devGrid(c, rhoGrid);
+	if(rho->nv != 1) fatal("puDistrND needs a scalar grid");
+	dropPredeposit(dp);
+	ensureFix(c, rho, dp->nS);
+	gridZero(c, rho);
+	for(int s = 0; s < dp->nS; s++){
+		long a = pop->iStart[s], n = pop->iStop[s] - a;
+		const double *X = dp->base + a, *Y = X + dp->cap, *Z = Y + dp->cap;
+		if(n > 0){
+			if(order == 1) PINC_LAUNCH(c, K_DEPOSIT, 24.0*n, (k_distr_nd<1><<<pGrid(c,n),256,0,c->stream>>>(X, Y, Z, n, rho->size[0], rho->size[1], rho->size[2], rho->d_fixS[s], c->d_flags)));
+			else PINC_LAUNCH(c, K_DEPOSIT, 24.0*n, (k_distr_nd<0><<<pGrid(c,n),256,0,c->stream>>>(X, Y, Z, n, rho->size[0], rho->size[1], rho->size[2], rho->d_fixS[s], c->d_flags)));
+		}
+		PINC_LAUNCH(c, K_DEPOSIT, 32.0*rho->n, (k_distr_finalize<<<gridFor(rho->n,256,c->numSMs*8),256,0,c->stream>>>(rho->d, rho->d_fixS[s], rho->n, 1.0/pop->charge[s], pop->charge[s], c->d_flags)));
+	}
+}
+
 static void scanHist(Ctx *c, unsigned *h, long n /* entries incl. the total slot */){
 	int nb = (int)((n + SCAN_CH - 1)/SCAN_CH);
 	unsigned *sums = (unsigned*)tmpBuffer(c, (size_t)nb*sizeof(unsigned));
@@ -1065,6 +1194,12 @@ void puMove(Population *pop, Object *obj){
 	invalidateOrder(dp);
 }
 
+void puAccND1(Population *pop, Grid *E){ accelerateND(cur(), pop, E, 1, 0); }            /* pusher.c:269 */
+void puAccND1KE(Population *pop, Grid *E){ accelerateND(cur(), pop, E, 1, 1); }          /* pusher.c:219 */
+void puAccND0(Population *pop, Grid *E){ accelerateND(cur(), pop, E, 0, 0); }            /* pusher.c:357 */
+void puAccND0KE(Population *pop, Grid *E){ accelerateND(cur(), pop, E, 0, 1); }          /* pusher.c:311 */
+void puDistrND1(const Population *pop, Grid *rho){ distributeND(cur(), pop, rho, 1); }   /* pusher.c:578 */
+void puDistrND0(const Population *pop, Grid *rho){ distributeND(cur(), pop, rho, 0); }   /* pusher.c:644 */
 void puAcc3D1(Population *pop, Grid *E){ accelerate(cur(), pop, E, ACC_LEAP, 0, nullptr, nullptr, nullptr); }
 void puAcc3D1KE(Population *pop, Grid *E){ accelerate(cur(), pop, E, ACC_LEAP, 1, nullptr, nullptr, nullptr); }
 // Quirk Q3: the reference rotates particle 0's velocity for every particle; this implements the Boris
@@ -1085,6 +1220,10 @@ void pincGet3DRotationParameters(int nSpecies, const double *BExt, const double 
 	}
 }
 
+void puExtractEmigrants3D(Population *pop, MpiInfo *mpiInfo);
+// src/pusher.c:864-910: the N-dimensional form classifies by the same thresholds into the same 27 neighbours (only the order
+// in which the reference back-fills the holes differs, and that order is not reproduced by either)
+void puExtractEmigrantsND(Population *pop, MpiInfo *mpiInfo){ puExtractEmigrants3D(pop, mpiInfo); }
 // src/pusher.c:782-855 as a counting sort (see the header comment)
 void puExtractEmigrants3D(Population *pop, MpiInfo *mpiInfo){
 	Ctx *c = cur(); DevPop *dp = devPopRaw(c, pop);

@@ -84,6 +84,13 @@ SIGNATURES = {
     "pincMgSetMode": (None, [C.c_int]),
     "pincMgSetReplica": (None, [C.c_int]),
     "pincMgSetRowMode": (None, [C.c_int]),
+    "puAccND1": (None, [P(abi.Population), P(abi.Grid)]),
+    "puAccND1KE": (None, [P(abi.Population), P(abi.Grid)]),
+    "puAccND0": (None, [P(abi.Population), P(abi.Grid)]),
+    "puAccND0KE": (None, [P(abi.Population), P(abi.Grid)]),
+    "puDistrND1": (None, [P(abi.Population), P(abi.Grid)]),
+    "puDistrND0": (None, [P(abi.Population), P(abi.Grid)]),
+    "puExtractEmigrantsND": (None, [P(abi.Population), P(abi.MpiInfo)]),
     "pincSetSlotted": (None, [C.c_int, C.c_int, C.c_int]),
     "pincPopLayout": (C.c_int, [P(abi.Population)]),
     "pincSlottedOverflows": (C.c_long, []),
@@ -94,6 +101,13 @@ SIGNATURES = {
     "puAcc3D1_set": (C.c_void_p, [C.c_void_p]),
     "puAcc3D1KE_set": (C.c_void_p, [C.c_void_p]),
     "puDistr3D1_set": (C.c_void_p, [C.c_void_p]),
+    "puAccND1_set": (C.c_void_p, [C.c_void_p]),
+    "puAccND1KE_set": (C.c_void_p, [C.c_void_p]),
+    "puAccND0_set": (C.c_void_p, [C.c_void_p]),
+    "puAccND0KE_set": (C.c_void_p, [C.c_void_p]),
+    "puDistrND1_set": (C.c_void_p, [C.c_void_p]),
+    "puDistrND0_set": (C.c_void_p, [C.c_void_p]),
+    "puExtractEmigrantsND_set": (C.c_void_p, [C.c_void_p]),
     "puExtractEmigrants3D_set": (C.c_void_p, [C.c_void_p]),
     "puGet3DRotationParameters": (None, [C.c_void_p, abi.c_double_p, abi.c_double_p]),
     "mgSolver_set": (C.c_void_p, [C.c_void_p]),

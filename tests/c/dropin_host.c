@@ -31,9 +31,9 @@ int main(int argc, char *argv[]){
 	dictionary *ini = iniOpen(argc, argv);                       /* src/main.c:31, src/io.c */
 
 	/* src/main.c:55-80: method selection through the reference's select() (src/io.c:115-168) */
-	void (*acc)() = select(ini, "methods:acc", puAcc3D1_set, puAcc3D1KE_set);
-	void (*distr)() = select(ini, "methods:distr", puDistr3D1_set);
-	void (*extractEmigrants)() = select(ini, "methods:migrate", puExtractEmigrants3D_set);
+	void (*acc)() = select(ini, "methods:acc", puAcc3D1_set, puAcc3D1KE_set, puAccND1_set, puAccND1KE_set, puAccND0_set, puAccND0KE_set);
+	void (*distr)() = select(ini, "methods:distr", puDistr3D1_set, puDistrND1_set, puDistrND0_set);
+	void (*extractEmigrants)() = select(ini, "methods:migrate", puExtractEmigrants3D_set, puExtractEmigrantsND_set);
 	void (*solverInterface)() = select(ini, "methods:poisson", mgSolver_set);
 	void (*solve)() = NULL;
 	void *(*solverAlloc)() = NULL;

@@ -33,6 +33,10 @@ int main(int argc, char **argv){
 	/* main.c:55-61: the selectors return the compute functions */
 	if(puAcc3D1_set(&ini) != (funPtr)puAcc3D1 || puAcc3D1KE_set(&ini) != (funPtr)puAcc3D1KE) return 10;
 	if(puDistr3D1_set(&ini) != (funPtr)puDistr3D1 || puExtractEmigrants3D_set(&ini) != (funPtr)puExtractEmigrants3D) return 11;
+	/* main.c:58-70: the N-dimensional / zeroth-order targets (puAccND0_set hands out the KE form, as pusher.c:355 does) */
+	if(puAccND1_set(&ini) != (funPtr)puAccND1 || puAccND1KE_set(&ini) != (funPtr)puAccND1KE || puAccND0_set(&ini) != (funPtr)puAccND0KE
+	   || puAccND0KE_set(&ini) != (funPtr)puAccND0KE || puDistrND1_set(&ini) != (funPtr)puDistrND1 || puDistrND0_set(&ini) != (funPtr)puDistrND0
+	   || puExtractEmigrantsND_set(&ini) != (funPtr)puExtractEmigrantsND) return 15;
 	/* main.c:63-70: solver interface */
 	void (*solverInterface)() = mgSolver_set(&ini);
 	void (*solve)() = NULL; MultigridSolver *(*solverAlloc)() = NULL; void (*solverFree)() = NULL;

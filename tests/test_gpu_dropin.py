@@ -37,6 +37,10 @@ def run(exe, ini, over):
                   "population:nAlloc=16 pc", "population:perturbAmplitude=2e-3,0,0,0,0,0", "grid:nEmigrantsAlloc=4 pc", "time:nTimeSteps=10"]),
     ("cold.ini", ["grid:nSubdomains=1,1,1", "grid:trueSize=16,8,8", "multigrid:mgLevels=3", "population:nParticles=27 pc",
                   "population:nAlloc=32 pc", "population:perturbAmplitude=5e-3,0,0,0,0,0", "grid:nEmigrantsAlloc=4 pc", "time:nTimeSteps=12"]),
+    # the N-dimensional select() targets (src/main.c:58-70) through the reference's select()
+    ("cold.ini", ["grid:nSubdomains=1,1,1", "grid:trueSize=16,8,8", "multigrid:mgLevels=3", "population:nParticles=27 pc",
+                  "population:nAlloc=32 pc", "population:perturbAmplitude=5e-3,0,0,0,0,0", "grid:nEmigrantsAlloc=4 pc", "time:nTimeSteps=10",
+                  "methods:acc=puAccND1KE", "methods:distr=puDistrND1", "methods:migrate=puExtractEmigrantsND"]),
 ])
 def test_reference_host_runs_on_the_library(ini, over):
     if not (os.path.exists(GPU) and os.path.exists(CPU)):

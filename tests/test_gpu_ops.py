@@ -314,6 +314,75 @@ def test_acc3d1_matches_oracle(gpu_lib, ke):
     L.pincPopFree(p)
 
 
+@pytest.mark.parametrize("order,ke", [(1, 1), (1, 0), (0, 1), (0, 0)])
+def test_acc_nd_matches_oracle(gpu_lib, order, ke):
+    """puAccND1[KE] / puAccND0[KE] (src/pusher.c:215-391) for nDims = 3: per-particle arithmetic in the order of the reference's
+    recursion -> bit-exact velocities; the oracle itself is pinned live to the reference (test_live_nd_select_targets_bitwise)."""
+    L, O = gpu_lib, orc.load()
+    E = rand_grid(L, TRUE, 3, seed=40 + order)
+    p = _pop(L, [0, 0], 5000)
+    _fill(p, TRUE, 41 + 2 * order + ke, lo=0.1 if order else 0.6, hi_off=1.1 if order else 1.6)
+    pos, vel, iStart, iStop, charge, mass = _orc_pop(p)
+    Er = E.flat().copy()
+    kin = np.zeros(3)
+    O.orc_acc_nd(orc.dp(pos), orc.dp(vel), 2, orc.lp(iStart), orc.lp(iStop), orc.dp(charge), orc.dp(mass), orc.dp(Er),
+                 orc.ip(E.size), order, orc.dp(kin) if ke else None)
+    E.up()
+    L.pincSyncPopToDevice(p)
+    getattr(L, "puAccND%d%s" % (order, "KE" if ke else ""))(p, E.ptr)
+    L.pincSyncPopToHost(p)
+    gpos, gvel = abi.pop_arrays(p.contents)
+    assert np.array_equal(gvel.reshape(-1), vel)
+    assert np.array_equal(gpos.reshape(-1), pos)
+    assert np.array_equal(E.down().reshape(-1), Er)
+    if ke:
+        for s in range(2):
+            assert abs(p.contents.kinEnergy[s] - kin[s]) <= 1e-13 * abs(kin[s])
+    L.pincPopFree(p)
+
+
+@pytest.mark.parametrize("order", [1, 0])
+def test_distr_nd_matches_oracle(gpu_lib, order):
+    """puDistrND1 / puDistrND0 (src/pusher.c:578-678): first order within the fixed-point quantum of the 3D1 form's test,
+    zeroth order = integer counts per node (the reference adds them one by one, so with a charge whose reciprocal is not
+    exact its sum rounds at every particle; unit charges keep every intermediate an integer and the comparison exact)."""
+    L, O = gpu_lib, orc.load()
+    rho = GridH(L, TRUE, 1)
+    p = _pop(L, [0, 0], 60000, charge=(-1.0, 3.0) if order else (-1.0, 1.0))
+    _fill(p, TRUE, 45 + order, lo=0.1 if order else 0.6, hi_off=1.1 if order else 1.6)
+    pos, vel, iStart, iStop, charge, mass = _orc_pop(p)
+    rr = rho.flat().copy()
+    O.orc_distr_nd(orc.dp(pos), 2, orc.lp(iStart), orc.lp(iStop), orc.dp(charge), orc.dp(rr), orc.ip(rho.size), order)
+    rho.up()
+    L.pincSyncPopToDevice(p)
+    outs = []
+    for rep in range(2):
+        getattr(L, "puDistrND%d" % order)(p, rho.ptr)
+        outs.append(rho.down().reshape(-1).copy())
+    assert np.array_equal(outs[0], outs[1])
+    assert np.abs(outs[0] - rr).max() <= 1e-12 * np.abs(rr).max()
+    if order == 0:
+        assert np.array_equal(outs[0], rr)        # integer counts: nothing to round
+    L.pincPopFree(p)
+
+
+def test_extract_nd_is_extract_3d(gpu_lib):
+    """puExtractEmigrantsND (src/pusher.c:864-910) classifies into the same 27 neighbours with the same comparisons."""
+    L, O = gpu_lib, orc.load()
+    rho = GridH(L, TRUE, 1)
+    tabs = []
+    for fn in ("puExtractEmigrants3D", "puExtractEmigrantsND"):
+        p = _pop(L, [0, 0], 6000)
+        _fill(p, TRUE, 49)
+        L.pincSyncPopToDevice(p)
+        m = single_mpi(L, TRUE)
+        L.pincCreateNeighborhood(m, rho.ptr, la([100000]), 1, da([0.4] * 6))
+        getattr(L, fn)(p, m)
+        tabs.append(([m.contents.nEmigrants[i] for i in range(54)], [p.contents.iStop[s] for s in range(2)]))
+        L.pincPopFree(p)
+    assert tabs[0] == tabs[1] and sum(tabs[0][0]) > 100
+
+
 def test_boris_matches_textbook_oracle(gpu_lib):
     L, O = gpu_lib, orc.load()
     E = rand_grid(L, TRUE, 3, seed=32)
