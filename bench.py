@@ -8,8 +8,9 @@ Workload at N=1: BASELINE.json configs[1] — warm Maxwellian electron-ion plasm
 sub-domain (weak scaling): nSubdomains = 1,1,2 / 1,2,2 / 2,2,2, one process per GPU (torchrun), halos and
 migrants over NCCL.  A step = one pass of src/main.c:197-274 (canonical order) over all particles.
 
-value   device-resident throughput: fused particle pass (pincAccMove3D1KE) + persistent multigrid kernel,
-        CUDA-event timed on the library's stream, max over ranks.
+value   device-resident throughput: fused particle pass (pincAccMoveDistr3D1KE: kick, move, re-binning and the deposition of
+        the particles that keep their cell in one pass over the cell slots) + persistent multigrid kernel, CUDA-event timed
+        on the library's stream, max over ranks.
 e2e     the same K steps as a JOB that starts and ends in HOST buffers, through the PINC-named entry points in
         the reference's call order (puMove, puExtractEmigrants3D, puMigrate, puDistr3D1, gHaloOp, mgSolve,
         gFinDiff1st, puAcc3D1KE, ...): the population is copied host->device from page-locked memory at the
@@ -54,43 +55,77 @@ def load_cfg(workload, n_gpus, particles_scale=1.0):
 
 
 class ClockSampler:
+    """nvidia-smi polled every 100 ms in the background.  It is started ahead of the warm-up steps (its own start-up takes longer
+    than a short timed region) and every line is time-stamped as it arrives; the summary uses the samples that fall between
+    mark_start() and mark_stop(), i.e. inside the timed region, and says so when it had to widen to the warm-up steps."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.device = device
         self.p = None
+        self.rows = []
+        self.t0 = self.t1 = None
+        self.thread = None
+
+    def _pump(self):
+        for line in self.p.stdout:
+            self.rows.append((time.perf_counter(), line))
 
     def start(self):
+        import threading
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
         except Exception:
             self.p = None
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_stop(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.t1 is None:
+            self.mark_stop()
+        if self.t0 is None:
+            self.t0 = float("-inf")
         self.p.terminate()
         try:
-            out, _ = self.p.communicate(timeout=5)
+            self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
-            out = ""
-        sm, mx, reasons = [], [], set()
-        for line in out.splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+        if self.thread is not None:
+            self.thread.join(timeout=5)
+
+        def digest(rows):
+            sm, mx, reasons = [], [], set()
+            for _, line in rows:
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+        inside = [r for r in self.rows if self.t0 <= r[0] <= self.t1 + 0.1]
+        sm, mx, reasons = digest(inside)
+        window = "timed region"
+        if not sm:
+            # a timed region shorter than one polling period: the samples of the warm-up steps right before it (same load)
+            sm, mx, reasons = digest([r for r in self.rows if r[0] <= self.t1 + 0.1][-5:])
+            window = "warm-up steps + timed region (the timed region is shorter than one 100 ms polling period)"
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def host_cores():
@@ -157,12 +192,14 @@ def run_mg_error_scaling(args, n_gpus):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     L = plib.load()
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
     for _ in range(max(1, args.warmup // 2)):
         mg_bench.run_case(L, 64, "sin", 2, reps=1)
-    sampler.start()
+    sampler.mark_start()
     launches0 = L.pincLaunchCount()
     recs, orders = mg_bench.error_scaling(L, (16, 32, 64, 128))
     launches = L.pincLaunchCount() - launches0
+    sampler.mark_stop()
     clocks = sampler.stop()
     big = recs[-2]                       # 64^3: the grid of BASELINE configs[1]
     n_fine = 64 ** 3
@@ -298,18 +335,20 @@ def run_ours(args, n_gpus, rank, world_size):
            "path": "PINC entry points in reference order; population H2D at start and D2H at end inside the timed region (page-locked), fields+energies D2H every step"}
 
     # ---------------- device-resident throughput (fused particle pass) ------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()                      # ahead of the warm-up: nvidia-smi's own start-up is longer than a short timed region
     for _ in range(args.warmup):
         W.step(fused=FUSED)
-    sampler = ClockSampler(local_rank)
     barrier()
     launches0 = L.pincLaunchCount()
-    sampler.start()
+    sampler.mark_start()
     L.pincTimerStart()
     cycles = []
     for _ in range(args.steps):
         W.step(fused=FUSED)
     ms = L.pincTimerStopMs()
     barrier()
+    sampler.mark_stop()
     clocks = sampler.stop()
     launches = L.pincLaunchCount() - launches0
     ms = allmax(ms)
@@ -390,6 +429,7 @@ def run_ours(args, n_gpus, rank, world_size):
                        "global_particles": int(n_global), "mgLevels": cfg.mgLevels, "parallelism": f"domain-decomposition x{world_size}",
                        "l2": "particle arrays (48 B x particles per GPU) exceed the 126 MB L2; no explicit flush",
                        "vcycles_last_solve": len(hist), "ic_seconds": t_ic,
+                       "particle_pass": "pincAccMoveDistr3D1KE (kick + move + re-binning + deposition of the stayers)" if FUSED is True else "pincAccMove3D1KE + puDistr3D1",
                        "mg_path": {0: "distributed, one kernel per reference call", 1: "all-SM persistent kernel", 2: "cluster kernel",
                                    5: "replicated: global problem on every rank, all-SM persistent kernel",
                                    6: "replicated: global problem on every rank, cluster kernel",
@@ -415,9 +455,10 @@ def main():
     ap.add_argument("--cpu-sample", type=float, default=1.0, help="fraction of the 70 particles/cell used by the CPU arms")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the NCCL path that N > 1 runs ahead of the timed region")
-    ap.add_argument("--particle-pass", default="nodeposit", choices=["full", "nodeposit"],
-                    help="nodeposit (default, measured faster): acc+move+classify in one pass, deposit as its own kernel; "
-                         "full: the deposit of the staying particles joins the pass")
+    ap.add_argument("--particle-pass", default="full", choices=["full", "nodeposit"],
+                    help="full (default, measured faster: 1.35 against 1.47 ms per step at 36.7 M particles): kick + move + re-binning + the "
+                         "deposition of the particles that keep their cell in one pass (pincAccMoveDistr3D1KE); nodeposit: the deposition is "
+                         "puDistr3D1's own pass over the slots (pincAccMove3D1KE)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

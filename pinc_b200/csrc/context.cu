@@ -2,6 +2,9 @@
 #include "common.h"
 #include <cstdarg>
 #include <mutex>
+#include <execinfo.h>
+#include <csignal>
+#include <unistd.h>
 
 namespace pinc {
 
@@ -378,3 +381,17 @@ int pincLastError(char *buf, int len){
 }
 
 } // extern "C"
+
+// $PINC_B200_SEGV_TRACE=1: a native back trace on SIGSEGV/SIGABRT (debugging aid for hosts that only report "Segmentation fault")
+namespace {
+void segvTrace(int sig){
+	void *frames[64];
+	int n = backtrace(frames, 64);
+	const char msg[] = "PINC-B200: fatal signal, native back trace:\n";
+	if(write(2, msg, sizeof msg - 1) < 0){}
+	backtrace_symbols_fd(frames, n, 2);
+	signal(sig, SIG_DFL);
+	raise(sig);
+}
+struct SegvInstall { SegvInstall(){ const char *e = getenv("PINC_B200_SEGV_TRACE"); if(e && atoi(e)){ signal(SIGSEGV, segvTrace); signal(SIGABRT, segvTrace); } } } g_segvInstall;
+}

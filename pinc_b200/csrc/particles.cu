@@ -21,6 +21,7 @@
 // compiled with -fmad=false (the reference's x86 build has no FMA contraction).
 #include "common.h"
 #include <atomic>
+#include <mutex>
 
 namespace pinc {
 
@@ -56,6 +57,9 @@ __device__ __forceinline__ long long fixw(double w){
 	const double M = 6755399441055744.0;               // 1.5 * 2^52
 	return __double_as_longlong(__fma_rn(w, (double)(1LL<<PINC_FIX_BITS), M)) - __double_as_longlong(M);
 }
+// fixw without the subtraction: a sum of n of these is the sum of the n integers plus n*FIXW_BIAS (modulo 2^64)
+__device__ __forceinline__ long long fixwRaw(double w){ return __double_as_longlong(__fma_rn(w, (double)(1LL<<PINC_FIX_BITS), 6755399441055744.0)); }
+#define FIXW_BIAS 0x4338000000000000ULL            // bits of 1.5*2^52
 // the eight trilinear weights of a particle at fractional position (xf,yf,zf), products in the reference's order
 // (src/pusher.c:556-563), index = dx + 2*dy + 4*dz
 __device__ __forceinline__ void cornerWeights(double xf, double yf, double zf, long long a[8]){
@@ -340,13 +344,17 @@ __global__ void __launch_bounds__(256, 4) k_distr_cells(const double *__restrict
 			#pragma unroll
 			for(int u = 0; u < 3; u++){
 				if(i0 + lane + 32*u >= e) continue;
-				long long w[8];
-				cornerWeights(x[u]-dj, y[u]-dk, z[u]-dl, w);
-				#pragma unroll
-				for(int q = 0; q < 8; q++) a[q] += w[q];
+				// raw bits of fma(w, 2^46, 1.5*2^52): the bias comes off the warp total (e x bits(1.5*2^52), modulo 2^64), which
+				// saves the 64-bit subtraction per weight in a kernel that is bound by instruction issue
+				const double xf = x[u]-dj, yf = y[u]-dk, zf = z[u]-dl;
+				const double xc = 1-xf, yc = 1-yf, zc = 1-zf;
+				const double cc = xc*yc, fc = xf*yc, cf = xc*yf, ff = xf*yf;
+				a[0] += fixwRaw(cc*zc); a[1] += fixwRaw(fc*zc); a[2] += fixwRaw(cf*zc); a[3] += fixwRaw(ff*zc);
+				a[4] += fixwRaw(cc*zf); a[5] += fixwRaw(fc*zf); a[6] += fixwRaw(cf*zf); a[7] += fixwRaw(ff*zf);
 			}
 		}
 		long long tot = warpCornerTotal(a);
+		tot -= (long long)((unsigned long long)(e - b)*FIXW_BIAS);
 		if((lane & 3) == 0 && tot != 0)
 			atomicAdd((unsigned long long*)&fix[cj + sx*ck + sxy*cl + cornerOffset(sx, sxy)], (unsigned long long)tot);
 	}
@@ -441,8 +449,9 @@ struct SlotPar { double *S; long plane; long off; int cap; unsigned *cnt; };
 
 // MODE 0: pincAccMove3D1KE (kick + move + re-binning); 1: puAcc3D1(KE) alone (velocities in place, nothing moves);
 // 2: puMove alone (pos += vel, re-binning).  1 followed by 2 is the reference's call order and leaves the same bits as 0.
-template<int KE, int MODE> __global__ void __launch_bounds__(256, 2) k_cell_push(SlotPar Q, const double *__restrict__ E, long sx3, long sxy3,
-		CellSpace C, Thr T, double *__restrict__ partial, double *__restrict__ M, long mPlane, unsigned *__restrict__ mKey, unsigned *mCount, unsigned mCap, int *flags){
+template<int KE, int MODE, int DEP> __global__ void __launch_bounds__(256, 2) k_cell_push(SlotPar Q, const double *__restrict__ E, long sx3, long sxy3,
+		CellSpace C, Thr T, double *__restrict__ partial, double *__restrict__ M, long mPlane, unsigned *__restrict__ mKey, unsigned *mCount, unsigned mCap, int *flags,
+		long long *__restrict__ fix, long sx, long sxy){
 	const int lane = threadIdx.x & 31;
 	const unsigned lt = (1u << lane) - 1u;
 	long warp = (blockIdx.x*(long)blockDim.x + threadIdx.x) >> 5;
@@ -460,6 +469,11 @@ template<int KE, int MODE> __global__ void __launch_bounds__(256, 2) k_cell_push
 		const double *e0 = E + 3L*cj + ck*sx3 + cl*sxy3, *e1 = e0 + sx3, *e2 = e0 + sxy3, *e3 = e2 + sx3;
 		double *P = Q.S + Q.off + c*(long)Q.cap;
 		unsigned wr = 0;
+		long long a[8];
+		if(DEP){
+			#pragma unroll
+			for(int q = 0; q < 8; q++) a[q] = 0;
+		}
 		for(unsigned i0 = 0; i0 < n; i0 += 96){
 			// up to 96 particles per trip (nearly always the whole cell), every load in flight before the first use
 			double x[3], y[3], z[3], vx[3], vy[3], vz[3];
@@ -539,6 +553,14 @@ template<int KE, int MODE> __global__ void __launch_bounds__(256, 2) k_cell_push
 					const unsigned d = wr + __popc(ms[u] & lt);
 					P[d] = x[u]; P[d + Q.plane] = y[u]; P[d + 2*Q.plane] = z[u];
 					if(MODE == 0 || d != i0 + lane + 32*u){ P[d + 3*Q.plane] = vx[u]; P[d + 4*Q.plane] = vy[u]; P[d + 5*Q.plane] = vz[u]; }      // (puMove leaves velocities alone)
+					if(DEP){
+						// the next step's puDistr3D1 for the particles that keep their cell (see k_distr_cells for the raw-bits sum)
+						const double xf = x[u]-dj, yf = y[u]-dk, zf = z[u]-dl;
+						const double xc = 1-xf, yc = 1-yf, zc = 1-zf;
+						const double cc = xc*yc, fc = xf*yc, cf = xc*yf, ff = xf*yf;
+						a[0] += fixwRaw(cc*zc); a[1] += fixwRaw(fc*zc); a[2] += fixwRaw(cf*zc); a[3] += fixwRaw(ff*zc);
+						a[4] += fixwRaw(cc*zf); a[5] += fixwRaw(fc*zf); a[6] += fixwRaw(cf*zf); a[7] += fixwRaw(ff*zf);
+					}
 				} else if(ok){
 					const unsigned d = chBase + chUsed + __popc(mm[u] & lt);
 					M[d] = x[u]; M[d + mPlane] = y[u]; M[d + 2*mPlane] = z[u];
@@ -550,6 +572,12 @@ template<int KE, int MODE> __global__ void __launch_bounds__(256, 2) k_cell_push
 			}
 		}
 		if(MODE != 1 && lane == 0) Q.cnt[c] = wr;
+		if(DEP && wr){
+			long long tot = warpCornerTotal(a);
+			tot -= (long long)((unsigned long long)wr*FIXW_BIAS);
+			if((lane & 3) == 0 && tot != 0)
+				atomicAdd((unsigned long long*)&fix[cj + sx*ck + sxy*cl + cornerOffset(sx, sxy)], (unsigned long long)tot);
+		}
 	}
 	for(unsigned k = chUsed + lane; k < MV_CHUNK; k += 32) mKey[chBase + k] = SLOT_EMPTY_KEY;       // the unused rest of the last chunk
 	if(KE){
@@ -557,14 +585,29 @@ template<int KE, int MODE> __global__ void __launch_bounds__(256, 2) k_cell_push
 		if(threadIdx.x == 0) partial[blockIdx.x] = acc;
 	}
 }
+// the eight weights of one particle straight into the accumulators (movers and immigrants: ~5 % of the population)
+__device__ __forceinline__ void depositOne(long long *__restrict__ fix, long sx, long sxy, double x, double y, double z, int j, int k, int l){
+	long long w[8];
+	cornerWeights(x - (double)j, y - (double)k, z - (double)l, w);
+	unsigned long long *f = (unsigned long long*)fix + (j + sx*k + sxy*l);
+	atomicAdd(f, (unsigned long long)w[0]); atomicAdd(f + 1, (unsigned long long)w[1]);
+	atomicAdd(f + sx, (unsigned long long)w[2]); atomicAdd(f + sx + 1, (unsigned long long)w[3]);
+	atomicAdd(f + sxy, (unsigned long long)w[4]); atomicAdd(f + sxy + 1, (unsigned long long)w[5]);
+	atomicAdd(f + sxy + sx, (unsigned long long)w[6]); atomicAdd(f + sxy + sx + 1, (unsigned long long)w[7]);
+}
 // movers of this rank into their new cells; emigrants are counted per neighbour (they stay in the list for puMigrate)
+// fix != nullptr (pincAccMoveDistr3D1KE): the movers that stay on this rank are deposited here, whether or not their cell has room
 __global__ void k_mv_insert(SlotPar Q, const double *__restrict__ M, long mPlane, unsigned *__restrict__ mKey, const unsigned *mCount,
-		CellSpace C, unsigned *__restrict__ emHist, int *flags){
+		CellSpace C, unsigned *__restrict__ emHist, int *flags, long long *__restrict__ fix, long sx, long sxy){
 	const long n = *mCount;
 	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
 	for(; i < n; i += st){
 		const unsigned key = mKey[i];
 		if(key >= (unsigned)C.nCells){ if(key < SLOT_OVER_KEY) atomicAdd(&emHist[key - (unsigned)C.nCells], 1u); continue; }
+		if(fix){
+			const int cj = (int)(key % (unsigned)C.nc0); const unsigned cr = key / (unsigned)C.nc0; const int ck = (int)(cr % (unsigned)C.nc1), cl = (int)(cr / (unsigned)C.nc1);
+			depositOne(fix, sx, sxy, M[i], M[i + mPlane], M[i + 2*mPlane], cj, ck, cl);
+		}
 		const unsigned slot = atomicAdd(&Q.cnt[key], 1u);
 		if(slot >= (unsigned)Q.cap){ atomicOr(flags, ERR_SLOT_OVERFLOW); mKey[i] = SLOT_OVER_KEY; continue; }
 		double *P = Q.S + Q.off + (long)key*Q.cap + slot;
@@ -589,7 +632,7 @@ __global__ void k_mv_pack(const double *__restrict__ M, long mPlane, const unsig
 }
 // immigrants (records, shifted into the local frame as k_import does) straight into their cells
 __global__ void k_import_cells(SlotPar Q, long n, ImportPar ip, const double *__restrict__ in, CellSpace C,
-		double *__restrict__ M, long mPlane, unsigned *__restrict__ mKey, unsigned *mCount, int *flags){
+		double *__restrict__ M, long mPlane, unsigned *__restrict__ mKey, unsigned *mCount, int *flags, long long *__restrict__ fix, long sx, long sxy){
 	long i = blockIdx.x*(long)blockDim.x + threadIdx.x, st = (long)gridDim.x*blockDim.x;
 	for(; i < n; i += st){
 		long r = i; int ne = 0;
@@ -606,6 +649,7 @@ __global__ void k_import_cells(SlotPar Q, long n, ImportPar ip, const double *__
 			j = min(max(j,0),C.nc0-1); k = min(max(k,0),C.nc1-1); l = min(max(l,0),C.nc2-1);
 		}
 		const unsigned key = (unsigned)(j + C.nc0*(k + (long)C.nc1*l));
+		if(fix) depositOne(fix, sx, sxy, v[0], v[1], v[2], j, k, l);
 		const unsigned slot = atomicAdd(&Q.cnt[key], 1u);
 		if(slot >= (unsigned)Q.cap){
 			atomicOr(flags, ERR_SLOT_OVERFLOW);
@@ -699,13 +743,15 @@ __global__ void __launch_bounds__(256, 4) k_distr_slots(SlotPar Q, CellSpace C, 
 			#pragma unroll
 			for(int u = 0; u < 3; u++){
 				if(i0 + lane + 32*u >= e) continue;
-				long long w[8];
-				cornerWeights(x[u]-dj, y[u]-dk, z[u]-dl, w);
-				#pragma unroll
-				for(int q = 0; q < 8; q++) a[q] += w[q];
+				const double xf = x[u]-dj, yf = y[u]-dk, zf = z[u]-dl;
+				const double xc = 1-xf, yc = 1-yf, zc = 1-zf;
+				const double cc = xc*yc, fc = xf*yc, cf = xc*yf, ff = xf*yf;
+				a[0] += fixwRaw(cc*zc); a[1] += fixwRaw(fc*zc); a[2] += fixwRaw(cf*zc); a[3] += fixwRaw(ff*zc);
+				a[4] += fixwRaw(cc*zf); a[5] += fixwRaw(fc*zf); a[6] += fixwRaw(cf*zf); a[7] += fixwRaw(ff*zf);
 			}
 		}
 		long long tot = warpCornerTotal(a);
+		tot -= (long long)((unsigned long long)e*FIXW_BIAS);          // (see k_distr_cells)
 		if((lane & 3) == 0 && tot != 0)
 			atomicAdd((unsigned long long*)&fix[cj + sx*ck + sxy*cl + cornerOffset(sx, sxy)], (unsigned long long)tot);
 	}
@@ -868,7 +914,14 @@ static int g_slotted = -1;              // $PINC_B200_SLOTTED=0 keeps the counti
 static int g_slotHeadroom = 25;         // per cent of the fullest cell, plus g_slotExtra slots, kept free in every cell
 static int g_slotExtra = 16;
 static std::atomic<long> g_slotOverflows{0};   // how often a full cell sent a population back to the contiguous layout (rank threads share it)
-static bool slottedEnabled(){ if(g_slotted < 0) g_slotted = (getenv("PINC_B200_SLOTTED") && atoi(getenv("PINC_B200_SLOTTED")) == 0) ? 0 : 1; return g_slotted != 0; }
+static bool slottedEnabled(){
+	if(g_slotted < 0){
+		g_slotted = (getenv("PINC_B200_SLOTTED") && atoi(getenv("PINC_B200_SLOTTED")) == 0) ? 0 : 1;
+		int h, e;
+		if(getenv("PINC_B200_SLOT_HEADROOM") && sscanf(getenv("PINC_B200_SLOT_HEADROOM"), "%d,%d", &h, &e) == 2 && h >= 0 && e >= 0){ g_slotHeadroom = h; g_slotExtra = e; }
+	}
+	return g_slotted != 0;
+}
 static SlotPar slotPar(const DevPop *dp, int s){ return SlotPar{ dp->slot, dp->slotPlane, dp->slotOff[s], dp->slotCapS[s], dp->d_cnt[s] }; }
 static double *mvBase(const DevPop *dp, int s){ return dp->alt + dp->host->iStart[s]; }         // six planes of stride dp->cap
 static unsigned *mvKeys(const DevPop *dp, int s){ return dp->d_keys + dp->host->iStart[s]; }
@@ -888,6 +941,7 @@ static bool takeSlotOverflow(Ctx *c, const char *where){
 // path leaves, so every other entry point works unchanged
 void popLeaveSlotted(Ctx *c, DevPop *dp){
 	if(!dp->slotted) return;
+	dropPredeposit(dp);           // what pincAccMoveDistr3D1KE deposited from the slots is redone by the next puDistr3D1 (accumulators cleared first)
 	const Population *pop = dp->host;
 	const long nKeys = dp->nCells + 27;
 	for(int s = 0; s < dp->nS; s++){
@@ -942,7 +996,7 @@ static bool enterSlotted(Ctx *c, DevPop *dp, const double *thr6){
 		size_t have = dp->slot ? (size_t)6*dp->slotPlane*sizeof(double) : 0;
 		if((size_t)6*total*sizeof(double) > (freeB + have)/2) return false;        // not worth squeezing the device for
 		if(dp->slot){ PINC_CUDA(cudaFree(dp->slot)); dp->slot = nullptr; dp->slotPlane = 0; }
-		long want = total + total/16;
+		long want = (total + total/16 + 3) & ~3L;
 		if(cudaMalloc(&dp->slot, (size_t)6*want*sizeof(double)) != cudaSuccess){ cudaGetLastError(); return false; }
 		dp->slotPlane = want;
 	}
@@ -971,11 +1025,13 @@ static bool slotRoom(const DevPop *dp){
 }
 // pincAccMove3D1KE on the slots: kick + move + re-binning of every species, one warp per cell
 // mode 0: kick + move + re-binning (pincAccMove3D1KE); 1: kick only (puAcc3D1[KE]); 2: move + re-binning only (puMove)
-static void cellPush(Ctx *c, DevPop *dp, Population *pop, DevGrid *E, int ke, const double *thr6, int mode){
+// rho != nullptr (mode 0 only): the stayers are deposited into rho's accumulators by the push (pincAccMoveDistr3D1KE)
+static void cellPush(Ctx *c, DevPop *dp, Population *pop, DevGrid *E, int ke, const double *thr6, int mode, DevGrid *rho = nullptr){
 	const long sx3 = E ? 3L*E->size[0] : 0, sxy3 = E ? sx3*E->size[1] : 0;
 	if(E && (dp->nc[0] > E->size[0]-1 || dp->nc[1] > E->size[1]-1 || dp->nc[2] > E->size[2]-1)) fatal("accelerator: E is smaller than the migration thresholds allow");
 	const Thr thr = thrOf(thr6); const CellSpace C = cellsOf(dp);
 	if(mode == 2) ke = 0;
+	if(rho && mode != 0) fatal("cellPush: the fused deposition belongs to the fused push");
 	const int maxBlocks = cellBlocks(c, dp->nCells);
 	double *partial = ke ? partialBuffer(c, (long)maxBlocks*dp->nS) : nullptr;
 	if(mode != 1) PINC_CUDA(cudaMemsetAsync(dp->d_mvCount, 0, MV_WORDS*sizeof(unsigned), c->stream));
@@ -987,10 +1043,12 @@ static void cellPush(Ctx *c, DevPop *dp, Population *pop, DevGrid *E, int ke, co
 		const long mCap = pop->iStart[s+1] - pop->iStart[s];
 		int blocks = (int)std::min<long>(maxBlocks, slotWarpsFor(pop, s)/8);
 		if(n > 0){
-#define CELL_LAUNCH(KEE,MODE,CLS,BYTES) PINC_LAUNCH(c, CLS, (BYTES)*n, (k_cell_push<KEE,MODE><<<blocks,256,0,c->stream>>>(slotPar(dp,s), E ? E->d : nullptr, sx3, sxy3, C, thr, part, mvBase(dp,s), dp->cap, mvKeys(dp,s), dp->d_mvCount + MV_COUNT + s, (unsigned)mCap, c->d_flags)))
-			if(mode == 0){ if(ke) CELL_LAUNCH(1,0,K_PUSH,96.0); else CELL_LAUNCH(0,0,K_PUSH,96.0); }
-			else if(mode == 1){ if(ke) CELL_LAUNCH(1,1,K_PUSH,72.0); else CELL_LAUNCH(0,1,K_PUSH,72.0); }
-			else CELL_LAUNCH(0,2,K_MOVE,72.0);
+#define CELL_LAUNCH(KEE,MODE,DEP,CLS,BYTES) PINC_LAUNCH(c, CLS, (BYTES)*n, (k_cell_push<KEE,MODE,DEP><<<blocks,256,0,c->stream>>>(slotPar(dp,s), E ? E->d : nullptr, sx3, sxy3, C, thr, part, mvBase(dp,s), dp->cap, mvKeys(dp,s), dp->d_mvCount + MV_COUNT + s, (unsigned)mCap, c->d_flags, \
+				rho ? rho->d_fixS[s] : nullptr, rho ? (long)rho->size[0] : 0, rho ? (long)rho->size[0]*rho->size[1] : 0)))
+			if(mode == 0 && rho){ if(ke) CELL_LAUNCH(1,0,1,K_PUSH,120.0); else CELL_LAUNCH(0,0,1,K_PUSH,120.0); }
+			else if(mode == 0){ if(ke) CELL_LAUNCH(1,0,0,K_PUSH,96.0); else CELL_LAUNCH(0,0,0,K_PUSH,96.0); }
+			else if(mode == 1){ if(ke) CELL_LAUNCH(1,1,0,K_PUSH,72.0); else CELL_LAUNCH(0,1,0,K_PUSH,72.0); }
+			else CELL_LAUNCH(0,2,0,K_MOVE,72.0);
 #undef CELL_LAUNCH
 		}
 		if(ke) PINC_LAUNCH(c, K_REDUCE, 8.0*blocks, (k_final_sum_p<<<1,256,0,c->stream>>>(part, n > 0 ? blocks : 0, c->d_scal + 16 + s)));
@@ -1015,8 +1073,9 @@ static void cellExtract(Ctx *c, DevPop *dp, Population *pop, MpiInfo *m){
 	const CellSpace C = cellsOf(dp);
 	for(int s = 0; s < nS; s++){
 		const long n = pop->iStop[s] - pop->iStart[s];
+		DevGrid *rho = dp->predep;          // pincAccMoveDistr3D1KE deposited the stayers: the local movers follow here
 		if(n > 0) PINC_LAUNCH(c, K_EXTRACT, 100.0*(n/16), (k_mv_insert<<<pGrid(c, n/8 + 1024),256,0,c->stream>>>(slotPar(dp,s), mvBase(dp,s), dp->cap, mvKeys(dp,s), dp->d_mvCount + MV_COUNT + s,
-			C, dp->d_mvCount + MV_EMHIST + 27*s, c->d_flags)));
+			C, dp->d_mvCount + MV_EMHIST + 27*s, c->d_flags, rho ? rho->d_fixS[s] : nullptr, rho ? (long)rho->size[0] : 0, rho ? (long)rho->size[0]*rho->size[1] : 0)));
 	}
 	PINC_CUDA(cudaMemcpyAsync(c->h_long, dp->d_mvCount, MV_SCRATCH*sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
 	const bool over = takeSlotOverflow(c, "puExtractEmigrants3D");          // (synchronises)
@@ -1051,10 +1110,24 @@ static void accelerate(Ctx *c, Population *pop, Grid *Egrid, int kind, int ke, c
 	if(E->nv != 3) fatal("accelerator needs a 3-vector field grid");
 	{	// slotted mode: the steady state of pincAccMove3D1KE (leapfrog kick + move + re-binning, no fused deposition)
 		// (with `fuse` also the move and the re-binning; without, the kick alone - the reference's call order)
-		const bool eligible = kind == ACC_LEAP && !rhoGrid && slottedEnabled() && (fuse || dp->haveThr);
+		// (with rho - pincAccMoveDistr3D1KE - the stayers are deposited by the push as well)
+		bool eligible = kind == ACC_LEAP && (!rhoGrid || fuse) && slottedEnabled() && (fuse || dp->haveThr);
 		if(dp->slotted && (!eligible || dp->mvPending || dp->extracted || !slotRoom(dp))) popLeaveSlotted(c, dp);
 		if(eligible && !dp->slotted && slotRoom(dp)) enterSlotted(c, dp, fuse ? fuse->thresholds : dp->thr6);
-		if(dp->slotted){ double t[6]; for(int d = 0; d < 6; d++) t[d] = fuse ? fuse->thresholds[d] : dp->thr6[d]; cellPush(c, dp, pop, E, ke, t, fuse ? 0 : 1); return; }
+		if(dp->slotted){
+			double t[6]; for(int d = 0; d < 6; d++) t[d] = fuse ? fuse->thresholds[d] : dp->thr6[d];
+			DevGrid *rho = nullptr;
+			dropPredeposit(dp);
+			if(rhoGrid){
+				rho = devGrid(c, rhoGrid);
+				if(rho->nv != 1) fatal("pincAccMoveDistr3D1KE needs a scalar grid for rho");
+				if(dp->nc[0] > rho->size[0]-1 || dp->nc[1] > rho->size[1]-1 || dp->nc[2] > rho->size[2]-1) fatal("pincAccMoveDistr3D1KE: rho is smaller than the migration thresholds allow");
+				ensureFix(c, rho, dp->nS);
+			}
+			cellPush(c, dp, pop, E, ke, t, fuse ? 0 : 1, rho);
+			dp->predep = rho;
+			return;
+		}
 	}
 	long sx3 = 3L*E->size[0], sxy3 = sx3*E->size[1];
 	Thr thr{}; CellSpace C{1,1,1,1};
@@ -1358,8 +1431,9 @@ void puMigrate(Population *pop, MpiInfo *mpiInfo, Grid *grid){
 		}
 		if(pop->iStop[s] + tot > pop->iStart[s+1])
 			fatal("puMigrate: species %d overflows its allocation (%ld + %ld immigrants > %ld)", s, pop->iStop[s]-pop->iStart[s], tot, pop->iStart[s+1]-pop->iStart[s]);
+		DevGrid *pre = dp->slotted ? dp->predep : nullptr;          // pincAccMoveDistr3D1KE: the immigrants are deposited as they arrive
 		if(tot > 0 && dp->slotted) PINC_LAUNCH(c, K_IMPORT, 96.0*tot, (k_import_cells<<<pGrid(c,tot),256,0,c->stream>>>(slotPar(dp,s), tot, ip, dp->d_immig, cellsOf(dp),
-			mvBase(dp,s), dp->cap, mvKeys(dp,s), dp->d_mvCount + MV_COUNT + s, c->d_flags)));
+			mvBase(dp,s), dp->cap, mvKeys(dp,s), dp->d_mvCount + MV_COUNT + s, c->d_flags, pre ? pre->d_fixS[s] : nullptr, pre ? (long)pre->size[0] : 0, pre ? (long)pre->size[0]*pre->size[1] : 0)));
 		else if(tot > 0) PINC_LAUNCH(c, K_IMPORT, 96.0*tot, (k_import<<<pGrid(c,tot),256,0,c->stream>>>(dp->base, dp->cap, pop->iStop[s], tot, ip, dp->d_immig)));
 		pop->iStop[s] += tot;
 	}
@@ -1373,15 +1447,17 @@ void puDistr3D1(const Population *pop, Grid *rhoGrid){
 	if(rho->nv != 1) fatal("puDistr3D1 needs a scalar grid");
 	if(dp->slotted && (dp->mvPending || dp->nc[0] > rho->size[0]-1 || dp->nc[1] > rho->size[1]-1 || dp->nc[2] > rho->size[2]-1)) popLeaveSlotted(c, dp);
 	if(dp->slotted){
-		dropPredeposit(dp);
+		const bool pre = dp->predep == rho;           // stayers by the push, movers by k_mv_insert, immigrants by k_import_cells: only the conversion is left
+		if(!pre) dropPredeposit(dp);
 		ensureFix(c, rho, dp->nS);
 		gridZero(c, rho);
 		const long sx = rho->size[0], sxy = sx*rho->size[1];
 		for(int s = 0; s < dp->nS; s++){
 			const long n = pop->iStop[s] - pop->iStart[s];
-			if(n > 0) PINC_LAUNCH(c, K_DEPOSIT, 24.0*n, (k_distr_slots<<<cellBlocks(c,dp->nCells),256,0,c->stream>>>(slotPar(dp,s), cellsOf(dp), sx, sxy, rho->d_fixS[s])));
+			if(n > 0 && !pre) PINC_LAUNCH(c, K_DEPOSIT, 24.0*n, (k_distr_slots<<<cellBlocks(c,dp->nCells),256,0,c->stream>>>(slotPar(dp,s), cellsOf(dp), sx, sxy, rho->d_fixS[s])));
 			PINC_LAUNCH(c, K_DEPOSIT, 32.0*rho->n, (k_distr_finalize<<<gridFor(rho->n,256,c->numSMs*8),256,0,c->stream>>>(rho->d, rho->d_fixS[s], rho->n, 1.0/pop->charge[s], pop->charge[s], c->d_flags)));
 		}
+		dp->predep = nullptr;
 		return;
 	}
 	bool pre = dp->predep == rho;                 // the stayers were deposited by pincAccMoveDistr3D1KE

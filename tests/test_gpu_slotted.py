@@ -74,10 +74,12 @@ def run_against_oracle(L, cfg, steps, expect_slotted=True, per_rank=None, fused=
         W.close()
 
 
-@pytest.mark.parametrize("sub,fused", [("1,1,1", "nodeposit"), ("1,2,2", "nodeposit"), ("1,1,1", False), ("2,1,2", False)])
+@pytest.mark.parametrize("sub,fused", [("1,1,1", "nodeposit"), ("1,2,2", "nodeposit"), ("1,1,1", False), ("2,1,2", False),
+                                       ("1,1,1", True), ("1,2,2", True), ("2,1,2", True)])
 def test_slotted_steps_match_oracle(gpu_lib, sub, fused):
     """fused="nodeposit": pincAccMove3D1KE (kick + move + re-binning in one pass); False: the reference's call order, puAcc3D1KE
-    and puMove as separate slotted passes."""
+    and puMove as separate slotted passes; True: pincAccMoveDistr3D1KE (the push also deposits the particles that keep their
+    cell, movers and immigrants are deposited where they arrive, puDistr3D1 only converts the accumulators)."""
     L = gpu_lib
     L.pincSetSlotted(1, 25, 16)
     text, cfg = warm(sub)
@@ -94,7 +96,8 @@ def test_slotted_steps_match_oracle(gpu_lib, sub, fused):
             assert np.array_equal(a[r][n], b[r][n]), (r, n)
 
 
-def test_slot_overflow_falls_back_to_the_sort(gpu_lib):
+@pytest.mark.parametrize("fused", ["nodeposit", True])
+def test_slot_overflow_falls_back_to_the_sort(gpu_lib, fused):
     L = gpu_lib
     L.pincSetSlotted(1, 0, 0)                                   # no head room beyond the fullest cell's count
     try:
@@ -105,7 +108,7 @@ def test_slot_overflow_falls_back_to_the_sort(gpu_lib):
             for s, (pos, vel) in enumerate(per_rank[r]):
                 vel[:, 0] = -0.3 * np.sign(pos[:, 0] - (1 + cfg.trueSize[0] / 2))
         before = L.pincSlottedOverflows()
-        run_against_oracle(L, cfg, 6, expect_slotted=False, per_rank=per_rank)
+        run_against_oracle(L, cfg, 6, expect_slotted=False, per_rank=per_rank, fused=fused)
         assert L.pincSlottedOverflows() > before
     finally:
         L.pincSetSlotted(1, 25, 16)
