@@ -159,17 +159,14 @@ template<int N> static __device__ __noinline__ void sRestrict(const double *P, c
 }
 // trilinear prolongation in the nesting of the reference's three passes (z, then y, then x; multigrid.c:1127-1238);
 // H = coarse size, (x,y,z) = 0-based fine node
-template<int H> static __device__ __forceinline__ double sProlZ(const double *C, int X, int Y, int z){
-	if(!(z & 1)) return C[sIdx<H>(X, Y, z/2)];
-	return 0.5*(C[sIdx<H>(X, Y, (z-1)/2)] + C[sIdx<H>(X, Y, (z+1)/2)]);
-}
-template<int H> static __device__ __forceinline__ double sProlY(const double *C, int X, int y, int z){
-	if(!(y & 1)) return sProlZ<H>(C, X, y/2, z);
-	return 0.5*(sProlZ<H>(C, X, (y-1)/2, z) + sProlZ<H>(C, X, (y+1)/2, z));
-}
+// (branch-free: an even fine node's two coarse neighbours are the same node and 0.5*(a + a) == a exactly, see prolPoint)
 template<int H> static __device__ __forceinline__ double sProl(const double *C, int x, int y, int z){
-	if(!(x & 1)) return sProlY<H>(C, x/2, y, z);
-	return 0.5*(sProlY<H>(C, (x-1)/2, y, z) + sProlY<H>(C, (x+1)/2, y, z));
+	const int xa = x >> 1, xb = (x+1) >> 1, ya = y >> 1, yb = (y+1) >> 1, za = z >> 1, zb = (z+1) >> 1;
+	const double v000 = C[sIdx<H>(xa,ya,za)], v001 = C[sIdx<H>(xa,ya,zb)], v010 = C[sIdx<H>(xa,yb,za)], v011 = C[sIdx<H>(xa,yb,zb)];
+	const double v100 = C[sIdx<H>(xb,ya,za)], v101 = C[sIdx<H>(xb,ya,zb)], v110 = C[sIdx<H>(xb,yb,za)], v111 = C[sIdx<H>(xb,yb,zb)];
+	const double pa = 0.5*(0.5*(v000 + v001) + 0.5*(v010 + v011));
+	const double pb = 0.5*(0.5*(v100 + v101) + 0.5*(v110 + v111));
+	return 0.5*(pa + pb);
 }
 // res := P(phi coarse); phi += res; returns the mean of the new phi (the gBnd that follows is applied by the smoother)
 template<int N> static __device__ __noinline__ double sProlongAdd(double *P, const double *Pc, double *resG, int s0, int s1, CK &K){

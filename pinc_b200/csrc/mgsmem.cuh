@@ -388,17 +388,16 @@ template<bool SMALL, bool EXACT> __device__ __noinline__ void cBottom(const CPla
 	if(EXACT || P.nCoarse <= 0) cNeutralizePhi<SMALL>(L, K);      // batched mode: cGS just ended with this gBnd
 }
 // trilinear prolongation in the nesting of the reference's three passes (z, then y, then x; multigrid.c:1127-1238)
-static __device__ __forceinline__ double cProlZ(const CLvl &C, const CK &K, int J, int Kk, int l){
-	if(l & 1) return rdPhi(C, K, J, Kk, (l+1)/2);
-	return 0.5*(rdPhi(C, K, J, Kk, l/2) + rdPhi(C, K, J, Kk, upW(l/2, C.nz)));
-}
-static __device__ __forceinline__ double cProlY(const CLvl &C, const CK &K, int J, int k, int l){
-	if(k & 1) return cProlZ(C, K, J, (k+1)/2, l);
-	return 0.5*(cProlZ(C, K, J, k/2, l) + cProlZ(C, K, J, upW(k/2, C.ny), l));
-}
+// (branch-free: for an odd fine index both coarse neighbours are the same node and 0.5*(a + a) == a exactly, see prolPoint)
+static __device__ __forceinline__ void cProlPair(int i, int n, int &a, int &b){ a = (i+1) >> 1; b = (i+2) >> 1; if(b > n) b = 1; }
 static __device__ __forceinline__ double cProl(const CLvl &C, const CK &K, int j, int k, int l){
-	if(j & 1) return cProlY(C, K, (j+1)/2, k, l);
-	return 0.5*(cProlY(C, K, j/2, k, l) + cProlY(C, K, upW(j/2, C.nx), k, l));
+	int Ja, Jb, Ka, Kb, La, Lb;
+	cProlPair(j, C.nx, Ja, Jb); cProlPair(k, C.ny, Ka, Kb); cProlPair(l, C.nz, La, Lb);
+	const double v000 = rdPhi(C, K, Ja, Ka, La), v001 = rdPhi(C, K, Ja, Ka, Lb), v010 = rdPhi(C, K, Ja, Kb, La), v011 = rdPhi(C, K, Ja, Kb, Lb);
+	const double v100 = rdPhi(C, K, Jb, Ka, La), v101 = rdPhi(C, K, Jb, Ka, Lb), v110 = rdPhi(C, K, Jb, Kb, La), v111 = rdPhi(C, K, Jb, Kb, Lb);
+	const double ya = 0.5*(0.5*(v000 + v001) + 0.5*(v010 + v011));
+	const double yb = 0.5*(0.5*(v100 + v101) + 0.5*(v110 + v111));
+	return 0.5*(ya + yb);
 }
 // post-smoothing leg of level q: res(q) := P(phi(q+1)); phi(q) += res(q); gBnd; mgGS3D; gBnd
 template<bool SMALL, bool EXACT> static __device__ __noinline__ void cUp(const CPlan &P, int q, CK &K){

@@ -71,20 +71,20 @@ template<bool WRAP> __device__ __forceinline__ double restrictPoint(const double
 }
 // Trilinear prolongation of the coarse grid to fine true node (j,k,l), in the nesting the reference's three
 // passes produce (z first, then y, then x; src/multigrid.c:1127-1238).  Periodic wrap on the coarse index.
-__device__ __forceinline__ double prolZ(const double *c, int J, int K, int l, int c0, int c1, int c2){
-	if(l & 1) return ldg2(c + ix(J,K,(l+1)/2,c0,c1));
-	int La = l/2, Lb = (l/2+1 == c2-1) ? 1 : l/2+1;
-	return 0.5*(ldg2(c + ix(J,K,La,c0,c1)) + ldg2(c + ix(J,K,Lb,c0,c1)));
-}
-__device__ __forceinline__ double prolY(const double *c, int J, int k, int l, int c0, int c1, int c2){
-	if(k & 1) return prolZ(c, J, (k+1)/2, l, c0, c1, c2);
-	int Ka = k/2, Kb = (k/2+1 == c1-1) ? 1 : k/2+1;
-	return 0.5*(prolZ(c, J, Ka, l, c0, c1, c2) + prolZ(c, J, Kb, l, c0, c1, c2));
-}
+// Branch-free: for an odd fine index both coarse neighbours are the same node, and 0.5*(a + a) == a exactly, so every node
+// takes the eight-load form - no divergence between the eight parity classes of a warp's nodes, and the eight loads (L2 or
+// shared memory) are in flight together instead of one dependent load per taken branch.
+__device__ __forceinline__ void prolPair(int i, int cN, int &a, int &b){ a = (i+1) >> 1; b = (i+2) >> 1; if(b == cN-1) b = 1; }
 __device__ __forceinline__ double prolPoint(const double *c, int j, int k, int l, int c0, int c1, int c2){
-	if(j & 1) return prolY(c, (j+1)/2, k, l, c0, c1, c2);
-	int Ja = j/2, Jb = (j/2+1 == c0-1) ? 1 : j/2+1;
-	return 0.5*(prolY(c, Ja, k, l, c0, c1, c2) + prolY(c, Jb, k, l, c0, c1, c2));
+	int Ja, Jb, Ka, Kb, La, Lb;
+	prolPair(j, c0, Ja, Jb); prolPair(k, c1, Ka, Kb); prolPair(l, c2, La, Lb);
+	const double v000 = ldg2(c + ix(Ja,Ka,La,c0,c1)), v001 = ldg2(c + ix(Ja,Ka,Lb,c0,c1));
+	const double v010 = ldg2(c + ix(Ja,Kb,La,c0,c1)), v011 = ldg2(c + ix(Ja,Kb,Lb,c0,c1));
+	const double v100 = ldg2(c + ix(Jb,Ka,La,c0,c1)), v101 = ldg2(c + ix(Jb,Ka,Lb,c0,c1));
+	const double v110 = ldg2(c + ix(Jb,Kb,La,c0,c1)), v111 = ldg2(c + ix(Jb,Kb,Lb,c0,c1));
+	const double ya = 0.5*(0.5*(v000 + v001) + 0.5*(v010 + v011));       // prolY at Ja: 0.5*(prolZ(Ka) + prolZ(Kb))
+	const double yb = 0.5*(0.5*(v100 + v101) + 0.5*(v110 + v111));
+	return 0.5*(ya + yb);
 }
 
 // (levels have fewer than 2^31 nodes: 32-bit divisions, ~10x cheaper than 64-bit ones)
