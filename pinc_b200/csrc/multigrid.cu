@@ -986,39 +986,46 @@ template<bool X> __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, i
 		// halo node i (0 <= i < nHalo) of colour c: mailbox slot and index into the block array
 		auto haloNode = [&](int i, int c, int &slot, int &hidx){
 			int f, w, j, k, l;
+			// (a face's slots are colour-separated: colour c's nodes of a row sit next to each other, so that the 16-byte stores
+			// and polls of consecutive threads are consecutive in memory - half the L2 sectors of the interleaved layout)
 			if(i < nA){
 				f = i >= nA/2; w = i - f*(nA/2);
 				int uu; dHy.divmod(w, l, uu); l += 1; j = f ? bx+1 : 0;
 				k = 2*uu + 1; k += ((j + k + l) & 1) != c;
-				slot = fb[f] + (k-1) + by*(l-1);
+				slot = fb[f] + c*(nA/2) + uu + (by/2)*(l-1);
 			} else if(i < nA + nB){
 				w = i - nA; f = w >= nB/2; w -= f*(nB/2);
 				int uu; dHx.divmod(w, l, uu); l += 1; k = f ? by+1 : 0;
 				j = 2*uu + 1; j += ((j + k + l) & 1) != c;
-				slot = fb[2+f] + (j-1) + bx*(l-1);
+				slot = fb[2+f] + c*(nB/2) + uu + (bx/2)*(l-1);
 			} else {
 				w = i - nA - nB; f = w >= nC/2; w -= f*(nC/2);
 				int uu; dHx.divmod(w, k, uu); k += 1; l = f ? bz+1 : 0;
 				j = 2*uu + 1; j += ((j + k + l) & 1) != c;
-				slot = fb[4+f] + (j-1) + bx*(k-1);
+				slot = fb[4+f] + c*(nC/2) + uu + (bx/2)*(k-1);
 			}
 			hidx = j + ex*(k + ey*l);
 		};
+		// slot of a boundary node inside the face it is sent across (see haloNode): colour half, then (u/2, v)
+		auto slotA = [&](int c, int k, int l){ return (unsigned)(c*(nA/2) + ((k-1) >> 1) + (by/2)*(l-1)); };
+		auto slotB = [&](int c, int j, int l){ return (unsigned)(c*(nB/2) + ((j-1) >> 1) + (bx/2)*(l-1)); };
+		auto slotC = [&](int c, int j, int k){ return (unsigned)(c*(nC/2) + ((j-1) >> 1) + (bx/2)*(k-1)); };
 		auto sendNode = [&](int j, int k, int l, double v, unsigned stag){
+			const int c = (j + k + l) & 1;
 			if constexpr(X){
-				if(j == 1)  llStoreSys(xBase[0] + out[0] + (k-1) + by*(l-1), v, stag);
-				if(j == bx) llStoreSys(xBase[1] + out[1] + (k-1) + by*(l-1), v, stag);
-				if(k == 1)  llStoreSys(xBase[2] + out[2] + (j-1) + bx*(l-1), v, stag);
-				if(k == by) llStoreSys(xBase[3] + out[3] + (j-1) + bx*(l-1), v, stag);
-				if(l == 1)  llStoreSys(xBase[4] + out[4] + (j-1) + bx*(k-1), v, stag);
-				if(l == bz) llStoreSys(xBase[5] + out[5] + (j-1) + bx*(k-1), v, stag);
+				if(j == 1)  llStoreSys(xBase[0] + out[0] + slotA(c,k,l), v, stag);
+				if(j == bx) llStoreSys(xBase[1] + out[1] + slotA(c,k,l), v, stag);
+				if(k == 1)  llStoreSys(xBase[2] + out[2] + slotB(c,j,l), v, stag);
+				if(k == by) llStoreSys(xBase[3] + out[3] + slotB(c,j,l), v, stag);
+				if(l == 1)  llStoreSys(xBase[4] + out[4] + slotC(c,j,k), v, stag);
+				if(l == bz) llStoreSys(xBase[5] + out[5] + slotC(c,j,k), v, stag);
 			} else {
-				if(j == 1)  llStore(B.mail + out[0] + (k-1) + by*(l-1), v, stag);
-				if(j == bx) llStore(B.mail + out[1] + (k-1) + by*(l-1), v, stag);
-				if(k == 1)  llStore(B.mail + out[2] + (j-1) + bx*(l-1), v, stag);
-				if(k == by) llStore(B.mail + out[3] + (j-1) + bx*(l-1), v, stag);
-				if(l == 1)  llStore(B.mail + out[4] + (j-1) + bx*(k-1), v, stag);
-				if(l == bz) llStore(B.mail + out[5] + (j-1) + bx*(k-1), v, stag);
+				if(j == 1)  llStore(B.mail + out[0] + slotA(c,k,l), v, stag);
+				if(j == bx) llStore(B.mail + out[1] + slotA(c,k,l), v, stag);
+				if(k == 1)  llStore(B.mail + out[2] + slotB(c,j,l), v, stag);
+				if(k == by) llStore(B.mail + out[3] + slotB(c,j,l), v, stag);
+				if(l == 1)  llStore(B.mail + out[4] + slotC(c,j,k), v, stag);
+				if(l == bz) llStore(B.mail + out[5] + slotC(c,j,k), v, stag);
 			}
 		};
 		if(fast){
@@ -1044,12 +1051,12 @@ template<bool X> __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, i
 						// face of that dimension takes a slot of its own
 						unsigned t[6]; int nt = 0;
 						constexpr unsigned FS = X ? (1u << LL_FACE_SHIFT) : 0u;       // X: the face rides in the top bits
-						if(j == 1)  t[nt++] = out[0] + (k-1) + by*(l-1);
-						if(j == bx) t[nt++] = out[1] + (k-1) + by*(l-1) + 1u*FS;
-						if(k == 1)  t[nt++] = out[2] + (j-1) + bx*(l-1) + 2u*FS;
-						if(k == by) t[nt++] = out[3] + (j-1) + bx*(l-1) + 3u*FS;
-						if(l == 1)  t[nt++] = out[4] + (j-1) + bx*(k-1) + 4u*FS;
-						if(l == bz) t[nt++] = out[5] + (j-1) + bx*(k-1) + 5u*FS;
+						if(j == 1)  t[nt++] = out[0] + slotA(c,k,l);
+						if(j == bx) t[nt++] = out[1] + slotA(c,k,l) + 1u*FS;
+						if(k == 1)  t[nt++] = out[2] + slotB(c,j,l) + 2u*FS;
+						if(k == by) t[nt++] = out[3] + slotB(c,j,l) + 3u*FS;
+						if(l == 1)  t[nt++] = out[4] + slotC(c,j,k) + 4u*FS;
+						if(l == bz) t[nt++] = out[5] + slotC(c,j,k) + 5u*FS;
 						if(nt > 0) n.t0 = t[0];
 						if(nt > 1) n.t1 = t[1];
 						if(nt > 2) n.t2 = t[2];
