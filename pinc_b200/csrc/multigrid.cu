@@ -850,9 +850,13 @@ __device__ __forceinline__ double llWait(const uint4 *p, unsigned tag){
 // ---- the inner loop of the block smoother for small blocks: everything a thread needs is in registers ------------
 #define LL_NONE 0xffffffffu
 struct FastNode { int idx; unsigned t0, t1, t2; double rho; };      // idx 0: no node; t*: mailbox slots (from B.mail) it is sent to
-__device__ __forceinline__ double fastVal(const double *Ph, int idx, int ex, int pl, double rho){
+// EX, PL: the block's row and plane strides as compile-time constants (0: the run-time values ex, pl).  With constants the six
+// neighbours are immediate offsets from one address register per node; with run-time strides they are four more registers per
+// node, which ptxas spilled (20 local-memory loads per half-sweep, several of them on the chain poll -> barrier -> update -> send)
+template<int EX, int PL> __device__ __forceinline__ double fastVal(const double *Ph, int idx, int ex, int pl, double rho){
 	const double coeff = 1./6.;
-	double a = Ph[idx+1], b = Ph[idx-1], c = Ph[idx+ex], d = Ph[idx-ex], e = Ph[idx+pl], f = Ph[idx-pl];
+	const int e_ = EX ? EX : ex, p_ = PL ? PL : pl;
+	double a = Ph[idx+1], b = Ph[idx-1], c = Ph[idx+e_], d = Ph[idx-e_], e = Ph[idx+p_], f = Ph[idx-p_];
 	return coeff*(a + b + c + d + e + f + rho);
 }
 // X (hybrid multi-rank solve, distributed level): a slot offset carries the face it crosses in its top three bits, the face's
@@ -870,13 +874,13 @@ template<bool X> __device__ __forceinline__ void fastSend(uint4 *mail, uint4 *co
 		if(n.t2 != LL_NONE) llStore(mail + n.t2, v, stag);
 	}
 }
-template<bool X> __device__ __forceinline__ void fastHalf(double *Ph, int ex, int pl, uint4 *mail, uint4 *const *xBase, const uint4 *pAddr, int pIdx, bool recv, unsigned tagIn,
+template<bool X, int EX, int PL> __device__ __forceinline__ void fastHalf(double *Ph, int ex, int pl, uint4 *mail, uint4 *const *xBase, const uint4 *pAddr, int pIdx, bool recv, unsigned tagIn,
 		const FastNode &a, const FastNode &b, unsigned stag, bool send){
 	if(recv && pAddr) Ph[pIdx] = X ? llWaitSys(pAddr, tagIn) : llWait(pAddr, tagIn);
 	__syncthreads();
 	double va = 0, vb = 0;
-	if(a.idx) va = fastVal(Ph, a.idx, ex, pl, a.rho);
-	if(b.idx) vb = fastVal(Ph, b.idx, ex, pl, b.rho);
+	if(a.idx) va = fastVal<EX,PL>(Ph, a.idx, ex, pl, a.rho);
+	if(b.idx) vb = fastVal<EX,PL>(Ph, b.idx, ex, pl, b.rho);
 	if(a.idx){ Ph[a.idx] = va; if(send) fastSend<X>(mail, xBase, a, va, stag); }
 	if(b.idx){ Ph[b.idx] = vb; if(send) fastSend<X>(mail, xBase, b, vb, stag); }
 }
@@ -884,7 +888,7 @@ template<bool X> __device__ __forceinline__ void fastHalf(double *Ph, int ex, in
 // colour 1 (h even) or 0 (h odd) and first receives the other colour's face nodes of half-sweep h-1.
 // X: the halo loaded from this rank's memory is not the neighbour rank's data, so the call starts with an exchange of the
 // colour-0 boundary nodes (tag seq+1) and the half-sweeps use tags seq+2 .. (the caller advances seq by 2*nCycles + 2).
-template<bool X> __device__ __noinline__ void bSmoothFast(double *Ph, int ex, int pl, uint4 *mail, uint4 *const *xBase, const uint4 *p0Addr, int p0Idx, const uint4 *p1Addr, int p1Idx,
+template<bool X, int EX, int PL> __device__ __noinline__ void bSmoothFast(double *Ph, int ex, int pl, uint4 *mail, uint4 *const *xBase, const uint4 *p0Addr, int p0Idx, const uint4 *p1Addr, int p1Idx,
 		FastNode a0, FastNode b0, FastNode a1, FastNode b1, int nCycles, unsigned seq, long long *pf, long long tEnter){
 	long long tW = 0;
 	if(pf){ pf[2*9] += clock64() - tEnter; pf[2*9+1] += 1; tW = clock64(); }
@@ -895,8 +899,8 @@ template<bool X> __device__ __noinline__ void bSmoothFast(double *Ph, int ex, in
 	}
 	for(int h2 = 0; h2 < nCycles; h2++){
 		const unsigned t = seq + 2u*(unsigned)h2;
-		fastHalf<X>(Ph, ex, pl, mail, xBase, p0Addr, p0Idx, X || h2 > 0, t, a1, b1, t + 1u, true);
-		fastHalf<X>(Ph, ex, pl, mail, xBase, p1Addr, p1Idx, true, t + 1u, a0, b0, t + 2u, h2 + 1 < nCycles);
+		fastHalf<X,EX,PL>(Ph, ex, pl, mail, xBase, p0Addr, p0Idx, X || h2 > 0, t, a1, b1, t + 1u, true);
+		fastHalf<X,EX,PL>(Ph, ex, pl, mail, xBase, p1Addr, p1Idx, true, t + 1u, a0, b0, t + 2u, h2 + 1 < nCycles);
 	}
 	if(pf){ pf[2*10] += clock64() - tW; pf[2*10+1] += 2*nCycles; }
 }
@@ -1063,8 +1067,11 @@ template<bool X> __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, i
 					}
 				}
 			}
-			bSmoothFast<X>(Ph, ex, pl, B.mail, xBase, pAddr[0], pIdx[0], pAddr[1], pIdx[1], nd[0][0], nd[0][1], nd[1][0], nd[1][1], nCycles, seq,
-				(S.K->prof && bid == 0 && threadIdx.x == 0) ? S.K->prof : nullptr, tEnter);
+			long long *pf = (S.K->prof && bid == 0 && threadIdx.x == 0) ? S.K->prof : nullptr;
+			// the two block shapes of the benchmark pyramid (64^3 -> 16x16x8, 32^3 -> 8x8x4) with their strides as constants
+			if(ex == 18 && pl == 324) bSmoothFast<X,18,324>(Ph, ex, pl, B.mail, xBase, pAddr[0], pIdx[0], pAddr[1], pIdx[1], nd[0][0], nd[0][1], nd[1][0], nd[1][1], nCycles, seq, pf, tEnter);
+			else if(ex == 10 && pl == 100) bSmoothFast<X,10,100>(Ph, ex, pl, B.mail, xBase, pAddr[0], pIdx[0], pAddr[1], pIdx[1], nd[0][0], nd[0][1], nd[1][0], nd[1][1], nCycles, seq, pf, tEnter);
+			else bSmoothFast<X,0,0>(Ph, ex, pl, B.mail, xBase, pAddr[0], pIdx[0], pAddr[1], pIdx[1], nd[0][0], nd[0][1], nd[1][0], nd[1][1], nCycles, seq, pf, tEnter);
 		} else {
 		const unsigned seqG = X ? seq + 1u : seq;
 		if constexpr(X){
