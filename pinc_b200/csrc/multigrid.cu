@@ -49,13 +49,15 @@ template<bool WRAP> __device__ __forceinline__ double gsPoint(const double *phi,
 	return coeff*(a + b + c + d + e + f + ldg2(rho + g));
 }
 // res = -6 phi; res += (sum of six neighbours); res += rho  (src/grid.c:318-322, src/multigrid.c:1400)
+// sh: a mean shift that is still pending on every stored value of phi (the block smoother leaves its gBnd to the readers, see
+// bGS): the value the reference would have stored is (stored - sh), formed here before anything else is done with it
 template<bool WRAP> __device__ __forceinline__ double resPoint(const double *phi, const double *rho, int j, int k, int l,
-		int s0, int s1, int s2){
+		int s0, int s1, int s2, double sh = 0.0){
 	long g = ix(j,k,l,s0,s1);
-	double r = -6.*ldg2(phi + g);
-	r += ldg2(phi + ix(upI<WRAP>(j,s0),k,l,s0,s1)) + ldg2(phi + ix(dnI<WRAP>(j,s0),k,l,s0,s1))
-	   + ldg2(phi + ix(j,upI<WRAP>(k,s1),l,s0,s1)) + ldg2(phi + ix(j,dnI<WRAP>(k,s1),l,s0,s1))
-	   + ldg2(phi + ix(j,k,upI<WRAP>(l,s2),s0,s1)) + ldg2(phi + ix(j,k,dnI<WRAP>(l,s2),s0,s1));
+	double r = -6.*(ldg2(phi + g) - sh);
+	r += (ldg2(phi + ix(upI<WRAP>(j,s0),k,l,s0,s1)) - sh) + (ldg2(phi + ix(dnI<WRAP>(j,s0),k,l,s0,s1)) - sh)
+	   + (ldg2(phi + ix(j,upI<WRAP>(k,s1),l,s0,s1)) - sh) + (ldg2(phi + ix(j,dnI<WRAP>(k,s1),l,s0,s1)) - sh)
+	   + (ldg2(phi + ix(j,k,upI<WRAP>(l,s2),s0,s1)) - sh) + (ldg2(phi + ix(j,k,dnI<WRAP>(l,s2),s0,s1)) - sh);
 	r += ldg2(rho + g);
 	return r;
 }
@@ -75,13 +77,13 @@ template<bool WRAP> __device__ __forceinline__ double restrictPoint(const double
 // takes the eight-load form - no divergence between the eight parity classes of a warp's nodes, and the eight loads (L2 or
 // shared memory) are in flight together instead of one dependent load per taken branch.
 __device__ __forceinline__ void prolPair(int i, int cN, int &a, int &b){ a = (i+1) >> 1; b = (i+2) >> 1; if(b == cN-1) b = 1; }
-__device__ __forceinline__ double prolPoint(const double *c, int j, int k, int l, int c0, int c1, int c2){
+__device__ __forceinline__ double prolPoint(const double *c, int j, int k, int l, int c0, int c1, int c2, double sh = 0.0){
 	int Ja, Jb, Ka, Kb, La, Lb;
 	prolPair(j, c0, Ja, Jb); prolPair(k, c1, Ka, Kb); prolPair(l, c2, La, Lb);
-	const double v000 = ldg2(c + ix(Ja,Ka,La,c0,c1)), v001 = ldg2(c + ix(Ja,Ka,Lb,c0,c1));
-	const double v010 = ldg2(c + ix(Ja,Kb,La,c0,c1)), v011 = ldg2(c + ix(Ja,Kb,Lb,c0,c1));
-	const double v100 = ldg2(c + ix(Jb,Ka,La,c0,c1)), v101 = ldg2(c + ix(Jb,Ka,Lb,c0,c1));
-	const double v110 = ldg2(c + ix(Jb,Kb,La,c0,c1)), v111 = ldg2(c + ix(Jb,Kb,Lb,c0,c1));
+	const double v000 = ldg2(c + ix(Ja,Ka,La,c0,c1)) - sh, v001 = ldg2(c + ix(Ja,Ka,Lb,c0,c1)) - sh;       // (sh: see resPoint)
+	const double v010 = ldg2(c + ix(Ja,Kb,La,c0,c1)) - sh, v011 = ldg2(c + ix(Ja,Kb,Lb,c0,c1)) - sh;
+	const double v100 = ldg2(c + ix(Jb,Ka,La,c0,c1)) - sh, v101 = ldg2(c + ix(Jb,Ka,Lb,c0,c1)) - sh;
+	const double v110 = ldg2(c + ix(Jb,Kb,La,c0,c1)) - sh, v111 = ldg2(c + ix(Jb,Kb,Lb,c0,c1)) - sh;
 	const double ya = 0.5*(0.5*(v000 + v001) + 0.5*(v010 + v011));       // prolY at Ja: 0.5*(prolZ(Ka) + prolZ(Kb))
 	const double yb = 0.5*(0.5*(v100 + v101) + 0.5*(v110 + v111));
 	return 0.5*(ya + yb);
@@ -911,7 +913,11 @@ template<bool X, int EX, int PL> __device__ __noinline__ void bSmoothFast(double
 // next half-sweep copies the tagged values it was sent into its halo layer.  A slot is rewritten two half-sweeps later,
 // which needs the value its reader produces in between: the protocol is its own back-pressure.  Same arithmetic per
 // node as fGS, hence the same bits.
-template<bool X> __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, double sIn, Scope &S, unsigned &seq){
+// pendOut (single-rank levels): the batched gBnd is NOT applied to the values written back; the mean goes to *pendOut and every
+// later reader of this level's phi forms (stored - mean) itself (resPoint, prolPoint, the prolongation's add, the next call's sIn,
+// the pass that ends the solve).  The same bits as subtracting here - and the barrier inside the sum publishes the write-back, so
+// the smoother call ends with one grid barrier instead of two.
+template<bool X> __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, int nCycles, double sIn, Scope &S, unsigned &seq, double *pendOut = nullptr){
 	ProfScope ps(*S.K, PS_GS_BIG);
 	__shared__ uint4 *xBase[6];
 	const int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2;
@@ -1130,6 +1136,16 @@ template<bool X> __device__ __noinline__ void bGS(const Lvl &L, const BLvl &B, i
 	}
 	seq += 2u*(unsigned)nCycles + (X ? 2u : 0u);
 	const long long tTail = clock64();
+	if(!X && pendOut){
+		if(act)
+			for(int i = threadIdx.x; i < bx*by*bz; i += blockDim.x){
+				int jl, r, kl, ll; dBx.divmod(i, r, jl); dBy.divmod(r, ll, kl);
+				L.phi[ix(ox+jl+1, oy+kl+1, oz+ll+1, L.s0, L.s1)] = Ph[(jl+1) + ex*((kl+1) + ey*(ll+1))];
+			}
+		*pendOut = S.allSum(bsum)/((double)t0*t1*t2);
+		if(S.K->prof && bid == 0 && threadIdx.x == 0){ S.K->prof[2*12] += clock64() - tTail; S.K->prof[2*12+1] += 1; }
+		return;
+	}
 	// the 2*nCycles gBnd calls, applied once (as fGS does in batched mode), on the way back to global memory
 	double avg = X ? S.allSumX(bsum)/((double)t0*t1*t2*(double)S.X->R) : S.allSum(bsum)/((double)t0*t1*t2);
 	if(act)
@@ -1228,7 +1244,8 @@ __device__ __noinline__ void xHalo(double *v, int s0, int s1, int s2, Scope &S, 
 // X: level q is distributed (hybrid multi-rank solve); its coarse level q+1 is the first replicated one (qDist = q+1)
 // ROWS: the plan has a row-smoothed level (mgrows.cuh); a compile-time switch because the persistent kernel is sensitive to
 // its instruction footprint (the row smoother's code cost the 64^3 solve 7 % while it was part of the default kernel)
-template<bool X = false, bool ROWS = false> __device__ __noinline__ void fDown(const MgPlan &P, int q, Scope &S, unsigned &seq){
+// pend[q]: mean shift still pending on the stored phi of level q (see bGS); X and row-smoothed levels always store final values
+template<bool X = false, bool ROWS = false> __device__ __noinline__ void fDown(const MgPlan &P, int q, Scope &S, unsigned &seq, double *pend){
 	const Lvl &L = P.L[q], &C = P.L[q+1];
 	const bool blk = P.B[q].on && !S.single && P.nPre > 0;
 	if constexpr(X){
@@ -1240,14 +1257,15 @@ template<bool X = false, bool ROWS = false> __device__ __noinline__ void fDown(c
 	if constexpr(ROWS) rows = blk && P.B[q].on == 3;
 	if constexpr(ROWS){ if(rows){ if(P.B[q].bx == 32) rNeutRho<16>(L, P.B[q], S); else rNeutRho<8>(L, P.B[q], S); } }
 	if(!rows){ if(blk && P.B[q].on == 1) bNeutRho<false>(L, P.B[q], S); else fNeutralize(L.rho, L.s0, L.s1, L.s2, S); }
-	if constexpr(ROWS){ if(rows){ if(P.B[q].bx == 32) rGS<16>(L, P.B[q], P.nPre, 0.0, S, seq); else rGS<8>(L, P.B[q], P.nPre, 0.0, S, seq); } }
-	if(!rows){ if(blk) bGS<false>(L, P.B[q], P.nPre, 0.0, S, seq); else fGS(L, P.nPre, 0.0, P.exact, S); }
+	const double sIn = pend[q];            // left by the previous V-cycle's post-smoothing of this level
+	if constexpr(ROWS){ if(rows){ if(P.B[q].bx == 32) rGS<16>(L, P.B[q], P.nPre, sIn, S, seq); else rGS<8>(L, P.B[q], P.nPre, sIn, S, seq); pend[q] = 0.0; } }
+	if(!rows){ if(blk) bGS<false>(L, P.B[q], P.nPre, sIn, S, seq, &pend[q]); else { fGS(L, P.nPre, sIn, P.exact, S); pend[q] = 0.0; } }
 	}
 	{
 		ProfScope psr(*S.K, S.single ? 27 : 29);
 		int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2; long nt = (long)t0*t1*t2;
 		for(long i = S.tid(); i < nt; i += S.nthr()){ int j,k,l; truePoint(i,t0,t1,j,k,l);
-			L.res[ix(j,k,l,L.s0,L.s1)] = resPoint<!X>(L.phi, L.rho, j, k, l, L.s0, L.s1, L.s2); }
+			L.res[ix(j,k,l,L.s0,L.s1)] = resPoint<!X>(L.phi, L.rho, j, k, l, L.s0, L.s1, L.s2, X ? 0.0 : pend[q]); }
 		S.sync();
 	}
 	if constexpr(X){
@@ -1286,21 +1304,23 @@ __device__ __noinline__ void fBottom(const MgPlan &P, Scope &S){
 	if(P.exact || P.nCoarse <= 0) fNeutralize(L.phi, L.s0, L.s1, L.s2, S);      // batched mode: fGS just ended with this gBnd
 }
 // res(q) := P(phi(q+1)); phi(q) += res(q); gBnd; post-smooth; gBnd
-template<bool X = false, bool ROWS = false> __device__ __noinline__ void fUp(const MgPlan &P, int q, Scope &S, unsigned &seq){
+template<bool X = false, bool ROWS = false> __device__ __noinline__ void fUp(const MgPlan &P, int q, Scope &S, unsigned &seq, double *pend){
 	const Lvl &L = P.L[q], &C = P.L[q+1];
 	int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2; long nt = (long)t0*t1*t2;
 	const long long tUp = clock64();
 	double acc = 0;
 	// X: the coarse level is the replicated global one; my fine node (j,k,l) is global node (ox+j, oy+k, oz+l)
 	const int ox = X ? S.X->sub[0]*t0 : 0, oy = X ? S.X->sub[1]*t1 : 0, oz = X ? S.X->sub[2]*t2 : 0;
+	const double sC = pend[q+1], sF = X ? 0.0 : pend[q];      // pending shifts of the coarse level's phi and of this level's
 	for(long i = S.tid(); i < nt; i += S.nthr()){
 		int j,k,l; truePoint(i,t0,t1,j,k,l); long g = ix(j,k,l,L.s0,L.s1);
-		double p = prolPoint(C.phi, ox+j, oy+k, oz+l, C.s0, C.s1, C.s2);
+		double p = prolPoint(C.phi, ox+j, oy+k, oz+l, C.s0, C.s1, C.s2, sC);
 		L.res[g] = p;
-		double v = ldg2(L.phi + g); v += p;
+		double v = ldg2(L.phi + g) - sF; v += p;
 		L.phi[g] = v;
 		acc += v;
 	}
+	if(!X) pend[q] = 0.0;
 	if constexpr(X){
 		double avg = S.allSumX(acc)/((double)nt*(double)S.X->R);
 		bGS<true>(L, P.B[q], P.nPost, avg, S, S.xMail);
@@ -1313,7 +1333,7 @@ template<bool X = false, bool ROWS = false> __device__ __noinline__ void fUp(con
 		rows = P.B[q].on == 3 && !S.single && P.nPost > 0;
 		if(rows){ if(P.B[q].bx == 32) rGS<16>(L, P.B[q], P.nPost, avg, S, seq); else rGS<8>(L, P.B[q], P.nPost, avg, S, seq); }
 	}
-	if(!rows){ if(P.B[q].on && !S.single && P.nPost > 0) bGS<false>(L, P.B[q], P.nPost, avg, S, seq); else fGS(L, P.nPost, avg, P.exact, S); }
+	if(!rows){ if(P.B[q].on && !S.single && P.nPost > 0) bGS<false>(L, P.B[q], P.nPost, avg, S, seq, &pend[q]); else fGS(L, P.nPost, avg, P.exact, S); }
 	if(P.exact || P.nPost <= 0) fNeutralize(L.phi, L.s0, L.s1, L.s2, S);
 }
 __device__ __noinline__ void fGhosts(double *v, int s0, int s1, int s2, Scope &S){
@@ -1423,6 +1443,8 @@ template<bool EXACT, bool DIST, bool ROWS> __global__ void __launch_bounds__(MG_
 	int qs = P.qSmall < 0 ? 0 : P.qSmall;
 	double barRes = 2.;
 	int cycles = 0;
+	double pend[MG_MAXLEV + 1];           // per level: mean shift still pending on the stored phi (bGS); identical in every thread
+	for(int q = 0; q <= MG_MAXLEV; q++) pend[q] = 0.0;
 	unsigned seq = *((volatile unsigned*)P.seqWord);       // rewritten only after the last grid barrier of this launch
 	if(seq > 0xE0000000u){
 		// the 32-bit tags are about to wrap (after ~10^6 time steps): back to the initial state - every slot zero,
@@ -1434,8 +1456,8 @@ template<bool EXACT, bool DIST, bool ROWS> __global__ void __launch_bounds__(MG_
 	}
 	while(barRes > P.tol && cycles < P.maxCycles){
 		for(int q = 0; q <= b && q < qs; q++){
-			if(DIST && q < P.X.qDist) fDown<DIST>(P, q, Sg, seq);
-			else if(q < b) fDown<false,ROWS>(P, q, Sg, seq); else fBottom(P, Sg);
+			if(DIST && q < P.X.qDist) fDown<DIST>(P, q, Sg, seq, pend);
+			else if(q < b) fDown<false,ROWS>(P, q, Sg, seq, pend); else fBottom(P, Sg);
 		}
 		if(qs <= b){
 			if(blockIdx.x == 0){
@@ -1444,14 +1466,14 @@ template<bool EXACT, bool DIST, bool ROWS> __global__ void __launch_bounds__(MG_
 				else if(P.smemSmall){
 					smallSection<EXACT>(P, K);
 				} else {
-					for(int q = qs; q < b; q++) fDown(P, q, S1, seq);
+					for(int q = qs; q < b; q++) fDown(P, q, S1, seq, pend);
 					fBottom(P, S1);
-					for(int q = b-1; q >= qs; q--) fUp(P, q, S1, seq);
+					for(int q = b-1; q >= qs; q--) fUp(P, q, S1, seq, pend);
 				}
 			}
 			Sg.sync();
 		}
-		for(int q = (qs <= b ? qs : b) - 1; q >= 0; q--){ if(DIST && q < P.X.qDist) fUp<DIST>(P, q, Sg, seq); else fUp<false,ROWS>(P, q, Sg, seq); }
+		for(int q = (qs <= b ? qs : b) - 1; q >= 0; q--){ if(DIST && q < P.X.qDist) fUp<DIST>(P, q, Sg, seq, pend); else fUp<false,ROWS>(P, q, Sg, seq, pend); }
 		// mgSolveRaw :1700-1704: residual, square in place, true-grid sum, RMS
 		const Lvl &L = P.L[0];
 		ProfScope psn(K, PS_NORM);
@@ -1460,7 +1482,7 @@ template<bool EXACT, bool DIST, bool ROWS> __global__ void __launch_bounds__(MG_
 		if constexpr(DIST) xHalo(L.phi, L.s0, L.s1, L.s2, Sg);
 		for(long i = Sg.tid(); i < nt; i += Sg.nthr()){
 			int j,k,l; truePoint(i,t0,t1,j,k,l);
-			double r = resPoint<!DIST>(L.phi, L.rho, j, k, l, L.s0, L.s1, L.s2);
+			double r = resPoint<!DIST>(L.phi, L.rho, j, k, l, L.s0, L.s1, L.s2, pend[0]);
 			r = r*r;
 			L.res[ix(j,k,l,L.s0,L.s1)] = r;
 			acc += r;
@@ -1473,6 +1495,17 @@ template<bool EXACT, bool DIST, bool ROWS> __global__ void __launch_bounds__(MG_
 	}
 	if(blockIdx.x == 0 && threadIdx.x == 0){ P.hist[0] = (double)cycles; P.hist[251] = barRes; }
 	const unsigned seqEnd = seq;
+	{	// the shifts that are still pending become part of the stored values: what the arrays hold after the solve is final
+		bool any = false;
+		for(int q = 0; q <= b; q++){
+			if(pend[q] == 0.0) continue;
+			any = true;
+			const Lvl &L = P.L[q];
+			int t0 = L.s0-2, t1 = L.s1-2, t2 = L.s2-2; long nt = (long)t0*t1*t2;
+			for(long i = Sg.tid(); i < nt; i += Sg.nthr()){ int j,k,l; truePoint(i,t0,t1,j,k,l); long g = ix(j,k,l,L.s0,L.s1); L.phi[g] = ldg2(L.phi + g) - pend[q]; }
+		}
+		if(any) Sg.sync();
+	}
 	if(P.smemSmall){
 		if(blockIdx.x == 0)
 			for(int q = P.qSmall; q <= b; q++){
