@@ -1,6 +1,8 @@
 /* pinc_main.c — C host of libpinc_b200: PINC's `regular()` run mode (/root/reference/src/main.c:50-304) on
  * top of the PINC-named entry points of include/pinc_b200.h, in the canonical order of SURVEY 8c (one rho fold
- * and one solve per step; no object calls; HDF5 is absent here, so the per-step diagnostics go to stdout).
+ * and one solve per step; no object calls).  Output: the per-step diagnostics on stdout and, when `files:output` is set, the
+ * reference's HDF5 files (<prefix>rho/phi/E.grid.h5, <prefix>pop.pop.h5, <prefix>history.xy.h5; src/main.c:120-131, 262-266)
+ * through the format-level writer of pinc_h5.c (libhdf5 is not in this image); single rank, see writeGrid below.
  *
  *   pinc_b200 input.ini [section:key=value ...]          (same command line as the reference's `pinc`)
  *
@@ -13,6 +15,7 @@
  * id passed through the file $PINC_B200_ID_FILE. */
 #define _POSIX_C_SOURCE 200809L
 #include "pinc_ini.h"
+#include "pinc_h5.h"
 #include "../include/pinc_b200.h"
 #include <math.h>
 #include <stdio.h>
@@ -32,6 +35,7 @@ static void fail(const char *msg){ fprintf(stderr, "ERROR: %s\n", msg); exit(EXI
 static double nowSec(void){ struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9*t.tv_nsec; }
 
 /* ---- uAlloc + uNormalize (src/units.c:61-252); same operation order as pinc_b200/config.py:normalize ---- */
+static double g_unitLength = 1, g_unitVelocity = 1;          /* units->length, units->velocity (src/units.c:225, 244) */
 static void normalize(Ini *ini){
 	int nD = iniGetInt(ini, "grid:nDims"), nS = iniGetInt(ini, "population:nSpecies");
 	int nSub[3], ts[3];
@@ -70,6 +74,7 @@ static void normalize(Ini *ini){
 	double Q = w[0]*fabs(charge[0]);
 	double M = pow(T*Q, 2)/(VACUUM_PERMITTIVITY*pow(X, nD));
 	double uVel = X/T, uDens = 1.0/pow(X, nD), uE = X*M/(T*T*Q), uB = M/(T*Q);
+	g_unitLength = X; g_unitVelocity = uVel;
 	iniGetDoubles(ini, "population:charge", nS, charge);
 	iniGetDoubles(ini, "population:mass", nS, mass);
 	iniGetDoubles(ini, "population:density", nS, dens);
@@ -161,6 +166,76 @@ static void icMaxwell(const Cfg *c, Population *pop, unsigned long long seed){
 			}
 			pNewLocal(pop, s, pos, vel);
 		}
+	}
+}
+
+/* ---- HDF5 output as src/main.c:120-131, 262-266 writes it (format-level writer, pinc_h5.c) ---------------------------------
+ * openH5File's name rule (src/io.c:566-604): prefix "." -> "./", a prefix that does not end in '/' gets '_' appended. */
+static PH5 *openH5(Ini *ini, const char *fName, const char *sub){
+	const char *prefix = iniRaw(ini, "files:output");
+	char path[1024];
+	size_t n = strlen(prefix);
+	const char *sep = !strcmp(prefix, ".") ? "/" : (n > 0 && prefix[n-1] != '/' ? "_" : "");
+	snprintf(path, sizeof path, "%s%s%s.%s.h5", prefix, sep, fName, sub);
+	PH5 *f = ph5Create(path);
+	if(!f){ fprintf(stderr, "ERROR: Could not open or create '%s'\n", path); exit(EXIT_FAILURE); }
+	return f;
+}
+/* gOpenH5 (src/grid.c:1210-1270): the two attributes; gWriteH5 (:1161): dataset "/n=%.1f" of the TRUE nodes, extents reversed
+ * (z, y, x, component).  One rank writes the whole grid here (the reference writes every rank's hyperslab through MPI-IO). */
+static PH5 *gridOpenH5(Ini *ini, const char *name){
+	PH5 *f = openH5(ini, name, "grid");
+	double denorm = 1.;
+	ph5Attr(f, "Axis denormalization factor", &g_unitLength, 1);
+	ph5Attr(f, "Quantity denormalization factor", &denorm, 1);
+	return f;
+}
+static void gridWriteH5(PH5 *f, Grid *g, double n){
+	pincSyncGridToHost(g);
+	const int nv = g->size[0], *sz = g->size, *ts = g->trueSize, *gl = g->nGhostLayers;
+	unsigned long long dims[4] = { (unsigned long long)ts[3], (unsigned long long)ts[2], (unsigned long long)ts[1], (unsigned long long)nv };
+	char name[64];
+	snprintf(name, sizeof name, "/n=%.1f", n);
+	int d = ph5Dataset(f, name, 4, dims);
+	if(d < 0){ fprintf(stderr, "ERROR: could not create dataset %s\n", name); exit(EXIT_FAILURE); }
+	unsigned long long at = 0;
+	const unsigned long long row = (unsigned long long)ts[1]*nv;          /* one x-row of true nodes with its components is contiguous in memory */
+	for(int l = 0; l < ts[3]; l++) for(int k = 0; k < ts[2]; k++){
+		const double *src = g->val + (long)nv*(gl[1] + (long)sz[1]*((k + gl[2]) + (long)sz[2]*(l + gl[3])));
+		ph5Write(f, d, at, row, src);
+		at += row;
+	}
+}
+/* pOpenH5 / pWriteH5 (src/population.c:497-651): positions in the GLOBAL frame (pToGlobalFrame: + offset), one (N, 3) dataset per
+ * species and step; the reference converts in place and back (quirk Q6), here a copy is converted so the particles keep their bits */
+static PH5 *popOpenH5(Ini *ini, int nS){
+	PH5 *f = openH5(ini, "pop", "pop");
+	char name[64];
+	for(int s = 0; s < nS; s++){
+		snprintf(name, sizeof name, "/pos/specie %i", s); ph5Group(f, name);
+		snprintf(name, sizeof name, "/vel/specie %i", s); ph5Group(f, name);
+	}
+	ph5Attr(f, "Position denormalization factor", &g_unitLength, 1);
+	ph5Attr(f, "Velocity denormalization factor", &g_unitVelocity, 1);
+	return f;
+}
+static void popWriteH5(PH5 *f, Population *pop, const int *offset, double posN, double velN){
+	pincSyncPopToHost(pop);
+	char name[64];
+	for(int s = 0; s < pop->nSpecies; s++){
+		long n = pop->iStop[s] - pop->iStart[s];
+		if(n <= 0){ fprintf(stderr, "WARNING: No particles of specie %i to store in .h5-file\n", s); continue; }
+		unsigned long long dims[2] = { (unsigned long long)n, 3 };
+		double *glob = malloc((size_t)n*3*sizeof *glob);
+		const double *p = pop->pos + 3*pop->iStart[s];
+		for(long i = 0; i < n; i++) for(int d = 0; d < 3; d++) glob[3*i+d] = p[3*i+d] + (double)offset[d];
+		snprintf(name, sizeof name, "/pos/specie %i/n=%.1f", s, posN);
+		int d = ph5Dataset(f, name, 2, dims);
+		if(d >= 0) ph5Write(f, d, 0, (unsigned long long)n*3, glob);
+		free(glob);
+		snprintf(name, sizeof name, "/vel/specie %i/n=%.1f", s, velN);
+		d = ph5Dataset(f, name, 2, dims);
+		if(d >= 0) ph5Write(f, d, 0, (unsigned long long)n*3, pop->vel + 3*pop->iStart[s]);
 	}
 }
 
@@ -272,6 +347,25 @@ int main(int argc, char **argv){
 	if(withKE) puAcc3D1KE(pop, E); else puAcc3D1(pop, E);
 	gMul(E, 2.0);
 
+	/* files: src/main.c:120-131 (opt-in here: only when files:output is given; particles only with files:particles = 1) */
+	const int writeH5 = iniHas(ini, "files:output");
+	const int writePop = writeH5 && iniHas(ini, "files:particles") && iniGetInt(ini, "files:particles");
+	PH5 *h5Rho = NULL, *h5Phi = NULL, *h5E = NULL, *h5Pop = NULL, *h5Hist = NULL;
+	int xyPot[9], xyKin[9];
+	if(writeH5){
+		if(c.size != 1) fail("files:output: the format-level HDF5 writer is single-rank (no MPI-IO); run one rank or leave files:output out");
+		if(writePop) h5Pop = popOpenH5(ini, c.nS);
+		h5Rho = gridOpenH5(ini, "rho"); h5Phi = gridOpenH5(ini, "phi"); h5E = gridOpenH5(ini, "E");
+		h5Hist = openH5(ini, "history", "xy");
+		char name[64];                                      /* pCreateEnergyDatasets (src/population.c:658-676) */
+		xyPot[c.nS] = ph5XYCreate(h5Hist, "/energy/potential/total");
+		xyKin[c.nS] = ph5XYCreate(h5Hist, "/energy/kinetic/total");
+		for(int s = 0; s < c.nS; s++){
+			snprintf(name, sizeof name, "/energy/potential/specie %i", s); xyPot[s] = ph5XYCreate(h5Hist, name);
+			snprintf(name, sizeof name, "/energy/kinetic/specie %i", s); xyKin[s] = ph5XYCreate(h5Hist, name);
+		}
+	}
+
 	long nLocal = 0;
 	for(int s = 0; s < c.nS; s++) nLocal += pop->iStop[s] - pop->iStart[s];
 	if(c.rank == 0) printf("STATUS: %ld particles on rank 0 of %d, grid %dx%dx%d per rank, %d steps%s\n", nLocal, c.size, c.ts[0], c.ts[1], c.ts[2], nSteps, fused ? " (fused particle pass)" : "");
@@ -300,6 +394,17 @@ int main(int argc, char **argv){
 		gPotEnergy(rho, phi, pop);
 		if(report > 0 && n % report == 0 && c.rank == 0)
 			printf("n=%d kinetic=%.17g potential=%.17g particles=%ld\n", n, pop->kinEnergy[c.nS], pop->potEnergy[c.nS], (long)(pop->iStop[0]-pop->iStart[0]));
+		if(writeH5){                                        /* src/main.c:262-266 */
+			gridWriteH5(h5E, E, (double)n); gridWriteH5(h5Rho, rho, (double)n); gridWriteH5(h5Phi, phi, (double)n);
+			if(writePop){
+				if(moved) fail("files:particles with methods:fused: the fused pass leaves the positions one puMove ahead of step n");
+				popWriteH5(h5Pop, pop, c.off, (double)n, (double)n + 0.5);
+			}
+			for(int s = 0; s <= c.nS; s++){                   /* pWriteEnergy (src/population.c:678-700) */
+				ph5XYAppend(h5Hist, xyPot[s], (double)n, pop->potEnergy[s]);
+				ph5XYAppend(h5Hist, xyKin[s], (double)n, pop->kinEnergy[s]);
+			}
+		}
 	}
 	double devMs = pincTimerStopMs();
 	double wall = nowSec() - t0;
@@ -309,6 +414,12 @@ int main(int argc, char **argv){
 		printf("TIMER: Time spent: %.3f s for %d steps (device %.3f ms/step), initial conditions %.2f s\n", wall, nSteps, devMs/nSteps, tIC);
 		printf("{\"particle_steps_per_s\": %.6g, \"ms_per_step\": %.6g, \"particles_rank0\": %ld, \"ranks\": %d, \"vcycles_last_solve\": %d, \"launches\": %ld, \"transport\": \"%s\"}\n",
 			(double)nLocal*c.size*nSteps/(devMs*1e-3), devMs/nSteps, nLocal, c.size, cyc, pincLaunchCount(), pincTransportName());
+	}
+	if(writeH5){
+		int bad = 0;
+		if(h5Pop) bad |= ph5Close(h5Pop);
+		bad |= ph5Close(h5Rho); bad |= ph5Close(h5Phi); bad |= ph5Close(h5E); bad |= ph5Close(h5Hist);
+		if(bad) fail("writing the .h5 files failed");
 	}
 	mgFreeSolver(solver);
 	pincGridFree(E); pincGridFree(rho); pincGridFree(phi);
